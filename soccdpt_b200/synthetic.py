@@ -25,6 +25,8 @@ def write_calib_yaml(path, calib=None):
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     with open(path, "w") as f:
         for k, v in calib.items():
+            if k in ("Camera.width", "Camera.height"):
+                v = int(v)
             f.write(f"{k}: {v}\n")
     return path
 

@@ -1,0 +1,163 @@
+/*
+ * soccdpt_b200 -- C ABI of the B200 (sm_100a) implementation of SOccDPT's inference hot path.
+ *
+ * The reference (AdityaNG/SOccDPT) is pure Python/PyTorch: it has no FFI of its own, so the
+ * entry points below are the operators its Python hot path would bind if it had one.  Each
+ * declaration cites the reference code it replaces (paths under /root/reference/).  The Python
+ * host side (soccdpt_b200/model/*.py) binds them with ctypes (soccdpt_b200/_cabi.py); see
+ * INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the library never
+ *     allocates user-visible memory (callers pass outputs and workspaces);
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t), never synchronises, keeps
+ *     no mutable global state besides the last-error string -> safe under CUDA-graph capture;
+ *   - return value: 0 = ok, negative = error (see SOCCDPT_E_*), text via soccdpt_last_error();
+ *   - activations are NHWC ("token-major") bf16; network inputs / final outputs are fp32.
+ */
+#ifndef SOCCDPT_B200_H
+#define SOCCDPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOCCDPT_ABI_VERSION 1
+
+#define SOCCDPT_OK 0
+#define SOCCDPT_E_INVALID (-1)   /* bad argument / unsupported shape */
+#define SOCCDPT_E_CUDA (-2)      /* a CUDA runtime / driver call failed */
+#define SOCCDPT_E_ARCH (-3)      /* device is not sm_100 */
+
+typedef void *soccdpt_stream_t;  /* cudaStream_t */
+
+int soccdpt_abi_version(void);
+const char *soccdpt_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long soccdpt_launch_count(void);
+int soccdpt_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------ post-processing (A8/A9)
+ * Geometry constants of the reference base class, SOccDPT/model/SOccDPT.py:134-228.  All
+ * values are prepared by the host exactly as the reference prepares them (fp32 casts,
+ * rotation matrices of SOccDPT.py:82-111, occupancy_shape of SOccDPT.py:175-181). */
+typedef struct {
+    float fx, fy, cx, cy;        /* Camera.* of the calib YAML, cast to fp32 */
+    int height, width;           /* camera resolution the maps are resized to */
+    int num_classes;             /* <= 4 (the reference only works for 3) */
+    int grid[3];                 /* occupancy grid size in voxels */
+    float occ_shape[3];          /* grid / scale, metres, fp32 */
+    float pc_scale[3];           /* applied to POINTS 0,1,2 of each frame (SOccDPT.py:351-353) */
+    float pc_shift[3];
+    float rot[27];               /* Ra, Rb, Rc row-major; points are multiplied p @ Ra @ Rb @ Rc */
+} soccdpt_geometry_t;
+
+#define SOCCDPT_OCC_REFERENCE_UNION 0 /* reference semantics: OR over the batch, written to every b */
+#define SOCCDPT_OCC_PER_FRAME 1       /* extension: each frame gets only its own voxels */
+
+/* bytes of scratch (bit-packed voxel mask) the two calls below need */
+size_t soccdpt_voxel_workspace_bytes(const soccdpt_geometry_t *g, int batch, int mode);
+
+/* Replaces SOccDPT.get_semantic_occupancy from the clamp onwards + points_to_occupancy_grid
+ * (SOccDPT/model/SOccDPT.py:288-372, :374-463) for maps ALREADY at camera resolution.
+ *   inv_depth_up (B,H,W) f32 in/out (clamped in place like the reference, :289)
+ *   seg_up       (B,C,H,W) f32 in
+ *   points       (B,H,W,3) f32 out (un-rotated, incl. the three altered points)
+ *   grid         (B,G0,G1,G2,C) f32 out, or NULL for compute_occ=False
+ * Bit-exact against the reference's CPU path. */
+int soccdpt_voxelize_fwd(float *inv_depth_up, const float *seg_up, int batch,
+                         const soccdpt_geometry_t *g, float *points, float *grid, int mode,
+                         void *workspace, size_t workspace_bytes, soccdpt_stream_t stream);
+
+/* Same, fused with the two resizes of SOccDPT.py:270-282 (bicubic align_corners=False for the
+ * inverse depth, legacy nearest for the classes) from network resolution (h,w):
+ *   inv_depth (B,h,w) f32, seg (B,C,h,w) f32  ->  inv_depth_up, seg_up (B,C,H,W), points, grid */
+int soccdpt_postprocess_fwd(const float *inv_depth, const float *seg, int batch, int h, int w,
+                            const soccdpt_geometry_t *g, float *inv_depth_up, float *seg_up,
+                            float *points, float *grid, int mode, void *workspace,
+                            size_t workspace_bytes, soccdpt_stream_t stream);
+
+/* ------------------------------------------------------------------ dense contractions
+ * One implicit-GEMM operator covers every convolution / linear layer of the path:
+ *   scratch.layerN_rn           SOccDPT/model/blocks.py:155-191
+ *   ResidualConvUnit_custom     SOccDPT/model/blocks.py:391-414   (bias, ReLU, residual adds)
+ *   FeatureFusionBlock out_conv SOccDPT/model/blocks.py:472-497   (1x1)
+ *   depth head                  SOccDPT/model/dpt.py:199-219      (incl. the fused 32->1 projection)
+ *   seg head                    SOccDPT/model/SOccDPT.py:660-674  (BN folded, fused 256->3 projection)
+ *   timm qkv/proj/fc1/fc2/reduction linears (K=1x1 over a (1,1,M,K) "image")
+ * y[n,h,w,:] = act( sum_{kh,kw,c} x[n,h+kh-KH/2,w+kw-KW/2,c] * wgt[:,kh,kw,c] + bias ) + res1 + res2
+ * stride 1, zero padding KH/2 / KW/2, fp32 accumulation, bf16 storage. */
+#define SOCCDPT_ACT_NONE 0
+#define SOCCDPT_ACT_RELU 1
+#define SOCCDPT_ACT_GELU 2 /* exact erf GELU (timm Mlp) */
+
+typedef struct {
+    const void *x;        /* bf16 [N,H,W,Cin] */
+    const void *wgt;      /* bf16 [Cout][KH*KW][Cin] */
+    const float *bias;    /* f32 [Cout] or NULL */
+    const void *res1;     /* bf16 [N,H,W,Cout] or NULL, added after the activation */
+    const void *res2;     /* bf16 [N,H,W,Cout] or NULL */
+    void *y;              /* bf16 [N,H,W,Cout] or NULL */
+    void *y_relu;         /* bf16 relu(y), second output for consumers that need both, or NULL */
+    int N, H, W, Cin, Cout, KH, KW;
+    int act;              /* SOCCDPT_ACT_* applied to (acc + bias) */
+    /* optional fused projection epilogue: p = proj_w @ y_row + proj_b (needs Cout <= 256) */
+    const float *proj_w;  /* f32 [proj_n][Cout] or NULL */
+    const float *proj_b;  /* f32 [proj_n] */
+    float *proj_out;      /* f32 [N*H*W][proj_n] */
+    int proj_n;           /* 1..4 */
+    int proj_relu;        /* ReLU on the projection */
+} soccdpt_conv_t;
+
+/* tcgen05 / TMEM / TMA kernel (the product path) */
+int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream);
+/* plain CUDA-core kernel with identical semantics: on-device cross-check used by the tests */
+int soccdpt_conv_ref_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream);
+
+/* ------------------------------------------------------------------ encoder pieces (timm SwinV2 0.6.12)
+ * timm PatchEmbed: conv4x4 s4 + bias + LayerNorm (eps 1e-5); x f32 NCHW -> tokens bf16 [B,H/4*W/4,E] */
+int soccdpt_patch_embed_fwd(const float *x, const float *w, const float *b, const float *ln_w,
+                            const float *ln_b, void *tokens, int batch, int H, int W, int E,
+                            soccdpt_stream_t stream);
+
+/* timm WindowAttention (v2, cosine) incl. window partition / cyclic shift / reverse:
+ *   qkv   bf16 [B, Hs*Ws, 3*C] (q|k|v, each heads x 32), biases already added by the qkv GEMM
+ *   bias  f32 [heads][N][N]  = 16*sigmoid(cpb_mlp(table))[rel_idx]  (input independent, baked at load)
+ *   scale f32 [heads]        = exp(min(logit_scale, ln 100))
+ *   out   bf16 [B, Hs*Ws, C]
+ * window ws x ws (N = ws*ws tokens), shift in {0, ws/2}; the -100 shift mask is generated from
+ * region ids exactly as timm's attn_mask buffer. head_dim must be 32. */
+int soccdpt_window_attention_fwd(const void *qkv, const float *bias, const float *scale, void *out,
+                                 int batch, int Hs, int Ws, int C, int heads, int ws, int shift,
+                                 soccdpt_stream_t stream);
+
+/* y = (res ? res : 0) + LayerNorm(t) over the last dim (eps), bf16 in/out, fp32 math.
+ * Swin res-post-norm: x + norm1(attn(x)), x + norm2(mlp(x)); PatchMerging norm (res = NULL). */
+int soccdpt_layernorm_fwd(const void *t, const void *res, const float *gamma, const float *beta,
+                          void *y, long long rows, int C, float eps, soccdpt_stream_t stream);
+
+/* timm PatchMerging gather: [B,H,W,C] -> [B,H/2,W/2,4C] in (x0,x1,x2,x3) = (0,0),(1,0),(0,1),(1,1) order */
+int soccdpt_patch_merge_gather_fwd(const void *x, void *y, int batch, int H, int W, int C,
+                                   soccdpt_stream_t stream);
+
+/* ------------------------------------------------------------------ decoder glue
+ * bilinear, align_corners=True, NHWC bf16 [N,h,w,C] -> [N,H,W,C] (blocks.py:488-493, dpt.py:209) */
+int soccdpt_upsample_bilinear_fwd(const void *x, void *y, int N, int h, int w, int H, int W, int C,
+                                  soccdpt_stream_t stream);
+
+/* seg head tail (SOccDPT.py:671-673): logits f32 [N,h,w,P] -> bilinear x2 (align_corners=True)
+ * -> sigmoid (act=0) or 0.5*tanh+0.5 (act=1) -> f32 NCHW [N,P,2h,2w] */
+int soccdpt_seg_finish_fwd(const float *logits, float *seg, int N, int h, int w, int P, int act,
+                           soccdpt_stream_t stream);
+
+/* dtype plumbing for the boundary: f32 <-> bf16 round-to-nearest-even, n elements */
+int soccdpt_f32_to_bf16(const float *x, void *y, long long n, soccdpt_stream_t stream);
+int soccdpt_bf16_to_f32(const void *x, float *y, long long n, soccdpt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOCCDPT_B200_H */

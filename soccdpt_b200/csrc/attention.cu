@@ -1,0 +1,165 @@
+// SwinV2 window attention (timm 0.6.12 WindowAttention + the window partition / cyclic shift /
+// reverse of SwinTransformerBlock._attn), one CTA per (window, head), one thread per query token.
+//
+//   q,k,v   : slices of the qkv GEMM output (bias already added), head_dim = 32
+//   scores  : normalize(q) . normalize(k)^T * exp(min(logit_scale, ln 100)) + cpb_bias[h] + shift_mask
+//   softmax : chunked online softmax in fp32, then P @ V
+// The cyclic shift is folded into the token index arithmetic (no roll kernels, no window copies);
+// the {0,-100} shift mask is regenerated from region ids exactly as timm builds its attn_mask buffer.
+//
+// Round-1 implementation: K/V of the window staged in shared memory as fp32, CUDA-core FMAs.
+// (The tcgen05 version keeps S/P in TMEM; see DESIGN.md "next".)
+#include "common.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+constexpr int D = 32;   // head dim of every SwinV2 config on the path
+constexpr int CH = 8;   // keys per online-softmax step
+
+__device__ __forceinline__ void load_head(const bf16 *p, float f[D]) {
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+        const uint4 u = *reinterpret_cast<const uint4 *>(p + i * 8);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 t = __bfloat1622float2(h[k]);
+            f[i * 8 + 2 * k] = t.x;
+            f[i * 8 + 2 * k + 1] = t.y;
+        }
+    }
+}
+
+__device__ __forceinline__ int region_of(int p, int size, int ws, int shift) {
+    // timm: slices (0,-ws), (-ws,-shift), (-shift,None) over the SHIFTED image
+    return p < size - ws ? 0 : (p < size - shift ? 1 : 2);
+}
+
+__global__ void window_attention_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ biasT,
+                                        const float *__restrict__ scale, bf16 *__restrict__ out, int Hs, int Ws,
+                                        int C, int ws, int shift) {
+    extern __shared__ float smem[];
+    const int N = ws * ws;
+    float *Ks = smem;                 // [N][32]
+    float *Vs = smem + (size_t)N * D; // [N][32]
+    int *reg = reinterpret_cast<int *>(Vs + (size_t)N * D);  // [N]
+
+    const int nwx = Ws / ws, nwy = Hs / ws;
+    const int win = blockIdx.x % (nwx * nwy), b = blockIdx.x / (nwx * nwy);
+    const int head = blockIdx.y;
+    const int i = threadIdx.x;
+    const bool live = i < N;
+
+    float q[D];
+    long long tok = 0;
+    int my_reg = 0;
+    if (live) {
+        const int ty = i / ws, tx = i % ws;
+        const int ys = (win / nwx) * ws + ty, xs = (win % nwx) * ws + tx;   // position in the shifted image
+        const int yo = (ys + shift) % Hs, xo = (xs + shift) % Ws;           // roll(-shift): shifted[y] = x[y+shift]
+        tok = ((long long)b * Hs + yo) * Ws + xo;
+        const bf16 *base = qkv + tok * 3 * C + head * D;
+        float k[D], v[D];
+        load_head(base, q);
+        load_head(base + C, k);
+        load_head(base + 2 * C, v);
+        float qq = 0.f, kk = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) { qq = fmaf(q[d], q[d], qq); kk = fmaf(k[d], k[d], kk); }
+        const float qs = scale[head] / fmaxf(sqrtf(qq), 1e-12f);   // F.normalize eps, logit scale folded in
+        const float ks = 1.0f / fmaxf(sqrtf(kk), 1e-12f);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            q[d] *= qs;
+            Ks[i * D + d] = k[d] * ks;
+            Vs[i * D + d] = v[d];
+        }
+        my_reg = shift > 0 ? region_of(ys, Hs, ws, shift) * 3 + region_of(xs, Ws, ws, shift) : 0;
+        reg[i] = my_reg;
+    }
+    __syncthreads();
+    if (!live) return;
+
+    const float *bias = biasT + (size_t)head * N * N + i;   // biasT[h][j][i]
+    float m = -INFINITY, l = 0.f, acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = 0.f;
+    for (int j0 = 0; j0 < N; j0 += CH) {
+        float s[CH];
+        float cm = -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < CH; ++jj) {
+            const int j = j0 + jj;
+            const float4 *kp = reinterpret_cast<const float4 *>(Ks + j * D);
+            float dot = 0.f;
+#pragma unroll
+            for (int d4 = 0; d4 < D / 4; ++d4) {
+                const float4 kv = kp[d4];
+                dot = fmaf(q[d4 * 4 + 0], kv.x, dot);
+                dot = fmaf(q[d4 * 4 + 1], kv.y, dot);
+                dot = fmaf(q[d4 * 4 + 2], kv.z, dot);
+                dot = fmaf(q[d4 * 4 + 3], kv.w, dot);
+            }
+            dot += __ldg(bias + (size_t)j * N);
+            if (reg[j] != my_reg) dot += -100.0f;
+            s[jj] = dot;
+            cm = fmaxf(cm, dot);
+        }
+        const float mn = fmaxf(m, cm);
+        const float corr = __expf(m - mn);
+        l *= corr;
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[d] *= corr;
+#pragma unroll
+        for (int jj = 0; jj < CH; ++jj) {
+            const float p = __expf(s[jj] - mn);
+            l += p;
+            const float4 *vp = reinterpret_cast<const float4 *>(Vs + (j0 + jj) * D);
+#pragma unroll
+            for (int d4 = 0; d4 < D / 4; ++d4) {
+                const float4 vv = vp[d4];
+                acc[d4 * 4 + 0] = fmaf(p, vv.x, acc[d4 * 4 + 0]);
+                acc[d4 * 4 + 1] = fmaf(p, vv.y, acc[d4 * 4 + 1]);
+                acc[d4 * 4 + 2] = fmaf(p, vv.z, acc[d4 * 4 + 2]);
+                acc[d4 * 4 + 3] = fmaf(p, vv.w, acc[d4 * 4 + 3]);
+            }
+        }
+        m = mn;
+    }
+    const float inv = 1.0f / l;
+    bf16 *op = out + tok * C + head * D;
+#pragma unroll
+    for (int i8 = 0; i8 < D / 8; ++i8) {
+        uint4 u;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(acc[i8 * 8 + 2 * k] * inv, acc[i8 * 8 + 2 * k + 1] * inv);
+        *reinterpret_cast<uint4 *>(op + i8 * 8) = u;
+    }
+}
+
+}  // namespace
+
+extern "C" int soccdpt_window_attention_fwd(const void *qkv, const float *bias, const float *scale, void *out,
+                                            int batch, int Hs, int Ws, int C, int heads, int ws, int shift,
+                                            soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(qkv && bias && scale && out, "window_attention: NULL pointer");
+    SOCCDPT_REQUIRE(batch >= 1 && heads >= 1 && C == heads * D, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
+    SOCCDPT_REQUIRE(ws >= 1 && Hs % ws == 0 && Ws % ws == 0, "window_attention: window %d does not tile %dx%d", ws, Hs, Ws);
+    SOCCDPT_REQUIRE(shift >= 0 && shift < ws, "window_attention: bad shift %d", shift);
+    const int N = ws * ws;
+    SOCCDPT_REQUIRE(N % CH == 0 && N <= 1024, "window_attention: window tokens must be a multiple of %d and <= 1024 (got %d)", CH, N);
+    const int threads = (N + 31) / 32 * 32;
+    const size_t smem = (size_t)N * D * 2 * sizeof(float) + (size_t)N * sizeof(int);
+    SOCCDPT_REQUIRE(smem <= 227 * 1024, "window_attention: window too large for shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        SOCCDPT_CUDA(cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)(batch * (Hs / ws) * (Ws / ws)), (unsigned)heads);
+    window_attention_kernel<<<grid, threads, smem, soccdpt::as_stream(stream)>>>(
+        static_cast<const bf16 *>(qkv), bias, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift);
+    return soccdpt::check_launch("window_attention_kernel");
+}

@@ -1,0 +1,462 @@
+// Implicit-GEMM convolution / linear layer on the 5th-gen tensor cores (sm_100a only).
+//
+//   D[pixel, cout] = sum_{tap, c} X[pixel + tap, c] * Wt[cout, tap, c]      bf16 x bf16 -> fp32 (TMEM)
+//
+// * A operand (activations, NHWC): loaded by TMA as a 4-D box {64 ch, BW, BH, BN} whose coordinates
+//   are shifted by the filter tap -- the im2col never exists, and TMA's out-of-bounds zero fill IS the
+//   convolution's zero padding (and the K / M tails).  128 pixels x 64 channels land in shared
+//   memory in the 128B-swizzled K-major layout tcgen05.mma consumes directly.
+// * B operand (weights [Cout][tap][Cin]): 3-D box {64, 1, BLOCK_N}, same swizzle.
+// * tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N (16..256), K=16, issued by ONE thread;
+//   accumulators live in TMEM (2 stages x 256 columns) so the epilogue of tile i overlaps the
+//   MMAs of tile i+1.
+// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+//   warps 4-7 = epilogue (tcgen05.ld -> bias / ReLU / GELU / residual adds / bf16 store, or the fused
+//   narrow projection 32->1 / 256->3 of the depth / seg heads).
+// * persistent: grid = min(tiles, SMs); 4-stage smem ring (A 16 KB + B <=32 KB per stage).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace soccdpt {
+int validate_conv(const soccdpt_conv_t *c);
+}
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;            // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;       // 32 KB (BLOCK_N <= 256)
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = 512;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_THREADS = 128;
+// dynamic smem: ring + epilogue constants (bias 256 f32 + proj 4x256 f32 + proj bias) + barriers
+constexpr int EPI_CONST_BYTES = (256 + 4 * 256 + 4) * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_CONST_BYTES + 256 + 1024 /*alignment slack*/;
+
+struct Params {
+    // tile geometry
+    int BW, BH, BN;            // box of output pixels handled by one M tile (BW*BH*BN <= 128)
+    int tiles_w, tiles_h, tiles_n, n_blocks, total_tiles;
+    int block_n;               // output channels per tile
+    int k_blocks_per_tap;      // ceil(Cin / 64)
+    int pad;                   // KH / 2
+    uint32_t a_bytes, b_bytes; // TMA transaction bytes per stage
+    soccdpt_conv_t c;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows are 128 B,
+// 8-row groups are 1024 B apart (SBO), version 1 (Blackwell), layout type 2.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                            // version
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float *s_bias = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
+    float *s_projw = s_bias + 256;
+    float *s_projb = s_projw + 4 * 256;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_projb + 4);
+    uint64_t *empty = full + STAGES;
+    uint64_t *acc_full = empty + STAGES;
+    uint64_t *acc_empty = acc_full + ACC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const soccdpt_conv_t &c = p.c;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_THREADS); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int taps = c.KH * c.KW;
+    const int k_blocks = taps * p.k_blocks_per_tap;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+                const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    const int tap = kb / p.k_blocks_per_tap, cb = kb - tap * p.k_blocks_per_tap;
+                    const int kh = tap / c.KW, kw = tap - kh * c.KW;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
+                    uint8_t *sa = smem + stage * STAGE_BYTES;
+                    tma_load_4d(sa, &map_a, &full[stage], cb * BLOCK_K, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+                    tma_load_3d(sa + A_STAGE_BYTES, &map_b, &full[stage], cb * BLOCK_K, tap, nb * p.block_n);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(p.block_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    const int cb = kb % p.k_blocks_per_tap;
+                    const int rem = c.Cin - cb * BLOCK_K;
+                    const int ksteps = rem >= BLOCK_K ? BLOCK_K / UMMA_K : (rem + UMMA_K - 1) / UMMA_K;
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t da = umma_desc(sa), db = umma_desc(sa + A_STAGE_BYTES);
+                    for (int k = 0; k < ksteps; ++k) {
+                        // advance both descriptors by k * 32 B inside the 128 B swizzle row
+                        umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);              // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[acc]);                 // accumulator complete -> epilogue
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (128 threads, TMEM lane = tile row) =====================
+        const int et = threadIdx.x - 128;          // 0..127 == TMEM lane == row inside the tile
+        const int quarter = warp & 3;              // TMEM lanes [32*quarter, +32) are visible to this warp
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int cached_nb = -1;
+        const bf16 *res1 = static_cast<const bf16 *>(c.res1);
+        const bf16 *res2 = static_cast<const bf16 *>(c.res2);
+        bf16 *y = static_cast<bf16 *>(c.y);
+        bf16 *y_relu = static_cast<bf16 *>(c.y_relu);
+        const int m_valid = p.BW * p.BH * p.BN;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+            const int cout0 = nb * p.block_n;
+            if (nb != cached_nb) {
+                // per-channel constants of this N block -> smem (visible to the 128 epilogue threads only)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = et; i < p.block_n; i += EPI_THREADS) s_bias[i] = c.bias ? c.bias[cout0 + i] : 0.0f;
+                if (c.proj_n > 0) {
+                    for (int i = et; i < c.proj_n * c.Cout; i += EPI_THREADS) s_projw[i] = c.proj_w[i];
+                    if (et < c.proj_n) s_projb[et] = c.proj_b[et];
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cached_nb = nb;
+            }
+            // row -> pixel
+            const int bw = et % p.BW, bh = (et / p.BW) % p.BH, bn = et / (p.BW * p.BH);
+            const int wx = tw * p.BW + bw, hy = th * p.BH + bh, ni = tn * p.BN + bn;
+            const bool valid = (et < m_valid) && (wx < c.W) && (hy < c.H) && (ni < c.N);
+            const long long pix = ((long long)ni * c.H + hy) * c.W + wx;
+
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+            float proj[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int col = 0; col < p.block_n; col += 16) {
+                uint32_t raw[16];
+                tmem_ld16(t_row + (uint32_t)col, raw);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float t = __uint_as_float(raw[j]) + s_bias[col + j];
+                    if (c.act == SOCCDPT_ACT_RELU) t = fmaxf(t, 0.0f);
+                    else if (c.act == SOCCDPT_ACT_GELU) t = gelu_erf(t);
+                    v[j] = t;
+                }
+                if (valid) {
+                    const long long o = pix * c.Cout + cout0 + col;
+                    if (res1) {
+                        const uint4 *rp = reinterpret_cast<const uint4 *>(res1 + o);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint4 u = rp[h];
+                            const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 f = __bfloat1622float2(b2[k]);
+                                v[h * 8 + 2 * k] += f.x;
+                                v[h * 8 + 2 * k + 1] += f.y;
+                            }
+                        }
+                    }
+                    if (res2) {
+                        const uint4 *rp = reinterpret_cast<const uint4 *>(res2 + o);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint4 u = rp[h];
+                            const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 f = __bfloat1622float2(b2[k]);
+                                v[h * 8 + 2 * k] += f.x;
+                                v[h * 8 + 2 * k + 1] += f.y;
+                            }
+                        }
+                    }
+                    if (y) {
+                        uint4 *yp = reinterpret_cast<uint4 *>(y + o);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint4 u;
+                            __nv_bfloat162 *b2 = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) b2[k] = __floats2bfloat162_rn(v[h * 8 + 2 * k], v[h * 8 + 2 * k + 1]);
+                            yp[h] = u;
+                        }
+                    }
+                    if (y_relu) {
+                        uint4 *yp = reinterpret_cast<uint4 *>(y_relu + o);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint4 u;
+                            __nv_bfloat162 *b2 = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                b2[k] = __floats2bfloat162_rn(fmaxf(v[h * 8 + 2 * k], 0.0f), fmaxf(v[h * 8 + 2 * k + 1], 0.0f));
+                            yp[h] = u;
+                        }
+                    }
+                    for (int q = 0; q < c.proj_n; ++q) {
+                        const float *pw = s_projw + q * c.Cout + col;
+                        float s = proj[q];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) s = fmaf(pw[j], v[j], s);
+                        proj[q] = s;
+                    }
+                }
+            }
+            // accumulator fully read: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+            if (valid && c.proj_n > 0) {
+                for (int q = 0; q < c.proj_n; ++q) {
+                    float s = proj[q] + s_projb[q];
+                    if (c.proj_relu) s = fmaxf(s, 0.0f);
+                    c.proj_out[pix * c.proj_n + q] = s;
+                }
+            }
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int largest_divisor_leq(int n, int cap) {
+    for (int d = cap < n ? cap : n; d >= 1; --d)
+        if (n % d == 0) return d;
+    return 1;
+}
+
+int pick_block_n(int cout) {
+    for (int bn = 256; bn >= 16; bn -= 16)
+        if (cout % bn == 0) return bn;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream) {
+    int rc = soccdpt::validate_conv(c);
+    if (rc) return rc;
+    EncodeTiledFn encode = encode_fn();
+    SOCCDPT_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    SOCCDPT_REQUIRE((reinterpret_cast<uintptr_t>(c->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(c->wgt) & 15) == 0,
+                    "conv: x / wgt must be 16-byte aligned");
+    SOCCDPT_REQUIRE(c->Cout % 16 == 0, "conv: Cout must be a multiple of 16 (got %d)", c->Cout);
+
+    Params p{};
+    p.c = *c;
+    p.block_n = pick_block_n(c->Cout);
+    SOCCDPT_REQUIRE(p.block_n >= 16, "conv: no valid N tile for Cout=%d", c->Cout);
+    if (c->proj_n > 0) SOCCDPT_REQUIRE(p.block_n == c->Cout, "conv: fused projection needs the whole Cout in one tile");
+    // M tile = box of output pixels {BW, BH, BN}
+    if (c->W >= BLOCK_M) {
+        p.BW = (c->W % BLOCK_M == 0) ? BLOCK_M : largest_divisor_leq(c->W, BLOCK_M);
+        if (p.BW < 64) p.BW = BLOCK_M;   // poor divisor: use full tiles, mask the tail
+        p.BH = 1;
+        p.BN = 1;
+    } else {
+        p.BW = c->W;
+        const int rows = BLOCK_M / c->W;
+        if (c->H >= rows) {
+            p.BH = largest_divisor_leq(c->H, rows);
+            p.BN = 1;
+        } else {
+            p.BH = c->H;
+            p.BN = BLOCK_M / (c->W * c->H);
+            if (p.BN > c->N) p.BN = c->N;
+            if (p.BN < 1) p.BN = 1;
+        }
+    }
+    p.tiles_w = (c->W + p.BW - 1) / p.BW;
+    p.tiles_h = (c->H + p.BH - 1) / p.BH;
+    p.tiles_n = (c->N + p.BN - 1) / p.BN;
+    p.n_blocks = c->Cout / p.block_n;
+    const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
+    SOCCDPT_REQUIRE(total < (1ll << 31), "conv: too many tiles");
+    p.total_tiles = (int)total;
+    p.k_blocks_per_tap = (c->Cin + BLOCK_K - 1) / BLOCK_K;
+    p.pad = c->KH / 2;
+    p.a_bytes = (uint32_t)(p.BW * p.BH * p.BN) * BLOCK_K * 2;
+    p.b_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)c->Cin, (cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->N};
+        cuuint64_t strides[3] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)c->W * c->Cin * 2, (cuuint64_t)c->H * c->W * c->Cin * 2};
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BN};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(c->x), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SOCCDPT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed with %d (N=%d H=%d W=%d Cin=%d box=%d,%d,%d)", (int)r,
+                        c->N, c->H, c->W, c->Cin, p.BW, p.BH, p.BN);
+    }
+    {
+        const int taps = c->KH * c->KW;
+        cuuint64_t dims[3] = {(cuuint64_t)c->Cin, (cuuint64_t)taps, (cuuint64_t)c->Cout};
+        cuuint64_t strides[2] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)taps * c->Cin * 2};
+        cuuint32_t box[3] = {BLOCK_K, 1, (cuuint32_t)p.block_n};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(c->wgt), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SOCCDPT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed with %d (Cout=%d taps=%d Cin=%d)", (int)r, c->Cout, taps, c->Cin);
+    }
+
+    static bool configured = false;
+    if (!configured) {
+        SOCCDPT_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int grid = p.total_tiles < soccdpt::sm_count() ? p.total_tiles : soccdpt::sm_count();
+    conv_tcgen05_kernel<<<grid, NUM_THREADS, SMEM_BYTES, soccdpt::as_stream(stream)>>>(map_a, map_b, p);
+    return soccdpt::check_launch("conv_tcgen05_kernel");
+}

@@ -1,0 +1,341 @@
+// Bandwidth-bound glue kernels of the network path + the CUDA-core reference convolution.
+// Layout everywhere: NHWC / token-major bf16 activations, fp32 math inside the kernels.
+#include "common.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == SOCCDPT_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == SOCCDPT_ACT_GELU) return gelu_erf(v);
+    return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4 &u, float f[8]) {
+    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(p[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float f[8]) {
+    uint4 u;
+    __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return u;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------ reference convolution
+// One warp per output pixel; lane l owns output channels l, l+32, ...  Same epilogue contract as
+// the tcgen05 kernel (conv_tcgen05.cu) -- used by the tests as an on-device cross-check.
+__global__ void __launch_bounds__(256) conv_ref_kernel(const soccdpt_conv_t c) {
+    const int lane = threadIdx.x & 31;
+    const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long total = (long long)c.N * c.H * c.W;
+    if (pix >= total) return;
+    const int w0 = (int)(pix % c.W), h0 = (int)((pix / c.W) % c.H), n = (int)(pix / ((long long)c.W * c.H));
+    const bf16 *x = static_cast<const bf16 *>(c.x);
+    const bf16 *wgt = static_cast<const bf16 *>(c.wgt);
+    const int taps = c.KH * c.KW;
+    float proj[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int co = lane; co < c.Cout; co += 32) {
+        float acc = 0.0f;
+        for (int kh = 0; kh < c.KH; ++kh) {
+            const int hh = h0 + kh - c.KH / 2;
+            if (hh < 0 || hh >= c.H) continue;
+            for (int kw = 0; kw < c.KW; ++kw) {
+                const int ww = w0 + kw - c.KW / 2;
+                if (ww < 0 || ww >= c.W) continue;
+                const bf16 *xp = x + (((long long)n * c.H + hh) * c.W + ww) * c.Cin;
+                const bf16 *wp = wgt + ((long long)co * taps + kh * c.KW + kw) * c.Cin;
+                for (int ci = 0; ci < c.Cin; ci += 8) {
+                    float a[8], b[8];
+                    unpack8(*reinterpret_cast<const uint4 *>(xp + ci), a);
+                    unpack8(*reinterpret_cast<const uint4 *>(wp + ci), b);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc = fmaf(a[k], b[k], acc);
+                }
+            }
+        }
+        float v = acc + (c.bias ? c.bias[co] : 0.0f);
+        v = apply_act(v, c.act);
+        const long long o = pix * c.Cout + co;
+        if (c.res1) v += __bfloat162float(static_cast<const bf16 *>(c.res1)[o]);
+        if (c.res2) v += __bfloat162float(static_cast<const bf16 *>(c.res2)[o]);
+        if (c.y) static_cast<bf16 *>(c.y)[o] = __float2bfloat16_rn(v);
+        if (c.y_relu) static_cast<bf16 *>(c.y_relu)[o] = __float2bfloat16_rn(fmaxf(v, 0.0f));
+        for (int p = 0; p < c.proj_n; ++p) proj[p] = fmaf(c.proj_w[p * c.Cout + co], v, proj[p]);
+    }
+    for (int p = 0; p < c.proj_n; ++p) {
+        float s = warp_sum(proj[p]);
+        if (lane == 0) {
+            s += c.proj_b[p];
+            if (c.proj_relu) s = fmaxf(s, 0.0f);
+            c.proj_out[pix * c.proj_n + p] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ patch embed (conv4x4 s4 + LN)
+// One warp per token; lane l owns channels l, l+32, ... (E <= 256).
+__global__ void __launch_bounds__(256)
+patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
+                   const float *__restrict__ g, const float *__restrict__ be, bf16 *__restrict__ out, int B, int H,
+                   int W, int E) {
+    const int lane = threadIdx.x & 31;
+    const int ph = H / 4, pw = W / 4;
+    const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tok >= (long long)B * ph * pw) return;
+    const int tx = (int)(tok % pw), ty = (int)((tok / pw) % ph), n = (int)(tok / ((long long)pw * ph));
+    float in[48];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4 *>(x + (((long long)n * 3 + ci) * H + ty * 4 + i) * W + tx * 4);
+            in[ci * 16 + i * 4 + 0] = v.x; in[ci * 16 + i * 4 + 1] = v.y;
+            in[ci * 16 + i * 4 + 2] = v.z; in[ci * 16 + i * 4 + 3] = v.w;
+        }
+    float val[8];
+    float sum = 0.0f;
+    int cnt = 0;
+    for (int e = lane; e < E; e += 32, ++cnt) {
+        float acc = b[e];
+        const float *we = w + (long long)e * 48;
+#pragma unroll
+        for (int k = 0; k < 48; ++k) acc = fmaf(in[k], we[k], acc);
+        val[cnt] = acc;
+        sum += acc;
+    }
+    const float mean = warp_sum(sum) / (float)E;
+    float sq = 0.0f;
+    for (int i = 0; i < cnt; ++i) sq += (val[i] - mean) * (val[i] - mean);
+    const float rstd = rsqrtf(warp_sum(sq) / (float)E + 1e-5f);
+    cnt = 0;
+    for (int e = lane; e < E; e += 32, ++cnt)
+        out[tok * E + e] = __float2bfloat16_rn((val[cnt] - mean) * rstd * g[e] + be[e]);
+}
+
+// ------------------------------------------------------------------ y = res + LayerNorm(t)
+// One warp per row, 16-byte (8 x bf16) accesses; the row is re-read from L1 for the 2nd/3rd pass.
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const bf16 *__restrict__ t, const bf16 *__restrict__ res, const float *__restrict__ gamma,
+                 const float *__restrict__ beta, bf16 *__restrict__ y, long long rows, int C, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const uint4 *tp = reinterpret_cast<const uint4 *>(t + row * C);
+    const int chunks = C / 8;
+    float s = 0.0f;
+    for (int k = lane; k < chunks; k += 32) {
+        float f[8];
+        unpack8(tp[k], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += f[i];
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.0f;
+    for (int k = lane; k < chunks; k += 32) {
+        float f[8];
+        unpack8(tp[k], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q += (f[i] - mean) * (f[i] - mean);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    const uint4 *rp = res ? reinterpret_cast<const uint4 *>(res + row * C) : nullptr;
+    uint4 *yp = reinterpret_cast<uint4 *>(y + row * C);
+    for (int k = lane; k < chunks; k += 32) {
+        float f[8], r[8];
+        unpack8(tp[k], f);
+        if (rp) unpack8(rp[k], r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float v = (f[i] - mean) * rstd * gamma[k * 8 + i] + beta[k * 8 + i];
+            f[i] = rp ? r[i] + v : v;
+        }
+        yp[k] = pack8(f);
+    }
+}
+
+// ------------------------------------------------------------------ PatchMerging gather
+__global__ void __launch_bounds__(256)
+patch_merge_gather_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, int B, int H, int W, int C) {
+    const int chunks = C / 8;
+    const long long total = (long long)B * (H / 2) * (W / 2) * 4 * chunks;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int ck = (int)(i % chunks);
+        const int q = (int)((i / chunks) % 4);
+        const long long o = i / (4 * chunks);
+        const int ox = (int)(o % (W / 2)), oy = (int)((o / (W / 2)) % (H / 2)), n = (int)(o / ((long long)(W / 2) * (H / 2)));
+        const int dh = q & 1, dw = q >> 1;  // x0:(0,0) x1:(1,0) x2:(0,1) x3:(1,1)
+        const uint4 v = *reinterpret_cast<const uint4 *>(x + (((long long)n * H + oy * 2 + dh) * W + ox * 2 + dw) * C + ck * 8);
+        *reinterpret_cast<uint4 *>(y + (o * 4 + q) * C + ck * 8) = v;
+    }
+}
+
+// ------------------------------------------------------------------ bilinear, align_corners=True, NHWC bf16
+__global__ void __launch_bounds__(256)
+upsample_bilinear_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, int N, int h, int w, int H, int W, int C) {
+    const int chunks = C / 8;
+    const long long total = (long long)N * H * W * chunks;
+    const float sh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.0f;
+    const float sw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.0f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int ck = (int)(i % chunks);
+        const long long o = i / chunks;
+        const int X = (int)(o % W), Y = (int)((o / W) % H), n = (int)(o / ((long long)W * H));
+        const float fy = sh * (float)Y, fx = sw * (float)X;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float ly = fy - (float)y0, lx = fx - (float)x0;
+        const bf16 *base = x + (long long)n * h * w * C + ck * 8;
+        float a[8], b[8], c2[8], d[8], r[8];
+        unpack8(*reinterpret_cast<const uint4 *>(base + ((long long)y0 * w + x0) * C), a);
+        unpack8(*reinterpret_cast<const uint4 *>(base + ((long long)y0 * w + x1) * C), b);
+        unpack8(*reinterpret_cast<const uint4 *>(base + ((long long)y1 * w + x0) * C), c2);
+        unpack8(*reinterpret_cast<const uint4 *>(base + ((long long)y1 * w + x1) * C), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            r[k] = (1.0f - ly) * ((1.0f - lx) * a[k] + lx * b[k]) + ly * ((1.0f - lx) * c2[k] + lx * d[k]);
+        *reinterpret_cast<uint4 *>(y + o * C + ck * 8) = pack8(r);
+    }
+}
+
+// ------------------------------------------------------------------ seg head tail
+// logits f32 [N,h,w,P] -> bilinear x2 (align_corners=True) -> sigmoid | 0.5*tanh+0.5 -> f32 NCHW
+__global__ void __launch_bounds__(256)
+seg_finish_kernel(const float *__restrict__ lg, float *__restrict__ seg, int N, int h, int w, int P, int act) {
+    const int H = 2 * h, W = 2 * w;
+    const long long total = (long long)N * H * W;
+    const float sh = (float)(h - 1) / (float)(H - 1), sw = (float)(w - 1) / (float)(W - 1);
+    for (long long o = (long long)blockIdx.x * 256 + threadIdx.x; o < total; o += (long long)gridDim.x * 256) {
+        const int X = (int)(o % W), Y = (int)((o / W) % H), n = (int)(o / ((long long)W * H));
+        const float fy = sh * (float)Y, fx = sw * (float)X;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float ly = fy - (float)y0, lx = fx - (float)x0;
+        const float *base = lg + (long long)n * h * w * P;
+        for (int p = 0; p < P; ++p) {
+            const float a = base[((long long)y0 * w + x0) * P + p], b = base[((long long)y0 * w + x1) * P + p];
+            const float c = base[((long long)y1 * w + x0) * P + p], d = base[((long long)y1 * w + x1) * P + p];
+            const float v = (1.0f - ly) * ((1.0f - lx) * a + lx * b) + ly * ((1.0f - lx) * c + lx * d);
+            const float r = act == 0 ? 1.0f / (1.0f + expf(-v)) : 0.5f * tanhf(v) + 0.5f;
+            seg[(((long long)n * P + p) * H + Y) * W + X] = r;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restrict__ x, bf16 *__restrict__ y, long long n) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        y[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const bf16 *__restrict__ x, float *__restrict__ y, long long n) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        y[i] = __bfloat162float(x[i]);
+}
+
+int grid_for(long long work_items) {
+    long long blocks = (work_items + 255) / 256;
+    const long long cap = (long long)soccdpt::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+namespace soccdpt {
+int validate_conv(const soccdpt_conv_t *c) {
+    SOCCDPT_REQUIRE(c != nullptr, "conv descriptor is NULL");
+    SOCCDPT_REQUIRE(c->x && c->wgt, "conv: x / wgt is NULL");
+    SOCCDPT_REQUIRE(c->N >= 1 && c->H >= 1 && c->W >= 1, "conv: bad image dims %dx%dx%d", c->N, c->H, c->W);
+    SOCCDPT_REQUIRE(c->Cin >= 8 && c->Cin % 8 == 0, "conv: Cin must be a multiple of 8 (got %d)", c->Cin);
+    SOCCDPT_REQUIRE(c->Cout >= 8 && c->Cout % 8 == 0, "conv: Cout must be a multiple of 8 (got %d)", c->Cout);
+    SOCCDPT_REQUIRE((c->KH == 1 || c->KH == 3) && c->KW == c->KH, "conv: kernel must be 1x1 or 3x3");
+    SOCCDPT_REQUIRE(c->act >= 0 && c->act <= 2, "conv: bad activation %d", c->act);
+    SOCCDPT_REQUIRE(c->proj_n >= 0 && c->proj_n <= 4, "conv: proj_n must be in [0,4]");
+    if (c->proj_n > 0) {
+        SOCCDPT_REQUIRE(c->proj_w && c->proj_b && c->proj_out, "conv: projection pointers are NULL");
+        SOCCDPT_REQUIRE(c->Cout <= 256, "conv: fused projection needs Cout <= 256");
+    }
+    SOCCDPT_REQUIRE(c->y || c->y_relu || c->proj_n > 0, "conv: no output requested");
+    return SOCCDPT_OK;
+}
+}  // namespace soccdpt
+
+extern "C" {
+
+int soccdpt_conv_ref_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream) {
+    int rc = soccdpt::validate_conv(c);
+    if (rc) return rc;
+    const long long pix = (long long)c->N * c->H * c->W;
+    conv_ref_kernel<<<(unsigned)((pix + 7) / 8), 256, 0, soccdpt::as_stream(stream)>>>(*c);
+    return soccdpt::check_launch("conv_ref_kernel");
+}
+
+int soccdpt_patch_embed_fwd(const float *x, const float *w, const float *b, const float *ln_w, const float *ln_b,
+                            void *tokens, int batch, int H, int W, int E, soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(x && w && b && ln_w && ln_b && tokens, "patch_embed: NULL pointer");
+    SOCCDPT_REQUIRE(batch >= 1 && H % 4 == 0 && W % 4 == 0 && E >= 32 && E <= 256, "patch_embed: bad shape");
+    const long long toks = (long long)batch * (H / 4) * (W / 4);
+    patch_embed_kernel<<<(unsigned)((toks + 7) / 8), 256, 0, soccdpt::as_stream(stream)>>>(
+        x, w, b, ln_w, ln_b, static_cast<bf16 *>(tokens), batch, H, W, E);
+    return soccdpt::check_launch("patch_embed_kernel");
+}
+
+int soccdpt_layernorm_fwd(const void *t, const void *res, const float *gamma, const float *beta, void *y,
+                          long long rows, int C, float eps, soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(t && gamma && beta && y, "layernorm: NULL pointer");
+    SOCCDPT_REQUIRE(rows >= 1 && C >= 8 && C % 8 == 0, "layernorm: C must be a multiple of 8 (got %d)", C);
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, soccdpt::as_stream(stream)>>>(
+        static_cast<const bf16 *>(t), static_cast<const bf16 *>(res), gamma, beta, static_cast<bf16 *>(y), rows, C, eps);
+    return soccdpt::check_launch("layernorm_kernel");
+}
+
+int soccdpt_patch_merge_gather_fwd(const void *x, void *y, int batch, int H, int W, int C, soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(x && y && batch >= 1 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "patch_merge: bad arguments");
+    const long long items = (long long)batch * (H / 2) * (W / 2) * 4 * (C / 8);
+    patch_merge_gather_kernel<<<grid_for(items), 256, 0, soccdpt::as_stream(stream)>>>(
+        static_cast<const bf16 *>(x), static_cast<bf16 *>(y), batch, H, W, C);
+    return soccdpt::check_launch("patch_merge_gather_kernel");
+}
+
+int soccdpt_upsample_bilinear_fwd(const void *x, void *y, int N, int h, int w, int H, int W, int C,
+                                  soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(x && y && N >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && C % 8 == 0, "upsample: bad arguments");
+    const long long items = (long long)N * H * W * (C / 8);
+    upsample_bilinear_kernel<<<grid_for(items), 256, 0, soccdpt::as_stream(stream)>>>(
+        static_cast<const bf16 *>(x), static_cast<bf16 *>(y), N, h, w, H, W, C);
+    return soccdpt::check_launch("upsample_bilinear_kernel");
+}
+
+int soccdpt_seg_finish_fwd(const float *logits, float *seg, int N, int h, int w, int P, int act,
+                           soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(logits && seg && N >= 1 && h >= 2 && w >= 2 && P >= 1 && P <= 4 && (act == 0 || act == 1),
+                    "seg_finish: bad arguments");
+    seg_finish_kernel<<<grid_for((long long)N * 4 * h * w), 256, 0, soccdpt::as_stream(stream)>>>(logits, seg, N, h, w, P, act);
+    return soccdpt::check_launch("seg_finish_kernel");
+}
+
+int soccdpt_f32_to_bf16(const float *x, void *y, long long n, soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(x && y && n >= 1, "f32_to_bf16: bad arguments");
+    f32_to_bf16_kernel<<<grid_for(n), 256, 0, soccdpt::as_stream(stream)>>>(x, static_cast<bf16 *>(y), n);
+    return soccdpt::check_launch("f32_to_bf16_kernel");
+}
+int soccdpt_bf16_to_f32(const void *x, float *y, long long n, soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(x && y && n >= 1, "bf16_to_f32: bad arguments");
+    bf16_to_f32_kernel<<<grid_for(n), 256, 0, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(x), y, n);
+    return soccdpt::check_launch("bf16_to_f32_kernel");
+}
+}

@@ -1,0 +1,266 @@
+"""Execution engine: packs the weights of a SOccDPT_V3 module tree once (bf16, BN folded, attention
+bias tables baked) and replays the image -> (inverse depth, segmentation) network as a fixed list of
+C-ABI kernel launches on the current CUDA stream.  PyTorch only owns the device buffers.
+
+Kernel schedule per frame batch (reference call sites in include/soccdpt_b200.h):
+  patch_embed -> for every Swin block: qkv GEMM, window attention, proj GEMM, LN+residual,
+  fc1 GEMM (+GELU), fc2 GEMM, LN+residual -> patch-merge gather + GEMM + LN between stages ->
+  decoder: layerN_rn conv3x3, residual conv units (bias/ReLU/residual fused in the GEMM epilogue),
+  out_conv 1x1 evaluated BEFORE the bilinear upsample (they commute, 4x fewer FLOPs) ->
+  depth head (32->1 projection fused in the epilogue) and seg head (BN folded, 256->3 fused).
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _cabi
+from .model.encoder import relative_position_bias
+
+
+class _Launch:
+    """One enqueued C-ABI call with its arguments frozen (pointers stay valid: the plan owns the buffers)."""
+    __slots__ = ("fn", "args", "name")
+
+    def __init__(self, name, fn, *args):
+        self.name, self.fn, self.args = name, fn, args
+
+    def __call__(self, stream):
+        rc = self.fn(*self.args, stream)
+        if rc != 0:
+            _cabi.check(rc, self.name)
+
+
+def _bf16(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).to(torch.bfloat16).contiguous()
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _pack_conv(w, dev):
+    """(Cout, Cin, KH, KW) fp32 -> [Cout][KH*KW][Cin] bf16."""
+    return _bf16(w.detach().float().permute(0, 2, 3, 1), dev)
+
+
+class NetworkEngine:
+    def __init__(self, net, conv_impl="tcgen05"):
+        self.net = net
+        self.conv_impl = conv_impl        # "tcgen05" (product) | "ref" (CUDA-core cross-check, tests only)
+        self._weights = None
+        self._plans = {}
+        self.lib = _cabi.load()
+
+    def invalidate(self):
+        self._weights = None
+        self._plans = {}
+
+    # ------------------------------------------------------------------ weight packing
+    def _pack(self, dev):
+        net = self.net
+        enc = net.depth_net.pretrained.model
+        W = {"stages": []}
+        pe = enc.patch_embed
+        W["pe"] = (_f32(pe.proj.weight.reshape(pe.proj.weight.shape[0], -1), dev), _f32(pe.proj.bias, dev),
+                   _f32(pe.norm.weight, dev), _f32(pe.norm.bias, dev))
+        for layer in enc.layers:
+            blocks = []
+            for blk in layer.blocks:
+                a = blk.attn
+                C = a.qkv.weight.shape[1]
+                bias = relative_position_bias(a, blk.window_size, layer.pretrained_window)
+                blocks.append(dict(
+                    ws=blk.window_size, shift=blk.shift_size, heads=blk.num_heads,
+                    wqkv=_bf16(a.qkv.weight, dev),
+                    bqkv=_f32(torch.cat([a.q_bias.detach().float(), torch.zeros(C, device=a.q_bias.device),
+                                         a.v_bias.detach().float()]), dev),
+                    biasT=_f32(bias.transpose(1, 2), dev),          # [h][key j][query i]
+                    scale=_f32(torch.clamp(a.logit_scale.detach().float(), max=math.log(1.0 / 0.01)).exp().reshape(-1), dev),
+                    wproj=_bf16(a.proj.weight, dev), bproj=_f32(a.proj.bias, dev),
+                    n1=(_f32(blk.norm1.weight, dev), _f32(blk.norm1.bias, dev)),
+                    w1=_bf16(blk.mlp.fc1.weight, dev), b1=_f32(blk.mlp.fc1.bias, dev),
+                    w2=_bf16(blk.mlp.fc2.weight, dev), b2=_f32(blk.mlp.fc2.bias, dev),
+                    n2=(_f32(blk.norm2.weight, dev), _f32(blk.norm2.bias, dev))))
+            ds = None
+            if not isinstance(layer.downsample, torch.nn.Identity):
+                ds = dict(w=_bf16(layer.downsample.reduction.weight, dev),
+                          n=(_f32(layer.downsample.norm.weight, dev), _f32(layer.downsample.norm.bias, dev)))
+            W["stages"].append(dict(dim=layer.dim, res=layer.input_resolution, blocks=blocks, down=ds))
+        sc = net.depth_net.scratch
+        W["rn"] = [_pack_conv(getattr(sc, f"layer{i}_rn").weight, dev) for i in (1, 2, 3, 4)]
+        W["fusion"] = {}
+        for i in (1, 2, 3, 4):
+            f = getattr(sc, f"refinenet{i}")
+            W["fusion"][i] = dict(
+                out_w=_pack_conv(f.out_conv.weight, dev), out_b=_f32(f.out_conv.bias, dev),
+                rcu1=(_pack_conv(f.resConfUnit1.conv1.weight, dev), _f32(f.resConfUnit1.conv1.bias, dev),
+                      _pack_conv(f.resConfUnit1.conv2.weight, dev), _f32(f.resConfUnit1.conv2.bias, dev)),
+                rcu2=(_pack_conv(f.resConfUnit2.conv1.weight, dev), _f32(f.resConfUnit2.conv1.bias, dev),
+                      _pack_conv(f.resConfUnit2.conv2.weight, dev), _f32(f.resConfUnit2.conv2.bias, dev)))
+        oc = sc.output_conv
+        W["dh"] = dict(w0=_pack_conv(oc[0].weight, dev), b0=_f32(oc[0].bias, dev),
+                       w2=_pack_conv(oc[2].weight, dev), b2=_f32(oc[2].bias, dev),
+                       pw=_f32(oc[4].weight.reshape(1, -1), dev), pb=_f32(oc[4].bias, dev))
+        sh = net.seg_head
+        bn = sh[1]
+        inv_std = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+        g = bn.weight.detach().float() * inv_std
+        W["sh"] = dict(w0=_pack_conv(sh[0].weight.detach().float() * g.view(-1, 1, 1, 1), dev),
+                       b0=_f32(bn.bias.detach().float() - bn.running_mean.detach().float() * g, dev),
+                       pw=_f32(sh[4].weight.reshape(sh[4].weight.shape[0], -1), dev), pb=_f32(sh[4].bias, dev))
+        W["num_classes"] = sh[4].weight.shape[0]
+        W["seg_act"] = 0 if isinstance(sh[6], torch.nn.Sigmoid) else 1
+        return W
+
+    # ------------------------------------------------------------------ plan construction
+    def _conv(self, plan, x, w, N, H, Wd, Cin, Cout, K, bias=None, act=_cabi.ACT_NONE, res1=None, res2=None, y=None,
+              y_relu=None, proj=None):
+        c = _cabi.Conv()
+        c.x, c.wgt = x.data_ptr(), w.data_ptr()
+        c.bias = bias.data_ptr() if bias is not None else None
+        c.res1 = res1.data_ptr() if res1 is not None else None
+        c.res2 = res2.data_ptr() if res2 is not None else None
+        c.y = y.data_ptr() if y is not None else None
+        c.y_relu = y_relu.data_ptr() if y_relu is not None else None
+        c.N, c.H, c.W, c.Cin, c.Cout, c.KH, c.KW, c.act = N, H, Wd, Cin, Cout, K, K, act
+        if proj is not None:
+            pw, pb, out, relu = proj
+            c.proj_w, c.proj_b, c.proj_out = pw.data_ptr(), pb.data_ptr(), out.data_ptr()
+            c.proj_n, c.proj_relu = pw.shape[0], int(relu)
+        fn = self.lib.soccdpt_conv_fwd if self.conv_impl == "tcgen05" else self.lib.soccdpt_conv_ref_fwd
+        plan["keep"].append(c)
+        plan["ops"].append(_Launch("conv", fn, ctypes.byref(c)))
+
+    def _build_plan(self, B, dev):
+        Wt = self._weights
+        lib = self.lib
+        plan = {"ops": [], "keep": [], "B": B}
+        ops = plan["ops"]
+
+        def buf(*shape, dtype=torch.bfloat16):
+            t = torch.empty(shape, device=dev, dtype=dtype)
+            plan["keep"].append(t)
+            return t
+
+        enc = self.net.depth_net.pretrained.model
+        img = enc.img_size
+        plan["img"] = img
+        x_in = buf(B, 3, img, img, dtype=torch.float32)
+        plan["x_in"] = x_in
+        stages = Wt["stages"]
+        E = stages[0]["dim"]
+        g0 = img // 4
+        maxLC = max(st["res"][0] * st["res"][1] * st["dim"] for st in stages)
+        qkv = buf(B * maxLC * 3)
+        att = buf(B * maxLC)
+        tmp = buf(B * maxLC)
+        hid = buf(B * maxLC * 4)
+        gat = buf(B * maxLC)           # patch-merge gather: (L/4) * 4C = L*C elements
+        cur = buf(B * g0 * g0, E)
+        ops.append(_Launch("patch_embed", lib.soccdpt_patch_embed_fwd, x_in.data_ptr(), *(t.data_ptr() for t in Wt["pe"]),
+                           cur.data_ptr(), B, img, img, E))
+        taps = []
+        for si, st in enumerate(stages):
+            Hs, Ws = st["res"]
+            C, L = st["dim"], Hs * Ws
+            M = B * L
+            for b in st["blocks"]:
+                self._conv(plan, cur, b["wqkv"], 1, 1, M, C, 3 * C, 1, bias=b["bqkv"], y=qkv)
+                ops.append(_Launch("window_attention", lib.soccdpt_window_attention_fwd, qkv.data_ptr(), b["biasT"].data_ptr(),
+                                   b["scale"].data_ptr(), att.data_ptr(), B, Hs, Ws, C, b["heads"], b["ws"], b["shift"]))
+                self._conv(plan, att, b["wproj"], 1, 1, M, C, C, 1, bias=b["bproj"], y=tmp)
+                ops.append(_Launch("ln_res", lib.soccdpt_layernorm_fwd, tmp.data_ptr(), cur.data_ptr(), b["n1"][0].data_ptr(),
+                                   b["n1"][1].data_ptr(), cur.data_ptr(), M, C, ctypes.c_float(1e-5)))
+                self._conv(plan, cur, b["w1"], 1, 1, M, C, 4 * C, 1, bias=b["b1"], act=_cabi.ACT_GELU, y=hid)
+                self._conv(plan, hid, b["w2"], 1, 1, M, 4 * C, C, 1, bias=b["b2"], y=tmp)
+                ops.append(_Launch("ln_res", lib.soccdpt_layernorm_fwd, tmp.data_ptr(), cur.data_ptr(), b["n2"][0].data_ptr(),
+                                   b["n2"][1].data_ptr(), cur.data_ptr(), M, C, ctypes.c_float(1e-5)))
+            taps.append((cur, Hs, Ws, C))   # hooks sit on the last block of every stage (dpt.py:61-72)
+            if st["down"] is not None:
+                ops.append(_Launch("merge_gather", lib.soccdpt_patch_merge_gather_fwd, cur.data_ptr(), gat.data_ptr(), B, Hs, Ws, C))
+                M2 = B * L // 4
+                self._conv(plan, gat, st["down"]["w"], 1, 1, M2, 4 * C, 2 * C, 1, y=tmp)
+                nxt = buf(M2, 2 * C)
+                ops.append(_Launch("ln", lib.soccdpt_layernorm_fwd, tmp.data_ptr(), None, st["down"]["n"][0].data_ptr(),
+                                   st["down"]["n"][1].data_ptr(), nxt.data_ptr(), M2, 2 * C, ctypes.c_float(1e-5)))
+                cur = nxt
+        plan["taps"] = taps
+
+        # ---------------- decoder (dpt.py:152-172)
+        F = self.net.depth_net.features
+        lv = []
+        for i, (t, Hs, Ws, C) in enumerate(taps):
+            y, yr = buf(B, Hs, Ws, F), buf(B, Hs, Ws, F)
+            self._conv(plan, t, Wt["rn"][i], B, Hs, Ws, C, F, 3, y=y, y_relu=yr)
+            lv.append((y, yr, Hs, Ws))
+
+        def rcu(w, x, xr, H, Wd, res2=None, want_relu=False):
+            c1 = buf(B, H, Wd, F)
+            self._conv(plan, xr, w[0], B, H, Wd, F, F, 3, bias=w[1], act=_cabi.ACT_RELU, y=c1)
+            o = buf(B, H, Wd, F)
+            orl = buf(B, H, Wd, F) if want_relu else None
+            self._conv(plan, c1, w[2], B, H, Wd, F, F, 3, bias=w[3], res1=x, res2=res2, y=o, y_relu=orl)
+            return o, orl
+
+        path = None
+        for i in (4, 3, 2, 1):
+            fw = Wt["fusion"][i]
+            y, yr, H, Wd = lv[i - 1]
+            if path is None:
+                s, sr = y, yr
+            else:   # output = xs[0] + resConfUnit1(xs[1])   (blocks.py:476-479)
+                s, sr = rcu(fw["rcu1"], y, yr, H, Wd, res2=path, want_relu=True)
+            o, _ = rcu(fw["rcu2"], s, sr, H, Wd)
+            low = buf(B, H, Wd, F)
+            self._conv(plan, o, fw["out_w"], B, H, Wd, F, F, 1, bias=fw["out_b"], y=low)   # out_conv before the upsample
+            TH, TW = (lv[i - 2][2], lv[i - 2][3]) if i > 1 else (2 * H, 2 * Wd)
+            path = buf(B, TH, TW, F)
+            ops.append(_Launch("upsample", lib.soccdpt_upsample_bilinear_fwd, low.data_ptr(), path.data_ptr(), B, H, Wd, TH, TW, F))
+        PH, PW = 2 * lv[0][2], 2 * lv[0][3]
+        plan["path_1"] = path
+
+        # ---------------- heads
+        dh, sh = Wt["dh"], Wt["sh"]
+        d0 = buf(B, PH, PW, F // 2)
+        self._conv(plan, path, dh["w0"], B, PH, PW, F, F // 2, 3, bias=dh["b0"], y=d0)
+        d0u = buf(B, 2 * PH, 2 * PW, F // 2)
+        ops.append(_Launch("upsample", lib.soccdpt_upsample_bilinear_fwd, d0.data_ptr(), d0u.data_ptr(), B, PH, PW, 2 * PH, 2 * PW, F // 2))
+        depth = buf(B, 2 * PH, 2 * PW, dtype=torch.float32)
+        self._conv(plan, d0u, dh["w2"], B, 2 * PH, 2 * PW, F // 2, 32, 3, bias=dh["b2"], act=_cabi.ACT_RELU,
+                   proj=(dh["pw"], dh["pb"], depth, True))
+        P = Wt["num_classes"]
+        logits = buf(B, PH, PW, P, dtype=torch.float32)
+        self._conv(plan, path, sh["w0"], B, PH, PW, F, F, 3, bias=sh["b0"], act=_cabi.ACT_RELU,
+                   proj=(sh["pw"], sh["pb"], logits, False))
+        seg = buf(B, P, 2 * PH, 2 * PW, dtype=torch.float32)
+        ops.append(_Launch("seg_finish", lib.soccdpt_seg_finish_fwd, logits.data_ptr(), seg.data_ptr(), B, PH, PW, P, Wt["seg_act"]))
+        plan["depth"], plan["seg"] = depth, seg
+        return plan
+
+    # ------------------------------------------------------------------ run
+    def plan_for(self, B, dev):
+        if self._weights is None:
+            self._weights = self._pack(dev)
+        key = (B, str(dev))
+        if key not in self._plans:
+            self._plans[key] = self._build_plan(B, dev)
+        return self._plans[key]
+
+    def run(self, x):
+        """x: (B,3,S,S) fp32 CUDA tensor -> (inverse depth (B,S,S) f32, segmentation (B,C,S,S) f32).
+        The returned tensors are the plan's static output buffers (overwritten by the next call)."""
+        if not x.is_cuda:
+            raise _cabi.SoccdptError("soccdpt_b200 runs on CUDA devices only (no CPU fallback)")
+        B = x.shape[0]
+        plan = self.plan_for(B, x.device)
+        if tuple(x.shape[1:]) != (3, plan["img"], plan["img"]):
+            raise AssertionError("Input image size doesn't match model")
+        plan["x_in"].copy_(x, non_blocking=True)
+        stream = _cabi.current_stream()
+        for op in plan["ops"]:
+            op(stream)
+        return plan["depth"], plan["seg"]
+
+    def launches_per_forward(self, B, dev):
+        return len(self.plan_for(B, dev)["ops"])

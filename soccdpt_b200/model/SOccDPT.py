@@ -1,0 +1,258 @@
+"""Drop-in mirror of the reference's model API (SOccDPT/model/SOccDPT.py): same class names, constructor
+keywords, output tuple, attribute names and state_dict keys -- with the arithmetic on B200 kernels.
+
+    SOccDPT        base class: geometry constants + get_semantic_occupancy      (SOccDPT.py:133-463)
+    SOccDPT_V3     DPT depth net with return_features + segmentation head        (SOccDPT.py:626-685)
+    DepthNet/SegNet adaptors picking tuple element 0 / 1                         (SOccDPT.py:697-724)
+
+Deliberately preserved quirks of the reference: the returned inverse depth is clamped at
+1e-8; points #0,#1,#2 of every frame carry pc_scale/pc_shift; the occupancy grid is binary and, in the
+default ``occupancy_mode="reference_union"``, is the OR over the batch written to every batch element;
+planes i=0/j=0/k=0 are never filled; at batch 1 the segmentation output loses its batch dim.
+There is no CPU path: calling the model on CPU tensors raises.
+"""
+import os
+from typing import Type
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _cabi
+from ..engine import NetworkEngine
+from ..geometry import load_calib, make_geometry
+from .base_model import BaseModel
+from .dpt import DPTDepthModel
+
+cpu_device = torch.device("cpu")
+
+# reference: SOccDPT/datasets/bdd_helper.py:53-56 (not shipped with either repo)
+DEFAULT_CALIB = os.path.join("~", "Datasets", "Depth_Dataset_Bengaluru", "calibration", "pocoX3", "calib.yaml")
+
+default_depth_models = {
+    "dpt_swin2_base_384": "weights/dpt_swin2_base_384.pt",
+    "dpt_swin2_tiny_256": "weights/dpt_swin2_tiny_256.pt",
+    "dpt_hybrid_384": "weights/dpt_hybrid_384.pt",
+}
+model_types = default_depth_models.keys()
+
+DEPTH_l39icv3q = "checkpoints_pretrained/depth_dpt_hybrid/l39icv3q/checkpoint_epoch15.pth"  # reference default
+
+
+class ScaledTanh(nn.Module):
+    """0.5*tanh(x)+0.5 (reference scaled_tanh.py:8-10); marker module, evaluated in seg_finish_kernel."""
+
+
+class Interpolate(nn.Module):
+    """Marker for the x2 bilinear (align_corners=True) stage of the heads (reference blocks.py:239-273)."""
+
+    def __init__(self, scale_factor, mode, align_corners=False):
+        super().__init__()
+        self.scale_factor, self.mode, self.align_corners = scale_factor, mode, align_corners
+
+
+class SOccDPT(BaseModel):
+    def __init__(self, model_type="dpt_swin2_tiny_256", backbone="swin2t16_256", path=None, num_classes: int = 3,
+                 camera_intrinsics_yaml=DEFAULT_CALIB, point_compute_method="torch",
+                 grid_size=(256, 256, 32), scale=(2.0, 2.0, 0.666), shift=(0.0, 0.0, 0.0),
+                 pc_scale=(10000.0, 50000.0, 800.0), pc_shift=(55.0, -20.0, 15.0), correction_angle=(7.0, 0, 0),
+                 compute_occ=False, occupancy_mode="reference_union", **kwargs):
+        super(SOccDPT, self).__init__(**kwargs)
+        self.compute_occ = compute_occ
+        self.grid_size, self.scale, self.shift = grid_size, scale, shift
+        self.pc_scale, self.pc_shift, self.correction_angle = pc_scale, pc_shift, correction_angle
+        self.backbone, self.model_type, self.path = backbone, model_type, path
+        self.num_classes = num_classes
+        # SOccDPT.py:175-181: occupancy grid size in metres, fp32
+        self.occupancy_shape = np.array([float(grid_size[i] / scale[i]) for i in range(len(grid_size))], dtype=np.float32)
+        self.features = 256
+        assert point_compute_method in ("torch", "numpy")
+        self.point_compute_method = point_compute_method
+        assert occupancy_mode in ("reference_union", "per_frame")
+        self.occupancy_mode = occupancy_mode
+
+        self.camera_intrinsics_yaml = os.path.expanduser(camera_intrinsics_yaml)
+        self.cam_settings = load_calib(self.camera_intrinsics_yaml)
+        cs = self.cam_settings
+        self.DistCoef = np.array([cs["Camera.k1"], cs["Camera.k2"], cs["Camera.p1"], cs["Camera.p2"], cs.get("Camera.k3", 0)])
+        self.intrinsic_matrix = np.array([[cs["Camera.fx"], 0.0, cs["Camera.cx"]], [0.0, cs["Camera.fy"], cs["Camera.cy"]],
+                                          [0.0, 0.0, 1.0]])
+        self.fx, self.fy = self.intrinsic_matrix[0, 0], self.intrinsic_matrix[1, 1]
+        self.cx, self.cy = self.intrinsic_matrix[0, 2], self.intrinsic_matrix[1, 2]
+        self.width, self.height = cs["Camera.width"], cs["Camera.height"]
+        self.occupancy_conv = nn.Identity()
+        self._workspaces = {}
+
+    def forward(self, x: torch.Tensor):
+        assert False, "Not implemented, take input batch and produce inv_depth, segmentation and call " \
+                      "self.get_semantic_occupancy(inv_depth, segmentation)"
+
+    # ------------------------------------------------------------------ A8 / A9
+    def _geometry(self):
+        return make_geometry(self.fx, self.fy, self.cx, self.cy, self.height, self.width, self.num_classes,
+                             self.grid_size, self.occupancy_shape, self.pc_scale, self.pc_shift, self.correction_angle)
+
+    def _workspace(self, geom, B, mode, device):
+        lib = _cabi.load()
+        need = int(lib.soccdpt_voxel_workspace_bytes(ctypes_byref(geom), B, mode))
+        key = (str(device), need)
+        if key not in self._workspaces:
+            self._workspaces[key] = torch.empty(max(need, 16), dtype=torch.uint8, device=device)
+        return self._workspaces[key], need
+
+    def get_semantic_occupancy(self, inv_depth, segmentation):
+        """(B,h,w)|(B,1,h,w) inverse depth + (B,C,h,w) class scores -> the reference's 4-tuple
+        (inv_depth_up, segmentation_up, points_batched, occupancy_grid | None); SOccDPT.py:264-372."""
+        if not (inv_depth.is_cuda and segmentation.is_cuda):
+            raise _cabi.SoccdptError("soccdpt_b200 runs on CUDA devices only (no CPU fallback)")
+        lib = _cabi.load()
+        if inv_depth.dim() == 4:
+            inv_depth = inv_depth[:, 0]
+        inv_depth = inv_depth.to(torch.float32).contiguous()
+        segmentation = segmentation.to(torch.float32).contiguous()
+        B, h, w = inv_depth.shape
+        C = segmentation.shape[1]
+        assert C == self.num_classes and segmentation.shape[0] == B and tuple(segmentation.shape[2:]) == (h, w)
+        dev = inv_depth.device
+        H, Wd = int(self.height), int(self.width)
+        geom = self._geometry()
+        mode = _cabi.OCC_PER_FRAME if self.occupancy_mode == "per_frame" else _cabi.OCC_REFERENCE_UNION
+        inv_up = torch.empty((B, H, Wd), dtype=torch.float32, device=dev)
+        seg_up = torch.empty((B, C, H, Wd), dtype=torch.float32, device=dev)
+        points = torch.empty((B, H, Wd, 3), dtype=torch.float32, device=dev)
+        grid, ws, need = None, None, 0
+        if self.compute_occ:
+            G = self.grid_size
+            grid = torch.empty((B, G[0], G[1], G[2], C), dtype=torch.float32, device=dev)
+            ws, need = self._workspace(geom, B, mode, dev)
+        rc = lib.soccdpt_postprocess_fwd(
+            _cabi.ptr(inv_depth), _cabi.ptr(segmentation), B, h, w, ctypes_byref(geom), _cabi.ptr(inv_up), _cabi.ptr(seg_up),
+            _cabi.ptr(points), _cabi.ptr(grid), mode, _cabi.ptr(ws), need, _cabi.current_stream())
+        _cabi.check(rc, "soccdpt_postprocess_fwd")
+        # the reference's .squeeze() calls (SOccDPT.py:276,282-285)
+        seg_out = seg_up.squeeze()
+        inv_out = inv_up.squeeze()
+        if inv_out.dim() == 2:
+            inv_out = inv_out.unsqueeze(0)
+        return inv_out, seg_out, points, grid
+
+    def voxelize(self, inv_depth_up, segmentation_up):
+        """Standalone voxeliser on maps already at camera resolution (BASELINE config 5): clamps
+        ``inv_depth_up`` IN PLACE like the reference and returns (points, occupancy_grid | None)."""
+        if not (inv_depth_up.is_cuda and segmentation_up.is_cuda):
+            raise _cabi.SoccdptError("soccdpt_b200 runs on CUDA devices only (no CPU fallback)")
+        lib = _cabi.load()
+        assert inv_depth_up.dtype == torch.float32 and inv_depth_up.is_contiguous()
+        seg = segmentation_up.to(torch.float32).contiguous()
+        B, H, Wd = inv_depth_up.shape
+        assert (H, Wd) == (int(self.height), int(self.width)) and seg.shape == (B, self.num_classes, H, Wd)
+        dev = inv_depth_up.device
+        geom = self._geometry()
+        mode = _cabi.OCC_PER_FRAME if self.occupancy_mode == "per_frame" else _cabi.OCC_REFERENCE_UNION
+        points = torch.empty((B, H, Wd, 3), dtype=torch.float32, device=dev)
+        grid, ws, need = None, None, 0
+        if self.compute_occ:
+            G = self.grid_size
+            grid = torch.empty((B, G[0], G[1], G[2], self.num_classes), dtype=torch.float32, device=dev)
+            ws, need = self._workspace(geom, B, mode, dev)
+        rc = lib.soccdpt_voxelize_fwd(_cabi.ptr(inv_depth_up), _cabi.ptr(seg), B, ctypes_byref(geom), _cabi.ptr(points),
+                                      _cabi.ptr(grid), mode, _cabi.ptr(ws), need, _cabi.current_stream())
+        _cabi.check(rc, "soccdpt_voxelize_fwd")
+        return points, grid
+
+
+def ctypes_byref(s):
+    import ctypes
+    return ctypes.byref(s)
+
+
+class SOccDPT_V3(SOccDPT):
+    def __init__(self, sigmoid=True, load_depth: str = DEPTH_l39icv3q, **kwargs):
+        super(SOccDPT_V3, self).__init__(**kwargs)
+        from .loader import load_model
+
+        depth_model_weights = load_depth
+        if depth_model_weights is None:
+            depth_model_weights = default_depth_models[self.model_type]
+        print("Loading depth net")
+        self.depth_net = load_model(DPTDepthModel, dict(non_negative=True, return_features=True), cpu_device,
+                                    depth_model_weights, self.model_type)
+        self.depth_net.return_features = True
+        self.pretrained = self.depth_net.pretrained     # alias: duplicated state_dict prefix, as in the reference
+
+        activation = nn.Sigmoid() if sigmoid else ScaledTanh()
+        self.seg_head = nn.Sequential(
+            nn.Conv2d(self.features, self.features, kernel_size=3, padding=1, bias=False),
+            nn.BatchNorm2d(self.features),
+            nn.ReLU(True),
+            nn.Dropout(0.1, False),
+            nn.Conv2d(self.features, self.num_classes, kernel_size=1),
+            Interpolate(scale_factor=2, mode="bilinear", align_corners=True),
+            activation,
+        )
+        self._engine = None
+        self.load_net(self.path)
+
+    # weights changed -> repack on the next forward
+    def _invalidate(self):
+        if getattr(self, "_engine", None) is not None:
+            self._engine.invalidate()
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._invalidate()
+        return out
+
+    def engine(self, conv_impl=None):
+        if self._engine is None or (conv_impl is not None and self._engine.conv_impl != conv_impl):
+            self._engine = NetworkEngine(self, conv_impl or os.environ.get("SOCCDPT_CONV_IMPL", "tcgen05"))
+        return self._engine
+
+    def network(self, x):
+        """image -> (inverse depth (B,h,w) f32, segmentation (B,C,h,w) f32), i.e. depth_net + seg_head
+        (SOccDPT.py:682-683).  Returned tensors are static engine buffers."""
+        if self.training:
+            raise _cabi.SoccdptError("soccdpt_b200 implements the inference path only: call net.eval() first")
+        return self.engine().run(x)
+
+    def forward(self, x: torch.Tensor):
+        inv_depth, segmentation = self.network(x)
+        return self.get_semantic_occupancy(inv_depth, segmentation)
+
+
+SOccDPT_versions = {3: SOccDPT_V3}
+
+
+class DepthNet:
+    def __init__(self, net: Type[SOccDPT]) -> None:
+        self.net = net
+
+    def __call__(self, x: torch.Tensor):
+        y_disp_pred, _, _, _ = self.net(x)
+        return y_disp_pred
+
+    def eval(self):
+        self.net.eval()
+
+    def train(self):
+        self.net.train()
+
+
+class SegNet:
+    def __init__(self, net: Type[SOccDPT]) -> None:
+        self.net = net
+
+    def __call__(self, x: torch.Tensor):
+        _, y_seg_pred, _, _ = self.net(x)
+        return y_seg_pred
+
+    def eval(self):
+        self.net.eval()
+
+    def train(self):
+        self.net.train()

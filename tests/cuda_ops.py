@@ -1,0 +1,93 @@
+"""Thin tensor-level wrappers over the C-ABI used by the GPU tests (pointers in, pointers out)."""
+import ctypes
+
+import torch
+
+from soccdpt_b200 import _cabi
+
+
+def _s():
+    return _cabi.current_stream()
+
+
+def conv(x, w, bias=None, act=0, res1=None, res2=None, want_y=True, want_relu=False, proj=None, impl="tcgen05"):
+    """x (N,H,W,Cin) bf16; w (Cout,KH*KW,Cin) bf16 packed. Returns (y, y_relu, proj_out)."""
+    lib = _cabi.load()
+    N, H, W, Cin = x.shape
+    Cout, taps, _ = w.shape
+    K = 3 if taps == 9 else 1
+    c = _cabi.Conv()
+    c.x, c.wgt = x.data_ptr(), w.data_ptr()
+    c.bias = bias.data_ptr() if bias is not None else None
+    c.res1 = res1.data_ptr() if res1 is not None else None
+    c.res2 = res2.data_ptr() if res2 is not None else None
+    y = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device=x.device) if want_y else None
+    yr = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device=x.device) if want_relu else None
+    c.y = y.data_ptr() if y is not None else None
+    c.y_relu = yr.data_ptr() if yr is not None else None
+    c.N, c.H, c.W, c.Cin, c.Cout, c.KH, c.KW, c.act = N, H, W, Cin, Cout, K, K, act
+    po = None
+    if proj is not None:
+        pw, pb, relu = proj
+        po = torch.empty((N, H, W, pw.shape[0]), dtype=torch.float32, device=x.device)
+        c.proj_w, c.proj_b, c.proj_out, c.proj_n, c.proj_relu = pw.data_ptr(), pb.data_ptr(), po.data_ptr(), pw.shape[0], int(relu)
+    fn = lib.soccdpt_conv_fwd if impl == "tcgen05" else lib.soccdpt_conv_ref_fwd
+    _cabi.check(fn(ctypes.byref(c), _s()), "conv")
+    return y, yr, po
+
+
+def pack_conv_weight(w):
+    """(Cout,Cin,KH,KW) f32 -> (Cout,KH*KW,Cin) bf16"""
+    Cout, Cin, KH, KW = w.shape
+    return w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin).to(torch.bfloat16).contiguous()
+
+
+def layernorm(t, res, g, b, eps=1e-5):
+    lib = _cabi.load()
+    y = torch.empty_like(t)
+    rows, C = t.shape
+    _cabi.check(lib.soccdpt_layernorm_fwd(t.data_ptr(), res.data_ptr() if res is not None else None, g.data_ptr(),
+                                          b.data_ptr(), y.data_ptr(), rows, C, eps, _s()), "layernorm")
+    return y
+
+
+def patch_embed(x, w, b, g, be):
+    lib = _cabi.load()
+    B, _, H, W = x.shape
+    E = w.shape[0]
+    out = torch.empty((B, (H // 4) * (W // 4), E), dtype=torch.bfloat16, device=x.device)
+    _cabi.check(lib.soccdpt_patch_embed_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), g.data_ptr(), be.data_ptr(),
+                                            out.data_ptr(), B, H, W, E, _s()), "patch_embed")
+    return out
+
+
+def merge_gather(x):
+    lib = _cabi.load()
+    B, H, W, C = x.shape
+    y = torch.empty((B, H // 2, W // 2, 4 * C), dtype=torch.bfloat16, device=x.device)
+    _cabi.check(lib.soccdpt_patch_merge_gather_fwd(x.data_ptr(), y.data_ptr(), B, H, W, C, _s()), "merge")
+    return y
+
+
+def upsample(x, H, W):
+    lib = _cabi.load()
+    N, h, w, C = x.shape
+    y = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=x.device)
+    _cabi.check(lib.soccdpt_upsample_bilinear_fwd(x.data_ptr(), y.data_ptr(), N, h, w, H, W, C, _s()), "upsample")
+    return y
+
+
+def seg_finish(logits, act):
+    lib = _cabi.load()
+    N, h, w, P = logits.shape
+    y = torch.empty((N, P, 2 * h, 2 * w), dtype=torch.float32, device=logits.device)
+    _cabi.check(lib.soccdpt_seg_finish_fwd(logits.data_ptr(), y.data_ptr(), N, h, w, P, act, _s()), "seg_finish")
+    return y
+
+
+def window_attention(qkv, biasT, scale, B, Hs, Ws, C, heads, ws, shift):
+    lib = _cabi.load()
+    out = torch.empty((B, Hs * Ws, C), dtype=torch.bfloat16, device=qkv.device)
+    _cabi.check(lib.soccdpt_window_attention_fwd(qkv.data_ptr(), biasT.data_ptr(), scale.data_ptr(), out.data_ptr(), B, Hs,
+                                                 Ws, C, heads, ws, shift, _s()), "window_attention")
+    return out

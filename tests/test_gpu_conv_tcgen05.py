@@ -1,0 +1,78 @@
+"""The tcgen05/TMEM/TMA implicit-GEMM kernel against (a) a PyTorch fp32 reference of the same op and
+(b) the CUDA-core reference kernel, over every tile geometry the network uses (incl. M/K tails)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cuda_ops as K
+
+pytestmark = pytest.mark.gpu
+
+# (N, H, W, Cin, Cout, k, act, bias, nres, relu_out, proj_n)
+CASES = [
+    (1, 1, 256, 64, 64, 1, 0, False, 0, False, 0),       # smallest GEMM, 2 full tiles
+    (1, 1, 4096, 96, 288, 1, 0, True, 0, False, 0),      # S0 qkv: K tail (96 = 64 + 32), N = 2 x 144
+    (1, 1, 64, 768, 2304, 1, 0, True, 0, False, 0),      # S3 qkv at B=1: M tail (64 < 128)
+    (1, 1, 200, 3072, 768, 1, 0, True, 0, False, 0),     # fc2, M tail, long K
+    (1, 1, 512, 384, 1536, 1, 2, True, 0, False, 0),     # fc1 + GELU
+    (1, 1, 128, 1536, 768, 1, 0, False, 0, False, 0),    # patch-merge reduction (no bias)
+    (2, 8, 8, 768, 256, 3, 0, False, 0, True, 0),        # layer4_rn: 2 images per tile
+    (3, 8, 8, 256, 256, 3, 1, True, 0, False, 0),        # 8x8 level, odd batch
+    (2, 16, 16, 256, 256, 3, 0, True, 2, True, 0),       # RCU conv2 with two residuals + relu copy
+    (2, 32, 32, 256, 256, 3, 1, True, 0, False, 0),
+    (1, 64, 64, 96, 256, 3, 0, False, 0, True, 0),       # layer1_rn: Cin = 96
+    (1, 64, 64, 256, 256, 1, 0, True, 0, False, 0),      # out_conv 1x1
+    (1, 128, 128, 256, 128, 3, 0, True, 0, False, 0),    # depth head conv 0
+    (1, 256, 256, 128, 32, 3, 1, True, 0, False, 1),     # depth head conv 2 + fused 32->1
+    (1, 128, 128, 256, 256, 3, 1, True, 0, False, 3),    # seg head + fused 256->3
+    (2, 12, 12, 1024, 256, 3, 0, False, 0, False, 0),    # swin2_base_384 levels (non power of two)
+    (1, 24, 24, 256, 256, 3, 1, True, 1, False, 0),
+    (1, 48, 48, 256, 256, 3, 0, True, 0, False, 0),
+    (1, 96, 96, 128, 256, 3, 0, False, 0, False, 0),
+    (1, 192, 192, 256, 128, 3, 0, True, 0, False, 0),
+    (1, 7, 150, 64, 48, 3, 0, True, 0, False, 0),        # W tail inside a row (150 = 128 + 22)
+]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,act,bias,nres,relu_out,proj_n", CASES)
+def test_tcgen05_conv(N, H, W, Cin, Cout, k, act, bias, nres, relu_out, proj_n):
+    g = torch.Generator().manual_seed(N * 1000 + H * 10 + Cin + Cout)
+    x = torch.randn(N, H, W, Cin, generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).bfloat16()
+    b = (torch.randn(Cout, generator=g) * 0.2) if bias else None
+    rs = [torch.randn(N, H, W, Cout, generator=g).bfloat16() for _ in range(nres)]
+    proj = None
+    if proj_n:
+        proj = ((torch.randn(proj_n, Cout, generator=g) * 0.1).cuda(), torch.randn(proj_n, generator=g).cuda(), proj_n == 1)
+    args = dict(bias=b.cuda() if bias else None, act=act, res1=rs[0].cuda() if nres > 0 else None,
+                res2=rs[1].cuda() if nres > 1 else None, want_y=proj_n == 0, want_relu=relu_out, proj=proj)
+    wp = K.pack_conv_weight(w.float()).cuda()
+    y, yr, po = K.conv(x.cuda(), wp, impl="tcgen05", **args)
+    y2, yr2, po2 = K.conv(x.cuda(), wp, impl="ref", **args)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=k // 2).permute(0, 2, 3, 1)
+    ref = F.relu(ref) if act == 1 else (F.gelu(ref) if act == 2 else ref)
+    for r in rs:
+        ref = ref + r.float()
+    tol = dict(rtol=2e-2, atol=2e-2)
+    if y is not None:
+        assert torch.allclose(y.float().cpu(), ref, **tol), (y.float().cpu() - ref).abs().max()
+        assert torch.allclose(y.float(), y2.float(), rtol=1e-2, atol=1e-2)
+    if yr is not None:
+        assert torch.allclose(yr.float().cpu(), F.relu(ref), **tol)
+    if po is not None:
+        pref = ref @ proj[0].cpu().t() + proj[1].cpu()
+        pref = F.relu(pref) if proj[2] else pref
+        assert torch.allclose(po.cpu(), pref, rtol=1e-3, atol=2e-3), (po.cpu() - pref).abs().max()
+        assert torch.allclose(po, po2, rtol=1e-3, atol=1e-3)
+
+
+def test_tcgen05_conv_is_deterministic_and_reentrant():
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 32, 32, 256, generator=g).bfloat16().cuda()
+    w = K.pack_conv_weight(torch.randn(256, 256, 3, 3, generator=g) / 48).cuda()
+    a = K.conv(x, w)[0]
+    for _ in range(3):
+        assert torch.equal(K.conv(x, w)[0], a)

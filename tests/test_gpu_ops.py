@@ -1,0 +1,141 @@
+"""GPU numerics of the glue kernels against plain PyTorch fp32 references of the same op
+(bf16 storage -> tolerances are a couple of bf16 ulps = 2^-8 relative)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cuda_ops as K
+import ref_env
+
+pytestmark = pytest.mark.gpu
+BF = dict(rtol=2e-2, atol=2e-2)
+
+
+def _g(seed=0):
+    return torch.Generator().manual_seed(seed)
+
+
+@pytest.mark.parametrize("rows,C,res", [(1000, 96, True), (77, 768, True), (64, 1536, False), (5, 2048, False)])
+def test_layernorm_residual(rows, C, res):
+    g = _g(1)
+    t = torch.randn(rows, C, generator=g) * 2 + 0.3
+    r = torch.randn(rows, C, generator=g) if res else None
+    w, b = torch.rand(C, generator=g) + 0.5, torch.rand(C, generator=g) - 0.5
+    tb, rb = t.bfloat16(), (r.bfloat16() if res else None)
+    y = K.layernorm(tb.cuda(), rb.cuda() if res else None, w.cuda(), b.cuda())
+    ref = F.layer_norm(tb.float(), (C,), w, b, 1e-5) + (rb.float() if res else 0)
+    assert torch.allclose(y.float().cpu(), ref, **BF)
+
+
+@pytest.mark.parametrize("B,S,E", [(2, 64, 96), (1, 32, 128)])
+def test_patch_embed(B, S, E):
+    g = _g(2)
+    x = torch.randn(B, 3, S, S, generator=g)
+    w, b = torch.randn(E, 3, 4, 4, generator=g) * 0.2, torch.randn(E, generator=g) * 0.1
+    lw, lb = torch.rand(E, generator=g) + 0.5, torch.rand(E, generator=g) - 0.5
+    y = K.patch_embed(x.cuda(), w.reshape(E, -1).contiguous().cuda(), b.cuda(), lw.cuda(), lb.cuda())
+    ref = F.layer_norm(F.conv2d(x, w, b, stride=4).flatten(2).transpose(1, 2), (E,), lw, lb, 1e-5)
+    assert torch.allclose(y.float().cpu(), ref, **BF)
+
+
+def test_patch_merge_gather():
+    x = torch.randn(2, 8, 12, 16, generator=_g(3)).bfloat16()
+    y = K.merge_gather(x.cuda())
+    ref = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
+    assert torch.equal(y.cpu(), ref)
+
+
+@pytest.mark.parametrize("h,w,H,W", [(8, 8, 16, 16), (16, 16, 32, 32), (12, 12, 24, 24), (5, 7, 9, 20)])
+def test_upsample_bilinear_align_corners(h, w, H, W):
+    x = torch.randn(2, h, w, 32, generator=_g(4)).bfloat16()
+    y = K.upsample(x.cuda(), H, W)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    assert torch.allclose(y.float().cpu(), ref, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("act", [0, 1])
+def test_seg_finish(act):
+    lg = torch.randn(2, 16, 16, 3, generator=_g(5)) * 3
+    y = K.seg_finish(lg.cuda(), act)
+    up = F.interpolate(lg.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
+    ref = torch.sigmoid(up) if act == 0 else 0.5 * torch.tanh(up) + 0.5
+    assert torch.allclose(y.cpu(), ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("res,ws,target_ws,heads,shift_block", [
+    (32, 16, 16, 3, True), (16, 16, 16, 12, True), (8, 8, 16, 24, False), (24, 12, 12, 4, True), (32, 8, 8, 2, False)])
+def test_window_attention_vs_timm_restatement(res, ws, target_ws, heads, shift_block):
+    """against the oracle's SwinTransformerBlock._attn minus the proj (roll, partition, cosine attention,
+    cpb bias, shift mask, softmax, PV, reverse)."""
+    ref_env.enable_shim()
+    from timm.models.swin_transformer_v2 import SwinTransformerBlock
+    from soccdpt_b200.model.encoder import relative_position_bias
+    C = heads * 32
+    torch.manual_seed(0)
+    blk = SwinTransformerBlock(C, (res, res), heads, target_ws, target_ws // 2 if shift_block else 0, 4.0, 0).eval()
+    g = _g(6)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.5 if p.dim() > 1 else 0.2))
+        blk.attn.logit_scale.copy_(torch.rand(heads, 1, 1, generator=g) * 2 + 1.5)
+        blk.attn.proj.weight.copy_(torch.eye(C))
+        blk.attn.proj.bias.zero_()
+    assert blk.window_size[0] == ws
+    B = 2
+    x = torch.randn(B, res * res, C, generator=g).bfloat16().float()
+    a = blk.attn
+    with torch.no_grad():
+        qkv = F.linear(x, a.qkv.weight, torch.cat((a.q_bias, a.k_bias, a.v_bias))).bfloat16()
+        # reference path on the SAME bf16-rounded qkv: temporarily make qkv an identity on a packed input
+        ref = _attn_from_qkv(blk, qkv.float(), B)
+        bias = relative_position_bias(a, ws, 0)
+        scale = torch.clamp(a.logit_scale, max=math.log(100.0)).exp().reshape(-1)
+    out = K.window_attention(qkv.cuda(), bias.transpose(1, 2).contiguous().cuda(), scale.contiguous().cuda(), B, res, res, C,
+                             heads, ws, blk.shift_size[0])
+    assert torch.allclose(out.float().cpu(), ref, rtol=2e-2, atol=2e-2), (out.float().cpu() - ref).abs().max()
+
+
+def _attn_from_qkv(blk, qkv, B):
+    """SwinTransformerBlock._attn with the qkv projection already applied (qkv: (B, L, 3C))."""
+    from timm.models.swin_transformer_v2 import window_partition, window_reverse
+    H, W = blk.input_resolution
+    C3 = qkv.shape[-1]
+    C = C3 // 3
+    a = blk.attn
+    x = qkv.view(B, H, W, C3)
+    if any(blk.shift_size):
+        x = torch.roll(x, shifts=(-blk.shift_size[0], -blk.shift_size[1]), dims=(1, 2))
+    xw = window_partition(x, blk.window_size).view(-1, blk.window_area, C3)
+    B_, N, _ = xw.shape
+    q, k, v = xw.reshape(B_, N, 3, a.num_heads, -1).permute(2, 0, 3, 1, 4).unbind(0)
+    attn = F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1)
+    attn = attn * torch.clamp(a.logit_scale, max=math.log(100.0)).exp()
+    attn = attn + a.relative_position_bias().unsqueeze(0)
+    if blk.attn_mask is not None:
+        nW = blk.attn_mask.shape[0]
+        attn = attn.view(B_ // nW, nW, a.num_heads, N, N) + blk.attn_mask.unsqueeze(1).unsqueeze(0)
+        attn = attn.view(-1, a.num_heads, N, N)
+    o = (attn.softmax(-1) @ v).transpose(1, 2).reshape(B_, N, C)
+    o = window_reverse(o.view(-1, blk.window_size[0], blk.window_size[1], C), blk.window_size, blk.input_resolution)
+    if any(blk.shift_size):
+        o = torch.roll(o, shifts=blk.shift_size, dims=(1, 2))
+    return o.reshape(B, H * W, C)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,K3", [(2, 8, 8, 64, 32, True), (1, 5, 9, 24, 16, True), (1, 1, 300, 96, 288, False)])
+def test_conv_ref_kernel_vs_torch(N, H, W, Cin, Cout, K3):
+    g = _g(7)
+    k = 3 if K3 else 1
+    x = torch.randn(N, H, W, Cin, generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).bfloat16()
+    b = torch.randn(Cout, generator=g) * 0.1
+    r1 = torch.randn(N, H, W, Cout, generator=g).bfloat16()
+    pw, pb = torch.randn(3, Cout, generator=g) * 0.1, torch.randn(3, generator=g)
+    y, yr, po = K.conv(x.cuda(), K.pack_conv_weight(w.float()).cuda(), b.cuda(), act=1, res1=r1.cuda(), want_relu=True,
+                       proj=(pw.cuda(), pb.cuda(), True), impl="ref")
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=k // 2)).permute(0, 2, 3, 1) + r1.float()
+    assert torch.allclose(y.float().cpu(), ref, **BF)
+    assert torch.allclose(yr.float().cpu(), F.relu(ref), **BF)
+    assert torch.allclose(po.cpu(), F.relu(ref @ pw.t() + pb), rtol=1e-3, atol=1e-3)

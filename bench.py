@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the SOccDPT inference hot path (BASELINE.json metric):
+
+    frames/s, SOccDPT-V3 dpt_swin2_tiny_256, image -> (inverse depth, segmentation, points, occupancy grid)
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 64] [--impl ours|reference]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); frames are batch-sharded, every rank
+runs the same per-GPU batch (weak scaling), there is no collective on the data path.  A "step" is one
+``net(x)`` call on one batch of synthetic frames (random seeded weights, randn images, the synthetic
+1920x1080 pinhole camera of SURVEY.md 8d).  Rank 0 prints ONE JSON line.
+
+  value     frames/s with the input batch already resident in HBM (CUDA events, max over ranks)
+  e2e       frames/s through the same public call with the batch in PINNED HOST memory: every step
+            copies the images host->device and reads the step's result back device->host
+            (network-resolution inverse depth + class maps, and the occupancy grid of the call -- in the
+            reference's semantics all B grid copies are identical, one copy is read)
+  roofline  tensor-pipe roofline of the dominant kernel (conv_tcgen05_kernel): algorithmic FLOPs of all its
+            launches in a step / their CUDA-event time, vs MEASURED_PEAKS.json bf16 sustained
+  roofline_voxeliser   HBM roofline of the post-processing kernels (compulsory bytes / event time)
+  cpu_baseline         the oracle port of the reference (oracle/soccdpt_oracle.py) on the host cores, bounded sample
+
+``--impl reference`` times the reference's algorithm on the host CPU (the oracle port; the unmodified
+reference is a Python package that imports timm==0.6.12, which is absent from the image and the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "frames/s SOccDPT-V3 swin2_tiny_256 image->occupancy"
+MODEL_TYPE = "dpt_swin2_tiny_256"
+FLOPS_PER_FRAME = 78.8e9          # SURVEY.md 8d / BASELINE.md section 3 (2*MAC, analytic)
+CAM_H, CAM_W, GRID, NCLS = 1080, 1920, (256, 256, 32), 3
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_net(device, batch_hint=None):
+    from soccdpt_b200 import SOccDPT_versions, load_model
+    from soccdpt_b200.synthetic import seeded_state_dict, write_calib_yaml
+    yml = write_calib_yaml(os.path.join("/tmp", f"soccdpt_bench_calib_{os.getpid()}.yaml"))
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = load_model(arch=SOccDPT_versions[3],
+                         model_kwargs=dict(load_depth=False, num_classes=NCLS, sigmoid=True, compute_occ=True,
+                                           camera_intrinsics_yaml=yml, model_type=MODEL_TYPE),
+                         device=torch.device("cpu"), model_path=None, model_type=MODEL_TYPE)
+    sd = seeded_state_dict(net.state_dict(), 0)
+    net.load_state_dict(sd, strict=True)
+    net.to(device).eval()
+    return net, sd
+
+
+def cpu_reference_fps(sd, frames, reps, threads=None):
+    """The reference's algorithm on the host cores (oracle port), frames/s over `reps` batches of `frames`."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import soccdpt_oracle as O
+    from soccdpt_b200.synthetic import synthetic_frames
+    if threads:
+        torch.set_num_threads(threads)
+    orc = O.OracleV3(sd, MODEL_TYPE, sigmoid=True, geom=O.Geometry(), compute_occ=True)
+    x = synthetic_frames(frames, 256, 0)
+    orc(x[:1])                                    # warm-up (thread pools, allocator)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc(x)
+        times.append(time.perf_counter() - t0)
+    return frames / statistics.median(times), times
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from soccdpt_b200.synthetic import seeded_state_dict
+    sd = _tiny_state_dict()
+    frames = args.ref_frames
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import soccdpt_oracle as O
+    from soccdpt_b200.synthetic import synthetic_frames
+    orc = O.OracleV3(sd, MODEL_TYPE, sigmoid=True, geom=O.Geometry(), compute_occ=True)
+    x = synthetic_frames(frames, 256, 0)
+    for _ in range(args.warmup):
+        orc(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc(x)
+    dt = time.perf_counter() - t0
+    fps = frames * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"SOccDPT V3 {MODEL_TYPE} image->depth+seg+points+occupancy, camera {CAM_W}x{CAM_H}, "
+                               f"grid {GRID}, {frames} frames per step on the host CPU (oracle port of the reference)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} steps x {frames} frames, fp32, torch {torch.__version__} CPU + C voxeliser"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _tiny_state_dict():
+    """Seeded weights without building the CUDA model (reference arm)."""
+    from soccdpt_b200 import SOccDPT_versions, load_model
+    from soccdpt_b200.synthetic import seeded_state_dict, write_calib_yaml
+    import contextlib
+    import io
+    yml = write_calib_yaml(os.path.join("/tmp", f"soccdpt_bench_calib_{os.getpid()}.yaml"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = load_model(arch=SOccDPT_versions[3],
+                         model_kwargs=dict(load_depth=False, num_classes=NCLS, sigmoid=True, compute_occ=True,
+                                           camera_intrinsics_yaml=yml, model_type=MODEL_TYPE),
+                         device=torch.device("cpu"), model_path=None, model_type=MODEL_TYPE)
+    return seeded_state_dict(net.state_dict(), 0)
+
+
+def conv_flops(c):
+    return 2.0 * c.N * c.H * c.W * c.Cout * c.KH * c.KW * c.Cin + 2.0 * c.N * c.H * c.W * c.Cout * c.proj_n
+
+
+def instrumented_pass(net, x, reps):
+    """Per-kernel CUDA-event times of one step (events bracket every launch on the launching stream)."""
+    from soccdpt_b200 import _cabi
+    eng = net.engine()
+    plan = eng.plan_for(x.shape[0], x.device)
+    stream = _cabi.current_stream()
+    agg = {}
+    for _ in range(reps):
+        plan["x_in"].copy_(x)
+        evs = []
+        for op in plan["ops"]:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            op(stream)
+            e.record()
+            evs.append((op, s, e))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        net.get_semantic_occupancy(plan["depth"], plan["seg"])
+        e.record()
+        torch.cuda.synchronize()
+        for op, a, b in evs:
+            name = op.name
+            if name == "conv":
+                name = "conv_tcgen05_kernel"
+            d = agg.setdefault(name, {"ms": 0.0, "launches": 0, "flops": 0.0})
+            d["ms"] += a.elapsed_time(b)
+            d["launches"] += 1
+            if op.name == "conv":
+                d["flops"] += conv_flops(op.args[0]._obj)
+        d = agg.setdefault("postprocess(unproject_scatter+grid_expand)", {"ms": 0.0, "launches": 0, "flops": 0.0})
+        d["ms"] += s.elapsed_time(e)
+        d["launches"] += 2
+    for d in agg.values():
+        d["ms"] /= reps
+        d["launches"] //= reps
+        d["flops"] /= reps
+    return agg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step (BASELINE config 2: 64)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-frames", type=int, default=2, help="frames per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from soccdpt_b200 import _cabi
+    from soccdpt_b200.synthetic import synthetic_frames
+    net, sd = build_net(dev)
+    B = args.batch
+    x_host = synthetic_frames(B, 256, seed=rank).pin_memory()
+    x = x_host.to(dev)
+
+    def step_resident():
+        return net(x)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            out = step_resident()
+        barrier()
+        launches0 = _cabi.launch_count()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(args.steps):
+            out = step_resident()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = _cabi.launch_count() - launches0
+
+        # ---- end to end: pinned host images in, results back to pinned host buffers, every step
+        eng_plan = net.engine().plan_for(B, dev)
+        d_host = torch.empty((B, 256, 256), dtype=torch.float32).pin_memory()
+        s_host = torch.empty((B, NCLS, 256, 256), dtype=torch.float32).pin_memory()
+        g_host = torch.empty((GRID[0], GRID[1], GRID[2], NCLS), dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            xd = x_host.to(dev, non_blocking=True)
+            o = net(xd)
+            d_host.copy_(eng_plan["depth"], non_blocking=True)
+            s_host.copy_(eng_plan["seg"], non_blocking=True)
+            g_host.copy_(o[3][0], non_blocking=True)
+            return o
+
+        for _ in range(3):
+            step_e2e()
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for _ in range(args.steps):
+            step_e2e()
+        e2.record()
+        barrier()
+        ms_e2e = s2.elapsed_time(e2)
+        h2d = x_host.numel() * 4
+        d2h = (d_host.numel() + s_host.numel() + g_host.numel()) * 4
+
+        agg = instrumented_pass(net, x, 3) if rank == 0 else None
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, tf_sustained, tf_burst, peak_kind = _peaks()
+    frames_total = B * world * args.steps
+    value = frames_total / (ms * 1e-3)
+    e2e_value = frames_total / (ms_e2e * 1e-3)
+
+    conv = agg["conv_tcgen05_kernel"]
+    conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+    step_kernel_ms = sum(d["ms"] for d in agg.values())
+    pp = agg["postprocess(unproject_scatter+grid_expand)"]
+    pp_bytes = B * (4 * 256 * 256 * (1 + NCLS) + 4 * CAM_H * CAM_W * (1 + NCLS) + 12 * CAM_H * CAM_W
+                    + 4 * GRID[0] * GRID[1] * GRID[2] * NCLS)
+    pp_gbs = pp_bytes / (pp["ms"] * 1e-3) / 1e9
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        fps, times = cpu_reference_fps(sd, frames=2, reps=3)
+        cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "3 x 2 frames of the same workload, fp32 oracle port (torch CPU + C voxeliser), median"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"SOccDPT V3 {MODEL_TYPE} inference, batch {B} synthetic 256x256 frames per GPU, "
+                               f"image->depth+seg+points+occupancy (camera {CAM_W}x{CAM_H}, grid {GRID}, fp32 outputs 83 MB/frame)",
+                   "per_gpu_batch": B, "parallelism": f"frame-sharded dp{world}, no data-path collective",
+                   "l2": "per-step working set (>5 GB of outputs + activations) exceeds the 126 MB L2; no explicit flush",
+                   "weights": "seeded random init (soccdpt_b200.synthetic.seeded_state_dict, seed 0)"},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "conv_tcgen05_kernel", "achieved": conv_tflops, "peak": tf_sustained,
+                     "unit": "TFLOP/s", "frac": conv_tflops / tf_sustained, "traffic": None,
+                     "launches_per_step": conv["launches"], "ms_per_step": conv["ms"],
+                     "share_of_step_kernel_time": conv["ms"] / step_kernel_ms, "peak_source": peak_kind + " (sustained bf16)"},
+        "roofline_voxeliser": {"bound": "hbm", "kernel": "unproject_scatter_kernel+grid_expand_kernel", "achieved": pp_gbs,
+                               "peak": hbm_peak, "unit": "GB/s", "frac": pp_gbs / hbm_peak, "ms_per_step": pp["ms"],
+                               "bytes_per_step": pp_bytes, "peak_source": peak_kind},
+        "model_tflops": value / world * FLOPS_PER_FRAME / 1e12,
+        "model_frac_of_peak": value / world * FLOPS_PER_FRAME / 1e12 / tf_sustained,
+        "kernels_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -118,10 +118,11 @@ int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream);
 int soccdpt_conv_ref_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream);
 
 /* ------------------------------------------------------------------ encoder pieces (timm SwinV2 0.6.12)
- * timm PatchEmbed: conv4x4 s4 + bias + LayerNorm (eps 1e-5); x f32 NCHW -> tokens bf16 [B,H/4*W/4,E] */
+ * timm PatchEmbed: conv4x4 s4 + bias + LayerNorm (eps 1e-5); x f32 NCHW -> tokens bf16 [B,H/4*W/4,E]
+ * (+ an optional fp32 copy that seeds the fp32 residual stream, or NULL) */
 int soccdpt_patch_embed_fwd(const float *x, const float *w, const float *b, const float *ln_w,
-                            const float *ln_b, void *tokens, int batch, int H, int W, int E,
-                            soccdpt_stream_t stream);
+                            const float *ln_b, void *tokens, float *tokens_f32, int batch, int H, int W,
+                            int E, soccdpt_stream_t stream);
 
 /* timm WindowAttention (v2, cosine) incl. window partition / cyclic shift / reverse:
  *   qkv   bf16 [B, Hs*Ws, 3*C] (q|k|v, each heads x 32), biases already added by the qkv GEMM
@@ -138,6 +139,11 @@ int soccdpt_window_attention_fwd(const void *qkv, const float *bias, const float
  * Swin res-post-norm: x + norm1(attn(x)), x + norm2(mlp(x)); PatchMerging norm (res = NULL). */
 int soccdpt_layernorm_fwd(const void *t, const void *res, const float *gamma, const float *beta,
                           void *y, long long rows, int C, float eps, soccdpt_stream_t stream);
+/* Same with the residual stream kept in fp32: master = (accumulate ? master : 0) + LayerNorm(t), updated in
+ * place; y = bf16(master) is the copy the next GEMM reads. */
+int soccdpt_layernorm_master_fwd(const void *t, float *master, int accumulate, const float *gamma,
+                                 const float *beta, void *y, long long rows, int C, float eps,
+                                 soccdpt_stream_t stream);
 
 /* timm PatchMerging gather: [B,H,W,C] -> [B,H/2,W/2,4C] in (x0,x1,x2,x3) = (0,0),(1,0),(0,1),(1,1) order */
 int soccdpt_patch_merge_gather_fwd(const void *x, void *y, int batch, int H, int W, int C,

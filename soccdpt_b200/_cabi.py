@@ -58,9 +58,10 @@ SYMBOLS = {
                                      c_void_p, c_void_p, _I, c_void_p, _SZ, c_void_p]),
     "soccdpt_conv_fwd": (_I, [ctypes.POINTER(Conv), c_void_p]),
     "soccdpt_conv_ref_fwd": (_I, [ctypes.POINTER(Conv), c_void_p]),
-    "soccdpt_patch_embed_fwd": (_I, [c_void_p] * 6 + [_I] * 4 + [c_void_p]),
+    "soccdpt_patch_embed_fwd": (_I, [c_void_p] * 7 + [_I] * 4 + [c_void_p]),
     "soccdpt_window_attention_fwd": (_I, [c_void_p] * 4 + [_I] * 7 + [c_void_p]),
     "soccdpt_layernorm_fwd": (_I, [c_void_p] * 5 + [_LL, _I, _F, c_void_p]),
+    "soccdpt_layernorm_master_fwd": (_I, [c_void_p, c_void_p, _I, c_void_p, c_void_p, c_void_p, _LL, _I, _F, c_void_p]),
     "soccdpt_patch_merge_gather_fwd": (_I, [c_void_p, c_void_p, _I, _I, _I, _I, c_void_p]),
     "soccdpt_upsample_bilinear_fwd": (_I, [c_void_p, c_void_p] + [_I] * 6 + [c_void_p]),
     "soccdpt_seg_finish_fwd": (_I, [c_void_p, c_void_p] + [_I] * 5 + [c_void_p]),

@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(256) conv_ref_kernel(const soccdpt_conv_t c) {
 // One warp per token; lane l owns channels l, l+32, ... (E <= 256).
 __global__ void __launch_bounds__(256)
 patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
-                   const float *__restrict__ g, const float *__restrict__ be, bf16 *__restrict__ out, int B, int H,
-                   int W, int E) {
+                   const float *__restrict__ g, const float *__restrict__ be, bf16 *__restrict__ out,
+                   float *__restrict__ out_f32, int B, int H, int W, int E) {
     const int lane = threadIdx.x & 31;
     const int ph = H / 4, pw = W / 4;
     const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -123,15 +123,22 @@ patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w, con
     for (int i = 0; i < cnt; ++i) sq += (val[i] - mean) * (val[i] - mean);
     const float rstd = rsqrtf(warp_sum(sq) / (float)E + 1e-5f);
     cnt = 0;
-    for (int e = lane; e < E; e += 32, ++cnt)
-        out[tok * E + e] = __float2bfloat16_rn((val[cnt] - mean) * rstd * g[e] + be[e]);
+    for (int e = lane; e < E; e += 32, ++cnt) {
+        const float v = (val[cnt] - mean) * rstd * g[e] + be[e];
+        out[tok * E + e] = __float2bfloat16_rn(v);
+        if (out_f32) out_f32[tok * E + e] = v;
+    }
 }
 
 // ------------------------------------------------------------------ y = res + LayerNorm(t)
 // One warp per row, 16-byte (8 x bf16) accesses; the row is re-read from L1 for the 2nd/3rd pass.
+// Two residual flavours: `res` (bf16) or `master` (fp32 residual stream, updated in place; `accumulate`
+// = 0 overwrites it).  The Swin residual stream is kept in fp32 so that 24 post-norm additions do not
+// each round to bf16; y is the bf16 copy the next GEMM consumes.
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const bf16 *__restrict__ t, const bf16 *__restrict__ res, const float *__restrict__ gamma,
-                 const float *__restrict__ beta, bf16 *__restrict__ y, long long rows, int C, float eps) {
+layernorm_kernel(const bf16 *__restrict__ t, const bf16 *__restrict__ res, float *__restrict__ master, int accumulate,
+                 const float *__restrict__ gamma, const float *__restrict__ beta, bf16 *__restrict__ y, long long rows,
+                 int C, float eps) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -154,15 +161,25 @@ layernorm_kernel(const bf16 *__restrict__ t, const bf16 *__restrict__ res, const
     }
     const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
     const uint4 *rp = res ? reinterpret_cast<const uint4 *>(res + row * C) : nullptr;
+    float4 *mp = master ? reinterpret_cast<float4 *>(master + row * C) : nullptr;
     uint4 *yp = reinterpret_cast<uint4 *>(y + row * C);
     for (int k = lane; k < chunks; k += 32) {
         float f[8], r[8];
         unpack8(tp[k], f);
         if (rp) unpack8(rp[k], r);
+        if (mp && accumulate) {
+            const float4 a = mp[2 * k], b = mp[2 * k + 1];
+            r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+        }
+        const bool add = rp || (mp && accumulate);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float v = (f[i] - mean) * rstd * gamma[k * 8 + i] + beta[k * 8 + i];
-            f[i] = rp ? r[i] + v : v;
+            f[i] = add ? r[i] + v : v;
+        }
+        if (mp) {
+            mp[2 * k] = make_float4(f[0], f[1], f[2], f[3]);
+            mp[2 * k + 1] = make_float4(f[4], f[5], f[6], f[7]);
         }
         yp[k] = pack8(f);
     }
@@ -285,12 +302,12 @@ int soccdpt_conv_ref_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream) {
 }
 
 int soccdpt_patch_embed_fwd(const float *x, const float *w, const float *b, const float *ln_w, const float *ln_b,
-                            void *tokens, int batch, int H, int W, int E, soccdpt_stream_t stream) {
+                            void *tokens, float *tokens_f32, int batch, int H, int W, int E, soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(x && w && b && ln_w && ln_b && tokens, "patch_embed: NULL pointer");
     SOCCDPT_REQUIRE(batch >= 1 && H % 4 == 0 && W % 4 == 0 && E >= 32 && E <= 256, "patch_embed: bad shape");
     const long long toks = (long long)batch * (H / 4) * (W / 4);
     patch_embed_kernel<<<(unsigned)((toks + 7) / 8), 256, 0, soccdpt::as_stream(stream)>>>(
-        x, w, b, ln_w, ln_b, static_cast<bf16 *>(tokens), batch, H, W, E);
+        x, w, b, ln_w, ln_b, static_cast<bf16 *>(tokens), tokens_f32, batch, H, W, E);
     return soccdpt::check_launch("patch_embed_kernel");
 }
 
@@ -299,7 +316,16 @@ int soccdpt_layernorm_fwd(const void *t, const void *res, const float *gamma, co
     SOCCDPT_REQUIRE(t && gamma && beta && y, "layernorm: NULL pointer");
     SOCCDPT_REQUIRE(rows >= 1 && C >= 8 && C % 8 == 0, "layernorm: C must be a multiple of 8 (got %d)", C);
     layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, soccdpt::as_stream(stream)>>>(
-        static_cast<const bf16 *>(t), static_cast<const bf16 *>(res), gamma, beta, static_cast<bf16 *>(y), rows, C, eps);
+        static_cast<const bf16 *>(t), static_cast<const bf16 *>(res), nullptr, 0, gamma, beta, static_cast<bf16 *>(y), rows, C, eps);
+    return soccdpt::check_launch("layernorm_kernel");
+}
+
+int soccdpt_layernorm_master_fwd(const void *t, float *master, int accumulate, const float *gamma, const float *beta,
+                                 void *y, long long rows, int C, float eps, soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(t && master && gamma && beta && y, "layernorm_master: NULL pointer");
+    SOCCDPT_REQUIRE(rows >= 1 && C >= 8 && C % 8 == 0, "layernorm_master: C must be a multiple of 8 (got %d)", C);
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, soccdpt::as_stream(stream)>>>(
+        static_cast<const bf16 *>(t), nullptr, master, accumulate, gamma, beta, static_cast<bf16 *>(y), rows, C, eps);
     return soccdpt::check_launch("layernorm_kernel");
 }
 

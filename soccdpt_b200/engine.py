@@ -157,9 +157,10 @@ class NetworkEngine:
         tmp = buf(B * maxLC)
         hid = buf(B * maxLC * 4)
         gat = buf(B * maxLC)           # patch-merge gather: (L/4) * 4C = L*C elements
-        cur = buf(B * g0 * g0, E)
+        cur = buf(B * g0 * g0, E)                               # bf16 copy of the residual stream (GEMM operand)
+        master = buf(B * g0 * g0, E, dtype=torch.float32)       # fp32 residual stream
         ops.append(_Launch("patch_embed", lib.soccdpt_patch_embed_fwd, x_in.data_ptr(), *(t.data_ptr() for t in Wt["pe"]),
-                           cur.data_ptr(), B, img, img, E))
+                           cur.data_ptr(), master.data_ptr(), B, img, img, E))
         taps = []
         for si, st in enumerate(stages):
             Hs, Ws = st["res"]
@@ -170,20 +171,22 @@ class NetworkEngine:
                 ops.append(_Launch("window_attention", lib.soccdpt_window_attention_fwd, qkv.data_ptr(), b["biasT"].data_ptr(),
                                    b["scale"].data_ptr(), att.data_ptr(), B, Hs, Ws, C, b["heads"], b["ws"], b["shift"]))
                 self._conv(plan, att, b["wproj"], 1, 1, M, C, C, 1, bias=b["bproj"], y=tmp)
-                ops.append(_Launch("ln_res", lib.soccdpt_layernorm_fwd, tmp.data_ptr(), cur.data_ptr(), b["n1"][0].data_ptr(),
-                                   b["n1"][1].data_ptr(), cur.data_ptr(), M, C, ctypes.c_float(1e-5)))
+                ops.append(_Launch("ln_res", lib.soccdpt_layernorm_master_fwd, tmp.data_ptr(), master.data_ptr(), 1,
+                                   b["n1"][0].data_ptr(), b["n1"][1].data_ptr(), cur.data_ptr(), M, C, ctypes.c_float(1e-5)))
                 self._conv(plan, cur, b["w1"], 1, 1, M, C, 4 * C, 1, bias=b["b1"], act=_cabi.ACT_GELU, y=hid)
                 self._conv(plan, hid, b["w2"], 1, 1, M, 4 * C, C, 1, bias=b["b2"], y=tmp)
-                ops.append(_Launch("ln_res", lib.soccdpt_layernorm_fwd, tmp.data_ptr(), cur.data_ptr(), b["n2"][0].data_ptr(),
-                                   b["n2"][1].data_ptr(), cur.data_ptr(), M, C, ctypes.c_float(1e-5)))
+                ops.append(_Launch("ln_res", lib.soccdpt_layernorm_master_fwd, tmp.data_ptr(), master.data_ptr(), 1,
+                                   b["n2"][0].data_ptr(), b["n2"][1].data_ptr(), cur.data_ptr(), M, C, ctypes.c_float(1e-5)))
             taps.append((cur, Hs, Ws, C))   # hooks sit on the last block of every stage (dpt.py:61-72)
             if st["down"] is not None:
                 ops.append(_Launch("merge_gather", lib.soccdpt_patch_merge_gather_fwd, cur.data_ptr(), gat.data_ptr(), B, Hs, Ws, C))
                 M2 = B * L // 4
                 self._conv(plan, gat, st["down"]["w"], 1, 1, M2, 4 * C, 2 * C, 1, y=tmp)
                 nxt = buf(M2, 2 * C)
-                ops.append(_Launch("ln", lib.soccdpt_layernorm_fwd, tmp.data_ptr(), None, st["down"]["n"][0].data_ptr(),
-                                   st["down"]["n"][1].data_ptr(), nxt.data_ptr(), M2, 2 * C, ctypes.c_float(1e-5)))
+                master = buf(M2, 2 * C, dtype=torch.float32)
+                ops.append(_Launch("ln", lib.soccdpt_layernorm_master_fwd, tmp.data_ptr(), master.data_ptr(), 0,
+                                   st["down"]["n"][0].data_ptr(), st["down"]["n"][1].data_ptr(), nxt.data_ptr(), M2, 2 * C,
+                                   ctypes.c_float(1e-5)))
                 cur = nxt
         plan["taps"] = taps
 

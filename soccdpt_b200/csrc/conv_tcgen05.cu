@@ -14,7 +14,12 @@
 //   warps 4-7 = epilogue (tcgen05.ld -> bias / ReLU / GELU / residual adds / bf16 store, or the fused
 //   narrow projection 32->1 / 256->3 of the depth / seg heads).
 // * persistent: grid = min(tiles, SMs); 4-stage smem ring (A 16 KB + B <=32 KB per stage).
+// * 2-CTA clusters: the two CTAs of a cluster work on neighbouring M tiles of the same N block; each
+//   loads HALF of the weight tile and TMA-multicasts it into both CTAs' shared memory, halving the weight
+//   traffic out of L2 (weights are 2/3 of the L2->smem bytes of a 256->256 3x3 conv, which is L2-bound).
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -45,6 +50,7 @@ struct Params {
     // tile geometry
     int BW, BH, BN;            // box of output pixels handled by one M tile (BW*BH*BN <= 128)
     int tiles_w, tiles_h, tiles_n, n_blocks, total_tiles;
+    int m_tiles, cluster, total_items;   // items = groups of `cluster` neighbouring M tiles x n_blocks
     int block_n;               // output channels per tile
     int k_blocks_per_tap;      // ceil(Cin / 64)
     int pad;                   // KH / 2
@@ -90,6 +96,20 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows are 128 B,
 // 8-row groups are 1024 B apart (SBO), version 1 (Blackwell), layout type 2.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
@@ -115,6 +135,10 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -150,7 +174,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        // a smem slot is free again once the MMAs of EVERY CTA the multicast writes into have retired
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)p.cluster); }
         for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_THREADS); }
         fence_barrier_init();
     }
@@ -160,8 +185,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();   // peer barriers must be initialised before any multicast lands
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int crank = p.cluster > 1 ? (int)cluster_ctarank() : 0;
+    const int item0 = blockIdx.x / p.cluster, item_stride = gridDim.x / p.cluster;
+    const uint16_t mc_mask = (uint16_t)((1u << p.cluster) - 1u);
 
     const int taps = c.KH * c.KW;
     const int k_blocks = taps * p.k_blocks_per_tap;
@@ -171,10 +200,13 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
+            for (int item = item0; item < p.total_items; item += item_stride) {
+                const int nb = item % p.n_blocks;
+                int mt = (item / p.n_blocks) * p.cluster + crank;
+                if (mt >= p.m_tiles) mt = p.m_tiles - 1;     // odd tail: redundant tile, stores are masked
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
                 const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+                const int b_rows = p.block_n / p.cluster;    // weight rows this CTA fetches (and multicasts)
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     const int tap = kb / p.k_blocks_per_tap, cb = kb - tap * p.k_blocks_per_tap;
                     const int kh = tap / c.KW, kw = tap - kh * c.KW;
@@ -182,7 +214,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
                     uint8_t *sa = smem + stage * STAGE_BYTES;
                     tma_load_4d(sa, &map_a, &full[stage], cb * BLOCK_K, w0 + kw - p.pad, h0 + kh - p.pad, n0);
-                    tma_load_3d(sa + A_STAGE_BYTES, &map_b, &full[stage], cb * BLOCK_K, tap, nb * p.block_n);
+                    uint8_t *sb = sa + A_STAGE_BYTES + crank * b_rows * (BLOCK_K * 2);
+                    if (p.cluster > 1)
+                        tma_load_3d_mc(sb, &map_b, &full[stage], cb * BLOCK_K, tap, nb * p.block_n + crank * b_rows, mc_mask);
+                    else
+                        tma_load_3d(sb, &map_b, &full[stage], cb * BLOCK_K, tap, nb * p.block_n);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -195,7 +231,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int item = item0; item < p.total_items; item += item_stride) {
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
@@ -211,7 +247,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         // advance both descriptors by k * 32 B inside the 128 B swizzle row
                         umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);              // frees the smem slot once these MMAs retire
+                    if (p.cluster > 1) umma_commit_mc(&empty[stage], mc_mask);   // slot is shared with the peer's multicast
+                    else umma_commit(&empty[stage]);         // frees the smem slot once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&acc_full[acc]);                 // accumulator complete -> epilogue
@@ -230,8 +267,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         bf16 *y = static_cast<bf16 *>(c.y);
         bf16 *y_relu = static_cast<bf16 *>(c.y_relu);
         const int m_valid = p.BW * p.BH * p.BN;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
+        for (int item = item0; item < p.total_items; item += item_stride) {
+            const int nb = item % p.n_blocks;
+            const int mt = (item / p.n_blocks) * p.cluster + crank;
+            const bool tile_valid = mt < p.m_tiles;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
             const int cout0 = nb * p.block_n;
             if (nb != cached_nb) {
@@ -248,7 +287,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             // row -> pixel
             const int bw = et % p.BW, bh = (et / p.BW) % p.BH, bn = et / (p.BW * p.BH);
             const int wx = tw * p.BW + bw, hy = th * p.BH + bh, ni = tn * p.BN + bn;
-            const bool valid = (et < m_valid) && (wx < c.W) && (hy < c.H) && (ni < c.N);
+            const bool valid = tile_valid && (et < m_valid) && (wx < c.W) && (hy < c.H) && (ni < c.N);
             const long long pix = ((long long)ni * c.H + hy) * c.W + wx;
 
             mbar_wait(&acc_full[acc], acc_phase);
@@ -345,6 +384,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into / signal this CTA
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -422,6 +462,10 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
     SOCCDPT_REQUIRE(total < (1ll << 31), "conv: too many tiles");
     p.total_tiles = (int)total;
+    p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    // 2-CTA clusters with weight multicast whenever there are at least two M tiles to pair up
+    p.cluster = (p.m_tiles >= 2 && (p.block_n / 2) % 8 == 0 && !getenv("SOCCDPT_NO_CLUSTER")) ? 2 : 1;
+    p.total_items = ((p.m_tiles + p.cluster - 1) / p.cluster) * p.n_blocks;
     p.k_blocks_per_tap = (c->Cin + BLOCK_K - 1) / BLOCK_K;
     p.pad = c->KH / 2;
     p.a_bytes = (uint32_t)(p.BW * p.BH * p.BN) * BLOCK_K * 2;
@@ -443,7 +487,7 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
         const int taps = c->KH * c->KW;
         cuuint64_t dims[3] = {(cuuint64_t)c->Cin, (cuuint64_t)taps, (cuuint64_t)c->Cout};
         cuuint64_t strides[2] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)taps * c->Cin * 2};
-        cuuint32_t box[3] = {BLOCK_K, 1, (cuuint32_t)p.block_n};
+        cuuint32_t box[3] = {BLOCK_K, 1, (cuuint32_t)(p.block_n / p.cluster)};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(c->wgt), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -456,7 +500,21 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
         SOCCDPT_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
-    const int grid = p.total_tiles < soccdpt::sm_count() ? p.total_tiles : soccdpt::sm_count();
-    conv_tcgen05_kernel<<<grid, NUM_THREADS, SMEM_BYTES, soccdpt::as_stream(stream)>>>(map_a, map_b, p);
+    int grid = p.total_items * p.cluster;
+    const int cap = soccdpt::sm_count() / p.cluster * p.cluster;
+    if (grid > cap) grid = cap;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = soccdpt::as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SOCCDPT_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel, map_a, map_b, p));
     return soccdpt::check_launch("conv_tcgen05_kernel");
 }

@@ -14,9 +14,9 @@
 //   warps 4-7 = epilogue (tcgen05.ld -> bias / ReLU / GELU / residual adds / bf16 store, or the fused
 //   narrow projection 32->1 / 256->3 of the depth / seg heads).
 // * persistent: grid = min(tiles, SMs); 4-stage smem ring (A 16 KB + B <=32 KB per stage).
-// * 2-CTA clusters: the two CTAs of a cluster work on neighbouring M tiles of the same N block; each
-//   loads HALF of the weight tile and TMA-multicasts it into both CTAs' shared memory, halving the weight
-//   traffic out of L2 (weights are 2/3 of the L2->smem bytes of a 256->256 3x3 conv, which is L2-bound).
+// * optional 2-CTA clusters (SOCCDPT_CONV_CLUSTER=2): the two CTAs of a cluster work on neighbouring M
+//   tiles of the same N block; each loads HALF of the weight tile and TMA-multicasts it into both CTAs'
+//   shared memory.  Halves weight reads from L2 but not the bytes arriving per SM -> no gain (see host code).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -463,8 +463,11 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     SOCCDPT_REQUIRE(total < (1ll << 31), "conv: too many tiles");
     p.total_tiles = (int)total;
     p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    // 2-CTA clusters with weight multicast whenever there are at least two M tiles to pair up
-    p.cluster = (p.m_tiles >= 2 && (p.block_n / 2) % 8 == 0 && !getenv("SOCCDPT_NO_CLUSTER")) ? 2 : 1;
+    // 2-CTA clusters with weight multicast: measured SLOWER on B200 (11.2 vs 10.2 ms/step): the kernel is bound
+    // by per-SM inbound bandwidth (A 16 KB + B 32 KB per 512 MMA cycles), which multicast does not reduce --
+    // only L2 reads, and L2 is 44 % busy.  Kept for the cta_group::2 follow-up; opt-in for experiments.
+    const char *ce = getenv("SOCCDPT_CONV_CLUSTER");
+    p.cluster = (ce && ce[0] == '2' && p.m_tiles >= 2 && (p.block_n / 2) % 8 == 0) ? 2 : 1;
     p.total_items = ((p.m_tiles + p.cluster - 1) / p.cluster) * p.n_blocks;
     p.k_blocks_per_tap = (c->Cin + BLOCK_K - 1) / BLOCK_K;
     p.pad = c->KH / 2;

@@ -517,7 +517,7 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = p.cluster > 1 ? 1 : 0;   // a 1x1x1 cluster attribute switches the CTA scheduler mode (measured -9 %)
     SOCCDPT_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel, map_a, map_b, p));
     return soccdpt::check_launch("conv_tcgen05_kernel");
 }

@@ -11,15 +11,13 @@
 //   accumulators live in TMEM (2 stages x 256 columns) so the epilogue of tile i overlaps the
 //   MMAs of tile i+1.
 // * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-//   warps 4-7 = epilogue (tcgen05.ld -> bias / ReLU / GELU / residual adds / bf16 store, or the fused
-//   narrow projection 32->1 / 256->3 of the depth / seg heads).
+//   warps 4-11 = epilogue: two warpgroups, each draining half of the accumulator columns of all 128 rows
+//   (tcgen05.ld -> bias / ReLU / GELU / residual adds / bf16 store, or the fused narrow projection
+//   32->1 / 256->3 of the depth / seg heads).  The epilogue is template-specialised on <activation, mode>:
+//   with per-element runtime branches it ran ~170 warp-instructions per 16 columns and was as long as the
+//   whole K=2304 mainloop.
 // * persistent: grid = min(tiles, SMs); 4-stage smem ring (A 16 KB + B <=32 KB per stage).
-// * optional 2-CTA clusters (SOCCDPT_CONV_CLUSTER=2): the two CTAs of a cluster work on neighbouring M
-//   tiles of the same N block; each loads HALF of the weight tile and TMA-multicasts it into both CTAs'
-//   shared memory.  Halves weight reads from L2 but not the bytes arriving per SM -> no gain (see host code).
 #include <cuda.h>
-
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -40,17 +38,16 @@ constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;       // 32 KB (BLOCK_N <= 256)
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 384;          // 4 control warps + 8 epilogue warps
+constexpr int EPI_THREADS = 256;          // two epilogue warpgroups, each owns half of the tile's columns
 // dynamic smem: ring + epilogue constants (bias 256 f32 + proj 4x256 f32 + proj bias) + barriers
-constexpr int EPI_CONST_BYTES = (256 + 4 * 256 + 4) * 4;
+constexpr int EPI_CONST_BYTES = (256 + 4 * 256 + 4 + 128 * 4) * 4;   // bias, proj weights, proj bias, proj partials
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_CONST_BYTES + 256 + 1024 /*alignment slack*/;
 
 struct Params {
     // tile geometry
     int BW, BH, BN;            // box of output pixels handled by one M tile (BW*BH*BN <= 128)
     int tiles_w, tiles_h, tiles_n, n_blocks, total_tiles;
-    int m_tiles, cluster, total_items;   // items = groups of `cluster` neighbouring M tiles x n_blocks
     int block_n;               // output channels per tile
     int k_blocks_per_tap;      // ceil(Cin / 64)
     int pad;                   // KH / 2
@@ -96,20 +93,6 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-__device__ __forceinline__ void tma_load_3d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows are 128 B,
 // 8-row groups are 1024 B apart (SBO), version 1 (Blackwell), layout type 2.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
@@ -136,10 +119,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -147,11 +126,58 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // ------------------------------------------------------------------ the kernel
+// v[8*N] += bf16 values at p (N x 16 bytes)
+template <int N, int LEN>
+__device__ __forceinline__ void add_bf16_impl(float (&v)[LEN], const uint4 *p) {
+#pragma unroll
+    for (int h = 0; h < N; ++h) {
+        const uint4 u = p[h];
+        const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(b2[k]);
+            v[h * 8 + 2 * k] += f.x;
+            v[h * 8 + 2 * k + 1] += f.y;
+        }
+    }
+}
+template <int N, int LEN>
+__device__ __forceinline__ void add_bf16(float (&v)[LEN], const uint4 *p) { add_bf16_impl<N, LEN>(v, p); }
+template <int N, bool RELU, int LEN>
+__device__ __forceinline__ void store_bf16(const float (&v)[LEN], uint4 *p) {
+#pragma unroll
+    for (int h = 0; h < N; ++h) {
+        uint4 u;
+        __nv_bfloat162 *b2 = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = RELU ? fmaxf(v[h * 8 + 2 * k], 0.0f) : v[h * 8 + 2 * k];
+            const float b = RELU ? fmaxf(v[h * 8 + 2 * k + 1], 0.0f) : v[h * 8 + 2 * k + 1];
+            b2[k] = __floats2bfloat162_rn(a, b);
+        }
+        p[h] = u;
+    }
+}
+
+// MODE 0: y = act(acc + bias)            (no residual, no ReLU copy, no projection)
+// MODE 1: general: optional res1 / res2 / y / y_relu
+// MODE 2: fused projection only (proj_out), no y
+template <int ACT, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ Params p) {
@@ -160,7 +186,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     float *s_bias = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
     float *s_projw = s_bias + 256;
     float *s_projb = s_projw + 4 * 256;
-    uint64_t *full = reinterpret_cast<uint64_t *>(s_projb + 4);
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_projb + 4 + 128 * 4);   // after the [128][4] projection partials
     uint64_t *empty = full + STAGES;
     uint64_t *acc_full = empty + STAGES;
     uint64_t *acc_empty = acc_full + ACC_STAGES;
@@ -174,8 +200,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        // a smem slot is free again once the MMAs of EVERY CTA the multicast writes into have retired
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)p.cluster); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_THREADS); }
         fence_barrier_init();
     }
@@ -185,12 +210,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
-    if (p.cluster > 1) cluster_sync_all();   // peer barriers must be initialised before any multicast lands
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int crank = p.cluster > 1 ? (int)cluster_ctarank() : 0;
-    const int item0 = blockIdx.x / p.cluster, item_stride = gridDim.x / p.cluster;
-    const uint16_t mc_mask = (uint16_t)((1u << p.cluster) - 1u);
 
     const int taps = c.KH * c.KW;
     const int k_blocks = taps * p.k_blocks_per_tap;
@@ -200,13 +221,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = item0; item < p.total_items; item += item_stride) {
-                const int nb = item % p.n_blocks;
-                int mt = (item / p.n_blocks) * p.cluster + crank;
-                if (mt >= p.m_tiles) mt = p.m_tiles - 1;     // odd tail: redundant tile, stores are masked
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
                 const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
-                const int b_rows = p.block_n / p.cluster;    // weight rows this CTA fetches (and multicasts)
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     const int tap = kb / p.k_blocks_per_tap, cb = kb - tap * p.k_blocks_per_tap;
                     const int kh = tap / c.KW, kw = tap - kh * c.KW;
@@ -214,11 +232,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
                     uint8_t *sa = smem + stage * STAGE_BYTES;
                     tma_load_4d(sa, &map_a, &full[stage], cb * BLOCK_K, w0 + kw - p.pad, h0 + kh - p.pad, n0);
-                    uint8_t *sb = sa + A_STAGE_BYTES + crank * b_rows * (BLOCK_K * 2);
-                    if (p.cluster > 1)
-                        tma_load_3d_mc(sb, &map_b, &full[stage], cb * BLOCK_K, tap, nb * p.block_n + crank * b_rows, mc_mask);
-                    else
-                        tma_load_3d(sb, &map_b, &full[stage], cb * BLOCK_K, tap, nb * p.block_n);
+                    tma_load_3d(sa + A_STAGE_BYTES, &map_b, &full[stage], cb * BLOCK_K, tap, nb * p.block_n);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -231,7 +245,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int item = item0; item < p.total_items; item += item_stride) {
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
@@ -247,8 +261,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         // advance both descriptors by k * 32 B inside the 128 B swizzle row
                         umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    if (p.cluster > 1) umma_commit_mc(&empty[stage], mc_mask);   // slot is shared with the peer's multicast
-                    else umma_commit(&empty[stage]);         // frees the smem slot once these MMAs retire
+                    umma_commit(&empty[stage]);              // frees the smem slot once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&acc_full[acc]);                 // accumulator complete -> epilogue
@@ -256,9 +269,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue (128 threads, TMEM lane = tile row) =====================
-        const int et = threadIdx.x - 128;          // 0..127 == TMEM lane == row inside the tile
+        // ===================== epilogue: 2 warpgroups x 128 threads; TMEM lane = tile row =====================
+        const int et = threadIdx.x - 128;          // 0..255
+        const int row = et & 127;                  // tile row == TMEM lane
+        const int wg = et >> 7;                    // which half of the columns this warpgroup drains
         const int quarter = warp & 3;              // TMEM lanes [32*quarter, +32) are visible to this warp
+        float *s_part = s_projb + 4;               // [128][4] projection partials of warpgroup 1
         int acc = 0;
         uint32_t acc_phase = 0;
         int cached_nb = -1;
@@ -267,34 +283,79 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         bf16 *y = static_cast<bf16 *>(c.y);
         bf16 *y_relu = static_cast<bf16 *>(c.y_relu);
         const int m_valid = p.BW * p.BH * p.BN;
-        for (int item = item0; item < p.total_items; item += item_stride) {
-            const int nb = item % p.n_blocks;
-            const int mt = (item / p.n_blocks) * p.cluster + crank;
-            const bool tile_valid = mt < p.m_tiles;
+        // column split in 16-column units: warpgroup 0 takes the first ceil(n/2)
+        const int units = p.block_n >> 4, u_split = (units + 1) >> 1;
+        const int col_begin = wg == 0 ? 0 : u_split * 16, col_end = wg == 0 ? u_split * 16 : p.block_n;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
             const int cout0 = nb * p.block_n;
             if (nb != cached_nb) {
-                // per-channel constants of this N block -> smem (visible to the 128 epilogue threads only)
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // per-channel constants of this N block -> smem (visible to the 256 epilogue threads only)
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 for (int i = et; i < p.block_n; i += EPI_THREADS) s_bias[i] = c.bias ? c.bias[cout0 + i] : 0.0f;
-                if (c.proj_n > 0) {
+                if (MODE == 2) {
                     for (int i = et; i < c.proj_n * c.Cout; i += EPI_THREADS) s_projw[i] = c.proj_w[i];
                     if (et < c.proj_n) s_projb[et] = c.proj_b[et];
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 cached_nb = nb;
             }
             // row -> pixel
-            const int bw = et % p.BW, bh = (et / p.BW) % p.BH, bn = et / (p.BW * p.BH);
+            const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
             const int wx = tw * p.BW + bw, hy = th * p.BH + bh, ni = tn * p.BN + bn;
-            const bool valid = tile_valid && (et < m_valid) && (wx < c.W) && (hy < c.H) && (ni < c.N);
+            const bool valid = (row < m_valid) && (wx < c.W) && (hy < c.H) && (ni < c.N);
             const long long pix = ((long long)ni * c.H + hy) * c.W + wx;
+            const long long obase = pix * c.Cout + cout0;
 
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
             float proj[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int col = 0; col < p.block_n; col += 16) {
+            int col = col_begin;
+            // ---- 32-column steps
+            for (; col + 32 <= col_end; col += 32) {
+                uint32_t raw[32];
+                tmem_ld32(t_row + (uint32_t)col, raw);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 bb = *reinterpret_cast<const float4 *>(s_bias + col + j4 * 4);
+                    v[j4 * 4 + 0] = __uint_as_float(raw[j4 * 4 + 0]) + bb.x;
+                    v[j4 * 4 + 1] = __uint_as_float(raw[j4 * 4 + 1]) + bb.y;
+                    v[j4 * 4 + 2] = __uint_as_float(raw[j4 * 4 + 2]) + bb.z;
+                    v[j4 * 4 + 3] = __uint_as_float(raw[j4 * 4 + 3]) + bb.w;
+                }
+                if (ACT == SOCCDPT_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                } else if (ACT == SOCCDPT_ACT_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                }
+                if (MODE == 2) {
+                    for (int q = 0; q < c.proj_n; ++q) {
+                        const float *pw = s_projw + q * c.Cout + col;
+                        float sacc = proj[q];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sacc = fmaf(pw[j], v[j], sacc);
+                        proj[q] = sacc;
+                    }
+                } else if (valid) {
+                    const long long o = obase + col;
+                    if (MODE == 1) {
+                        if (res1) add_bf16<4>(v, reinterpret_cast<const uint4 *>(res1 + o));
+                        if (res2) add_bf16<4>(v, reinterpret_cast<const uint4 *>(res2 + o));
+                        if (y) store_bf16<4, false>(v, reinterpret_cast<uint4 *>(y + o));
+                        if (y_relu) store_bf16<4, true>(v, reinterpret_cast<uint4 *>(y_relu + o));
+                    } else {
+                        store_bf16<4, false>(v, reinterpret_cast<uint4 *>(y + o));
+                    }
+                }
+            }
+            // ---- 16-column tail
+            for (; col < col_end; col += 16) {
                 uint32_t raw[16];
                 tmem_ld16(t_row + (uint32_t)col, raw);
                 tmem_ld_wait();
@@ -302,81 +363,48 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     float t = __uint_as_float(raw[j]) + s_bias[col + j];
-                    if (c.act == SOCCDPT_ACT_RELU) t = fmaxf(t, 0.0f);
-                    else if (c.act == SOCCDPT_ACT_GELU) t = gelu_erf(t);
+                    if (ACT == SOCCDPT_ACT_RELU) t = fmaxf(t, 0.0f);
+                    else if (ACT == SOCCDPT_ACT_GELU) t = gelu_erf(t);
                     v[j] = t;
                 }
-                if (valid) {
-                    const long long o = pix * c.Cout + cout0 + col;
-                    if (res1) {
-                        const uint4 *rp = reinterpret_cast<const uint4 *>(res1 + o);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const uint4 u = rp[h];
-                            const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float2 f = __bfloat1622float2(b2[k]);
-                                v[h * 8 + 2 * k] += f.x;
-                                v[h * 8 + 2 * k + 1] += f.y;
-                            }
-                        }
-                    }
-                    if (res2) {
-                        const uint4 *rp = reinterpret_cast<const uint4 *>(res2 + o);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const uint4 u = rp[h];
-                            const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float2 f = __bfloat1622float2(b2[k]);
-                                v[h * 8 + 2 * k] += f.x;
-                                v[h * 8 + 2 * k + 1] += f.y;
-                            }
-                        }
-                    }
-                    if (y) {
-                        uint4 *yp = reinterpret_cast<uint4 *>(y + o);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint4 u;
-                            __nv_bfloat162 *b2 = reinterpret_cast<__nv_bfloat162 *>(&u);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) b2[k] = __floats2bfloat162_rn(v[h * 8 + 2 * k], v[h * 8 + 2 * k + 1]);
-                            yp[h] = u;
-                        }
-                    }
-                    if (y_relu) {
-                        uint4 *yp = reinterpret_cast<uint4 *>(y_relu + o);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint4 u;
-                            __nv_bfloat162 *b2 = reinterpret_cast<__nv_bfloat162 *>(&u);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                b2[k] = __floats2bfloat162_rn(fmaxf(v[h * 8 + 2 * k], 0.0f), fmaxf(v[h * 8 + 2 * k + 1], 0.0f));
-                            yp[h] = u;
-                        }
-                    }
+                if (MODE == 2) {
                     for (int q = 0; q < c.proj_n; ++q) {
                         const float *pw = s_projw + q * c.Cout + col;
-                        float s = proj[q];
+                        float sacc = proj[q];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) s = fmaf(pw[j], v[j], s);
-                        proj[q] = s;
+                        for (int j = 0; j < 16; ++j) sacc = fmaf(pw[j], v[j], sacc);
+                        proj[q] = sacc;
+                    }
+                } else if (valid) {
+                    const long long o = obase + col;
+                    if (MODE == 1) {
+                        if (res1) add_bf16<2>(v, reinterpret_cast<const uint4 *>(res1 + o));
+                        if (res2) add_bf16<2>(v, reinterpret_cast<const uint4 *>(res2 + o));
+                        if (y) store_bf16<2, false>(v, reinterpret_cast<uint4 *>(y + o));
+                        if (y_relu) store_bf16<2, true>(v, reinterpret_cast<uint4 *>(y_relu + o));
+                    } else {
+                        store_bf16<2, false>(v, reinterpret_cast<uint4 *>(y + o));
                     }
                 }
             }
-            // accumulator fully read: hand the TMEM stage back to the MMA warp
+            // accumulator fully read by this thread: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
-            if (valid && c.proj_n > 0) {
-                for (int q = 0; q < c.proj_n; ++q) {
-                    float s = proj[q] + s_projb[q];
-                    if (c.proj_relu) s = fmaxf(s, 0.0f);
-                    c.proj_out[pix * c.proj_n + q] = s;
+            if (MODE == 2) {
+                // combine the two column halves: warpgroup 1 -> smem -> warpgroup 0 adds, finishes, stores
+                if (wg == 1) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) s_part[row * 4 + q] = proj[q];
                 }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (wg == 0 && valid) {
+                    for (int q = 0; q < c.proj_n; ++q) {
+                        float sacc = proj[q] + s_part[row * 4 + q] + s_projb[q];
+                        if (c.proj_relu) sacc = fmaxf(sacc, 0.0f);
+                        c.proj_out[pix * c.proj_n + q] = sacc;
+                    }
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
             }
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
@@ -384,7 +412,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     tc_fence_before();
     __syncthreads();
-    if (p.cluster > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into / signal this CTA
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -462,13 +489,6 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
     SOCCDPT_REQUIRE(total < (1ll << 31), "conv: too many tiles");
     p.total_tiles = (int)total;
-    p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    // 2-CTA clusters with weight multicast: measured SLOWER on B200 (11.2 vs 10.2 ms/step): the kernel is bound
-    // by per-SM inbound bandwidth (A 16 KB + B 32 KB per 512 MMA cycles), which multicast does not reduce --
-    // only L2 reads, and L2 is 44 % busy.  Kept for the cta_group::2 follow-up; opt-in for experiments.
-    const char *ce = getenv("SOCCDPT_CONV_CLUSTER");
-    p.cluster = (ce && ce[0] == '2' && p.m_tiles >= 2 && (p.block_n / 2) % 8 == 0) ? 2 : 1;
-    p.total_items = ((p.m_tiles + p.cluster - 1) / p.cluster) * p.n_blocks;
     p.k_blocks_per_tap = (c->Cin + BLOCK_K - 1) / BLOCK_K;
     p.pad = c->KH / 2;
     p.a_bytes = (uint32_t)(p.BW * p.BH * p.BN) * BLOCK_K * 2;
@@ -490,7 +510,7 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
         const int taps = c->KH * c->KW;
         cuuint64_t dims[3] = {(cuuint64_t)c->Cin, (cuuint64_t)taps, (cuuint64_t)c->Cout};
         cuuint64_t strides[2] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)taps * c->Cin * 2};
-        cuuint32_t box[3] = {BLOCK_K, 1, (cuuint32_t)(p.block_n / p.cluster)};
+        cuuint32_t box[3] = {BLOCK_K, 1, (cuuint32_t)p.block_n};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(c->wgt), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -498,26 +518,31 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
         SOCCDPT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed with %d (Cout=%d taps=%d Cin=%d)", (int)r, c->Cout, taps, c->Cin);
     }
 
-    static bool configured = false;
-    if (!configured) {
-        SOCCDPT_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
-    }
-    int grid = p.total_items * p.cluster;
-    const int cap = soccdpt::sm_count() / p.cluster * p.cluster;
-    if (grid > cap) grid = cap;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = soccdpt::as_stream(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)p.cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = p.cluster > 1 ? 1 : 0;   // a 1x1x1 cluster attribute switches the CTA scheduler mode (measured -9 %)
-    SOCCDPT_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel, map_a, map_b, p));
+    const int mode = c->proj_n > 0 ? 2 : ((c->res1 || c->res2 || c->y_relu || !c->y) ? 1 : 0);
+    if (mode == 2) SOCCDPT_REQUIRE(c->y == nullptr && c->y_relu == nullptr && !c->res1 && !c->res2,
+                                   "conv: the fused projection epilogue produces proj_out only");
+    const int grid = p.total_tiles < soccdpt::sm_count() ? p.total_tiles : soccdpt::sm_count();
+    cudaStream_t st = soccdpt::as_stream(stream);
+#define SOCC_LAUNCH(A, M)                                                                                          \
+    do {                                                                                                           \
+        static bool configured = false;                                                                            \
+        if (!configured) {                                                                                         \
+            SOCCDPT_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<A, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              SMEM_BYTES));                                                        \
+            configured = true;                                                                                     \
+        }                                                                                                          \
+        conv_tcgen05_kernel<A, M><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);                          \
+    } while (0)
+#define SOCC_MODES(A)                      \
+    do {                                   \
+        if (mode == 0) SOCC_LAUNCH(A, 0);  \
+        else if (mode == 1) SOCC_LAUNCH(A, 1); \
+        else SOCC_LAUNCH(A, 2);            \
+    } while (0)
+    if (c->act == SOCCDPT_ACT_NONE) SOCC_MODES(0);
+    else if (c->act == SOCCDPT_ACT_RELU) SOCC_MODES(1);
+    else SOCC_MODES(2);
+#undef SOCC_MODES
+#undef SOCC_LAUNCH
     return soccdpt::check_launch("conv_tcgen05_kernel");
 }

@@ -169,58 +169,95 @@ patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w, con
 }
 
 // ------------------------------------------------------------------ y = res + LayerNorm(t)
-// One warp per row, 16-byte (8 x bf16) accesses; the row is re-read from L1 for the 2nd/3rd pass.
+// A group of G lanes (16 or 32) owns one row; every lane keeps its ITERS x 8 elements in registers, so the
+// row is read once (16-byte bf16 loads).  C = 96 uses half-warps (12 of 16 lanes busy instead of 12 of 32).
 // Two residual flavours: `res` (bf16) or `master` (fp32 residual stream, updated in place; `accumulate`
 // = 0 overwrites it).  The Swin residual stream is kept in fp32 so that 24 post-norm additions do not
 // each round to bf16; y is the bf16 copy the next GEMM consumes.
+template <int G, int ITERS>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const bf16 *__restrict__ t, const bf16 *__restrict__ res, float *__restrict__ master, int accumulate,
                  const float *__restrict__ gamma, const float *__restrict__ beta, bf16 *__restrict__ y, long long rows,
                  int C, float eps) {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const uint4 *tp = reinterpret_cast<const uint4 *>(t + row * C);
+    const int gl = threadIdx.x % G;                              // lane inside the group
+    const long long row = (long long)blockIdx.x * (256 / G) + threadIdx.x / G;
+    const bool live = row < rows;                                // keep dead groups in the shuffles
     const int chunks = C / 8;
+    const uint4 *tp = reinterpret_cast<const uint4 *>(t + (live ? row : 0) * C);
+    float f[ITERS][8];
     float s = 0.0f;
-    for (int k = lane; k < chunks; k += 32) {
-        float f[8];
-        unpack8(tp[k], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += f[i];
+    for (int it = 0; it < ITERS; ++it) {
+        const int k = gl + it * G;
+        if (k < chunks) {
+            unpack8(tp[k], f[it]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += f[it][i];
+        }
     }
-    const float mean = warp_sum(s) / (float)C;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
     float q = 0.0f;
-    for (int k = lane; k < chunks; k += 32) {
-        float f[8];
-        unpack8(tp[k], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) q += (f[i] - mean) * (f[i] - mean);
+    for (int it = 0; it < ITERS; ++it) {
+        if (gl + it * G < chunks) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q += (f[it][i] - mean) * (f[it][i] - mean);
+        }
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    if (!live) return;
     const uint4 *rp = res ? reinterpret_cast<const uint4 *>(res + row * C) : nullptr;
     float4 *mp = master ? reinterpret_cast<float4 *>(master + row * C) : nullptr;
     uint4 *yp = reinterpret_cast<uint4 *>(y + row * C);
-    for (int k = lane; k < chunks; k += 32) {
-        float f[8], r[8];
-        unpack8(tp[k], f);
-        if (rp) unpack8(rp[k], r);
-        if (mp && accumulate) {
-            const float4 a = mp[2 * k], b = mp[2 * k + 1];
-            r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
-        }
-        const bool add = rp || (mp && accumulate);
+    const bool add = rp || (mp && accumulate);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float v = (f[i] - mean) * rstd * gamma[k * 8 + i] + beta[k * 8 + i];
-            f[i] = add ? r[i] + v : v;
+    for (int it = 0; it < ITERS; ++it) {
+        const int k = gl + it * G;
+        if (k < chunks) {
+            float r[8], o8[8];
+            if (rp) unpack8(rp[k], r);
+            if (mp && accumulate) {
+                const float4 a = mp[2 * k], b2 = mp[2 * k + 1];
+                r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b2.x; r[5] = b2.y; r[6] = b2.z; r[7] = b2.w;
+            }
+            const float4 g0 = *reinterpret_cast<const float4 *>(gamma + k * 8), g1 = *reinterpret_cast<const float4 *>(gamma + k * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4 *>(beta + k * 8), b1 = *reinterpret_cast<const float4 *>(beta + k * 8 + 4);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float v = (f[it][i] - mean) * rstd * gg[i] + bb[i];
+                o8[i] = add ? r[i] + v : v;
+            }
+            if (mp) {
+                mp[2 * k] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+                mp[2 * k + 1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+            }
+            yp[k] = pack8(o8);
         }
-        if (mp) {
-            mp[2 * k] = make_float4(f[0], f[1], f[2], f[3]);
-            mp[2 * k + 1] = make_float4(f[4], f[5], f[6], f[7]);
-        }
-        yp[k] = pack8(f);
     }
+}
+
+int launch_layernorm(const bf16 *t, const bf16 *res, float *master, int accumulate, const float *gamma, const float *beta,
+                     bf16 *y, long long rows, int C, float eps, cudaStream_t st) {
+#define SOCC_LN(G, IT)                                                                                              \
+    layernorm_kernel<G, IT><<<(unsigned)((rows + (256 / G) - 1) / (256 / G)), 256, 0, st>>>(t, res, master, accumulate, \
+                                                                                            gamma, beta, y, rows, C, eps)
+    if (C <= 128) SOCC_LN(16, 1);
+    else if (C <= 256) SOCC_LN(32, 1);
+    else if (C <= 512) SOCC_LN(32, 2);
+    else if (C <= 1024) SOCC_LN(32, 4);
+    else if (C <= 2048) SOCC_LN(32, 8);
+    else {
+        soccdpt::set_error("layernorm: C = %d > 2048 is not supported", C);
+        return SOCCDPT_E_INVALID;
+    }
+#undef SOCC_LN
+    return soccdpt::check_launch("layernorm_kernel");
 }
 
 // ------------------------------------------------------------------ PatchMerging gather
@@ -357,18 +394,16 @@ int soccdpt_layernorm_fwd(const void *t, const void *res, const float *gamma, co
                           long long rows, int C, float eps, soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(t && gamma && beta && y, "layernorm: NULL pointer");
     SOCCDPT_REQUIRE(rows >= 1 && C >= 8 && C % 8 == 0, "layernorm: C must be a multiple of 8 (got %d)", C);
-    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, soccdpt::as_stream(stream)>>>(
-        static_cast<const bf16 *>(t), static_cast<const bf16 *>(res), nullptr, 0, gamma, beta, static_cast<bf16 *>(y), rows, C, eps);
-    return soccdpt::check_launch("layernorm_kernel");
+    return launch_layernorm(static_cast<const bf16 *>(t), static_cast<const bf16 *>(res), nullptr, 0, gamma, beta,
+                            static_cast<bf16 *>(y), rows, C, eps, soccdpt::as_stream(stream));
 }
 
 int soccdpt_layernorm_master_fwd(const void *t, float *master, int accumulate, const float *gamma, const float *beta,
                                  void *y, long long rows, int C, float eps, soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(t && master && gamma && beta && y, "layernorm_master: NULL pointer");
     SOCCDPT_REQUIRE(rows >= 1 && C >= 8 && C % 8 == 0, "layernorm_master: C must be a multiple of 8 (got %d)", C);
-    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, soccdpt::as_stream(stream)>>>(
-        static_cast<const bf16 *>(t), nullptr, master, accumulate, gamma, beta, static_cast<bf16 *>(y), rows, C, eps);
-    return soccdpt::check_launch("layernorm_kernel");
+    return launch_layernorm(static_cast<const bf16 *>(t), nullptr, master, accumulate, gamma, beta, static_cast<bf16 *>(y),
+                            rows, C, eps, soccdpt::as_stream(stream));
 }
 
 int soccdpt_patch_merge_gather_fwd(const void *x, void *y, int batch, int H, int W, int C, soccdpt_stream_t stream) {

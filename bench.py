@@ -11,10 +11,11 @@ runs the same per-GPU batch (weak scaling), there is no collective on the data p
 1920x1080 pinhole camera of SURVEY.md 8d).  Rank 0 prints ONE JSON line.
 
   value     frames/s with the input batch already resident in HBM (CUDA events, max over ranks)
-  e2e       frames/s through the same public call with the batch in PINNED HOST memory: every step
-            copies the images host->device and reads the step's result back device->host
-            (network-resolution inverse depth + class maps, and the occupancy grid of the call -- in the
-            reference's semantics all B grid copies are identical, one copy is read)
+  e2e       frames/s through the public host-frame API (soccdpt_b200.pipeline.FrameStream) with the batch in
+            PINNED HOST memory: every step copies the images host->device and reads the step's result back
+            device->host (network-resolution inverse depth + class maps, and the occupancy grid of the call --
+            in the reference's semantics all B grid copies are identical, one copy is read); copies overlap
+            with compute on separate streams, the timed region spans first H2D to last D2H
   roofline  tensor-pipe roofline of the dominant kernel (conv_tcgen05_kernel): algorithmic FLOPs of all its
             launches in a step / their CUDA-event time, vs MEASURED_PEAKS.json bf16 sustained
   roofline_voxeliser   HBM roofline of the post-processing kernels (compulsory bytes / event time)
@@ -282,32 +283,27 @@ def main():
         clocks = sampler.stop() if rank == 0 else None
         launches = _cabi.launch_count() - launches0
 
-        # ---- end to end: pinned host images in, results back to pinned host buffers, every step
-        eng_plan = net.engine().plan_for(B, dev)
-        d_host = torch.empty((B, 256, 256), dtype=torch.float32).pin_memory()
-        s_host = torch.empty((B, NCLS, 256, 256), dtype=torch.float32).pin_memory()
-        g_host = torch.empty((GRID[0], GRID[1], GRID[2], NCLS), dtype=torch.float32).pin_memory()
+        # ---- end to end through the public host-frame API (soccdpt_b200.pipeline.FrameStream): pinned host
+        # images in, results back in pinned host buffers, every step; upload / compute / download overlap on
+        # three streams with double buffering.  Timed from the first H2D to the last D2H with CUDA events.
+        from soccdpt_b200.pipeline import FrameStream
+        fs = FrameStream(net, B, dev)
 
-        def step_e2e():
-            xd = x_host.to(dev, non_blocking=True)
-            o = net(xd)
-            d_host.copy_(eng_plan["depth"], non_blocking=True)
-            s_host.copy_(eng_plan["seg"], non_blocking=True)
-            g_host.copy_(o[3][0], non_blocking=True)
-            return o
+        def host_batches(n):
+            for _ in range(n):
+                yield x_host
 
-        for _ in range(3):
-            step_e2e()
+        for _ in fs.run(host_batches(3)):
+            pass
         barrier()
         s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s2.record()
-        for _ in range(args.steps):
-            step_e2e()
-        e2.record()
+        s2.record(fs.up)
+        for _ in fs.run(host_batches(args.steps)):
+            pass
+        e2.record(fs.down)
         barrier()
         ms_e2e = s2.elapsed_time(e2)
-        h2d = x_host.numel() * 4
-        d2h = (d_host.numel() + s_host.numel() + g_host.numel()) * 4
+        h2d, d2h = fs.h2d_bytes, fs.d2h_bytes
 
         agg = instrumented_pass(net, x, 3) if rank == 0 else None
 

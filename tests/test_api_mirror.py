@@ -66,3 +66,24 @@ def test_load_transforms_sizes():
         assert (w, h) == wh
     t, w, h = load_transforms("dpt_swin2_tiny_256", height=320)
     assert (w, h) == (320, 320)
+
+
+def test_base_384_state_dict_keys_equal_reference_live(tmp_path):
+    """dpt_swin2_base_384 builds with the reference's exact key set (live, build container only)."""
+    import ref_env
+    if not ref_env.reference_available():
+        pytest.skip("reference tree not present")
+    ref_loader, ref_model = ref_env.import_reference()
+    yml = write_calib_yaml(str(tmp_path / "c.yaml"))
+    mt = "dpt_swin2_base_384"
+    kw = dict(load_depth=False, num_classes=3, sigmoid=True, compute_occ=True, camera_intrinsics_yaml=yml, model_type=mt)
+    ref = ref_loader.load_model(arch=ref_model.SOccDPT_versions[3], model_kwargs=dict(kw), device=torch.device("cpu"),
+                                model_path=None, model_type=mt)
+    mine = load_model(arch=SOccDPT_versions[3], model_kwargs=dict(kw), device=torch.device("cpu"), model_path=None,
+                      model_type=mt)
+    a = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    assert list(a.keys()) == list(b.keys()) and a == b
+    for k, v in ref.state_dict().items():
+        if k.endswith("attn_mask"):
+            assert torch.equal(v, mine.state_dict()[k])

@@ -1,0 +1,37 @@
+"""SURVEY row A12 / BASELINE config 3 shape: SOccDPT V3 dpt_swin2_base_384 (window 24 -> 576-token windows,
+window 12 in the last stage, pretrained_window_sizes (12,12,12,6), 18-deep stage 2; decoder levels
+96/48/24/12, outputs 384x384) against the oracle on identical seeded weights.  Same tolerances as the tiny model."""
+import pytest
+import torch
+
+import soccdpt_oracle as O
+from soccdpt_b200 import SOccDPT_versions, load_model
+from soccdpt_b200.synthetic import seeded_state_dict, synthetic_frames, write_calib_yaml
+
+pytestmark = pytest.mark.gpu
+
+
+def test_base_384_matches_oracle(tmp_path):
+    yml = write_calib_yaml(str(tmp_path / "c.yaml"))
+    mt = "dpt_swin2_base_384"
+    net = load_model(arch=SOccDPT_versions[3],
+                     model_kwargs=dict(load_depth=False, num_classes=3, sigmoid=True, compute_occ=True,
+                                       camera_intrinsics_yaml=yml, model_type=mt),
+                     device=torch.device("cpu"), model_path=None, model_type=mt)
+    sd = seeded_state_dict(net.state_dict(), 0)
+    net.load_state_dict(sd, strict=True)
+    net.to("cuda").eval()
+    x = synthetic_frames(1, 384, 0)
+    with torch.no_grad():
+        depth, seg = (t.clone() for t in net.network(x.cuda()))
+        out = net(x.cuda())
+    torch.cuda.synchronize()
+    orc = O.OracleV3(sd, mt)
+    d_ref, s_ref, _, _ = orc.network(x)
+    derr = (depth.cpu() - d_ref).abs()
+    serr = (seg.cpu() - s_ref).abs()
+    print(f"base_384: depth max-abs err {derr.max().item():.3e} (max|d| {d_ref.abs().max().item():.3e}), "
+          f"seg max {serr.max().item():.3e} mean {serr.mean().item():.3e}")
+    assert bool((derr <= 2e-2 * d_ref.abs().max() + 2e-2 * d_ref.abs()).all())
+    assert serr.max().item() <= 8e-2 and serr.mean().item() <= 8e-3
+    assert out[0].shape == (1, 1080, 1920) and out[3].shape == (1, 256, 256, 32, 3)

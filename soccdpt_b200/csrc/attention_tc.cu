@@ -1,0 +1,338 @@
+// SwinV2 window attention on tcgen05 / TMEM for 256-token windows (16x16: stages 0-2 of
+// swinv2_tiny_window16_256, > 95 % of the attention FLOPs).  timm 0.6.12 WindowAttention +
+// SwinTransformerBlock._attn (window partition, cyclic shift, reverse) in one kernel:
+//
+//   one CTA (256 threads) per (window, head), two CTAs per SM (105 KB smem, 256 TMEM columns each)
+//   per 128-query half:
+//     S[128x256] = Qn * Kn^T         tcgen05.mma M128 N256 K32, fp32 accumulator in TMEM columns 0..255
+//     softmax                        two threads per query row (TMEM lane), each owns 128 keys:
+//                                    pass 1 adds cpb bias (+ shift mask), row max, logits back to TMEM;
+//                                    pass 2 exponentiates and writes P (bf16) into shared memory in the
+//                                    128B-swizzled K-major layout the tensor core reads
+//     O[128x32]  = P * V             tcgen05.mma M128 N32 K256 (A = P in smem, B = V^T staged through a
+//                                    register transpose), accumulated over TMEM columns 0..31
+//     out        = O / rowsum        bf16, written straight to the un-shifted token position
+//   q and k are L2-normalised in fp32 while being staged (q also carries the clamped logit scale).
+// The cyclic shift lives in the token index arithmetic; the {0,-100} mask is regenerated from region ids
+// exactly like timm's attn_mask buffer and compiled out for un-shifted blocks.
+#include "common.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+constexpr int D = 32;                     // head dim
+constexpr int TC_N = 256;                 // tokens per window
+constexpr int TC_THREADS = 256;
+constexpr int TC_SMEM_Q = 0;              // 128 rows x 64 B, SWIZZLE_64B
+constexpr int TC_SMEM_K = 8192;           // 256 rows x 64 B, SWIZZLE_64B
+constexpr int TC_SMEM_VT = 8192 + 16384;  // 4 k-blocks x (32 rows x 128 B), SWIZZLE_128B
+constexpr int TC_SMEM_P = TC_SMEM_VT + 16384;    // 4 k-blocks x (128 rows x 128 B), SWIZZLE_128B
+constexpr int TC_SMEM_MISC = TC_SMEM_P + 65536;  // region ids 256 B | row max [2][128] f32 | row sum [2][128] f32 | barrier | slot
+constexpr int TC_MISC_BYTES = 256 + 1024 + 1024 + 64;
+constexpr int TC_SMEM_BYTES = TC_SMEM_MISC + TC_MISC_BYTES + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// shared-memory matrix descriptor, K-major; swizzle_bytes in {64, 128}; 8-row groups are 8*swizzle_bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, int swizzle_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * swizzle_bytes) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(swizzle_bytes == 128 ? 2 : 4) << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t umma_idesc(int n) {   // D=f32, A=B=bf16, K-major, M=128
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n"
+        "tcgen05.wait::st.sync.aligned;"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+          "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+          "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+          "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+          "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])),
+          "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
+          "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
+          "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])),
+          "r"(__float_as_uint(v[31])) : "memory");
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&t);
+}
+__device__ __forceinline__ void load_head(const bf16 *p, float f[D]) {
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+        const uint4 u = *reinterpret_cast<const uint4 *>(p + i * 8);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 t = __bfloat1622float2(h[k]);
+            f[i * 8 + 2 * k] = t.x;
+            f[i * 8 + 2 * k + 1] = t.y;
+        }
+    }
+}
+__device__ __forceinline__ int region_of(int p, int size, int ws, int shift) {
+    // timm: slices (0,-ws), (-ws,-shift), (-shift,None) over the SHIFTED image
+    return p < size - ws ? 0 : (p < size - shift ? 1 : 2);
+}
+// 8 bf16 (one 16-byte chunk) from 8 floats scaled by s
+__device__ __forceinline__ uint4 pack8_scaled(const float *f, float s) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0] * s, f[1] * s);
+    u.y = pack_bf16x2(f[2] * s, f[3] * s);
+    u.z = pack_bf16x2(f[4] * s, f[5] * s);
+    u.w = pack_bf16x2(f[6] * s, f[7] * s);
+    return u;
+}
+
+template <bool MASK>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ biasT, const float *__restrict__ scale,
+                           bf16 *__restrict__ out, int Hs, int Ws, int C, int ws, int shift) {
+    extern __shared__ uint8_t tc_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *reg = smem + TC_SMEM_MISC;                                      // [256] region ids
+    float *s_max = reinterpret_cast<float *>(smem + TC_SMEM_MISC + 256);     // [2][128]
+    float *s_sum = s_max + 256;                                              // [2][128]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_sum + 256);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 2);
+
+    const int t = threadIdx.x, warp = t >> 5;
+    const int row = t & 127;            // query row inside the half == TMEM lane
+    const int wg = t >> 7;              // which 128 keys (and which 16 output channels) this thread owns
+    const int nwx = Ws / ws, nwy = Hs / ws;
+    const int win = blockIdx.x % (nwx * nwy), b = blockIdx.x / (nwx * nwy);
+    const int head = blockIdx.y;
+
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+
+    // token index (in the un-shifted image) of window row r, and its shift-mask region
+    auto token_of = [&](int r, int &region) -> long long {
+        const int ty = r / ws, tx = r - ty * ws;
+        const int ys = (win / nwx) * ws + ty, xs = (win % nwx) * ws + tx;
+        const int yo = (ys + shift) % Hs, xo = (xs + shift) % Ws;
+        region = MASK ? region_of(ys, Hs, ws, shift) * 3 + region_of(xs, Ws, ws, shift) : 0;
+        return ((long long)b * Hs + yo) * Ws + xo;
+    };
+
+    {   // ---- stage K (normalised, SW64) and V^T (SW128): one key row per thread
+        const int r = t;
+        int region;
+        const long long tok = token_of(r, region);
+        reg[r] = (uint8_t)region;
+        const bf16 *base = qkv + tok * 3 * C + head * D;
+        float k[D], v[D];
+        load_head(base + C, k);
+        load_head(base + 2 * C, v);
+        float kk = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) kk = fmaf(k[d], k[d], kk);
+        const float ks = 1.0f / fmaxf(sqrtf(kk), 1e-12f);     // F.normalize eps
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4)   // 4 x 16-byte chunks of the 64-byte row, Swizzle<2,4,3>
+            *reinterpret_cast<uint4 *>(smem + TC_SMEM_K + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4)) = pack8_scaled(k + c4 * 8, ks);
+        // V^T: element (d, key r) -> k-block r/64, row d, column r%64 (128-byte rows, Swizzle<3,4,3>)
+        const int kb = r >> 6, col = r & 63;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int off = TC_SMEM_VT + kb * 4096 + d * 128 + (((col >> 3) ^ (d & 7)) << 4) + (col & 7) * 2;
+            *reinterpret_cast<bf16 *>(smem + off) = __float2bfloat16_rn(v[d]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 TMEM lanes
+    const float sc = scale[head];
+    const float LOG2E = 1.4426950408889634f;
+    uint32_t phase = 0;
+
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        const int r = half * 128 + row;           // my query row inside the window
+        int my_reg;
+        const long long tok = token_of(r, my_reg);
+        if (wg == 0) {   // stage normalised, scaled Q of this half (row `row`)
+            float q[D];
+            load_head(qkv + tok * 3 * C + head * D, q);
+            float qq = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) qq = fmaf(q[d], q[d], qq);
+            const float qs = sc / fmaxf(sqrtf(qq), 1e-12f);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4)
+                *reinterpret_cast<uint4 *>(smem + TC_SMEM_Q + row * 64 + ((c4 ^ ((row >> 1) & 3)) << 4)) = pack8_scaled(q + c4 * 8, qs);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da = umma_desc(smem_u32(smem + TC_SMEM_Q), 64), db = umma_desc(smem_u32(smem + TC_SMEM_K), 64);
+            const uint32_t idesc = umma_idesc(TC_N);
+            umma_f16(tmem, da, db, idesc, 0u);
+            umma_f16(tmem, da + 2, db + 2, idesc, 1u);      // second K step: +32 bytes
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- pass 1 over my 128 keys: logits = S + bias (+ mask), row max, logits back to TMEM
+        const int key0 = wg * 128;
+        const float *bias = biasT + ((size_t)head * TC_N + key0) * TC_N + r;   // biasT[h][key j][query i]: coalesced over i
+        float m = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+            float v[32];
+            tmem_ld32(t_row + (uint32_t)(key0 + c0), v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = v[j] + __ldg(bias + (size_t)(c0 + j) * TC_N);
+                if (MASK) x += (reg[key0 + c0 + j] != my_reg) ? -100.0f : 0.0f;
+                v[j] = x;
+                m = fmaxf(m, x);
+            }
+            tmem_st32(t_row + (uint32_t)(key0 + c0), v);
+        }
+        s_max[wg * 128 + row] = m;
+        __syncthreads();
+        m = fmaxf(m, s_max[(wg ^ 1) * 128 + row]);
+        // ---- pass 2: P = exp(logit - max) -> bf16, K-major SW128 rows in smem; partial row sum
+        const float ml = m * LOG2E;
+        float l = 0.f;
+#pragma unroll 1
+        for (int kk = 0; kk < 2; ++kk) {
+            const int kb = wg * 2 + kk;
+            uint8_t *prow = smem + TC_SMEM_P + kb * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                float v[32];
+                tmem_ld32(t_row + (uint32_t)(kb * 64 + hh * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = fast_exp2(fmaf(v[j], LOG2E, -ml));
+                    l += v[j];
+                }
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4)
+                    *reinterpret_cast<uint4 *>(prow + (((hh * 4 + c4) ^ (row & 7)) << 4)) = pack8_scaled(v + c4 * 8, 1.0f);
+            }
+        }
+        s_sum[wg * 128 + row] = l;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                       // all S reads done, all P rows written, partial sums visible
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t idesc = umma_idesc(D);
+#pragma unroll 1
+            for (int kb = 0; kb < 4; ++kb) {
+                const uint64_t da = umma_desc(smem_u32(smem + TC_SMEM_P + kb * 16384), 128);
+                const uint64_t db = umma_desc(smem_u32(smem + TC_SMEM_VT + kb * 4096), 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(bar);
+        }
+        l += s_sum[(wg ^ 1) * 128 + row];
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {   // ---- epilogue: my 16 output channels: O / l -> bf16 -> out[token, head*32 + wg*16 ...]
+            float o[16];
+            tmem_ld16(t_row + (uint32_t)(wg * 16), o);
+            const float inv = 1.0f / l;
+            bf16 *op = out + tok * C + head * D + wg * 16;
+            *reinterpret_cast<uint4 *>(op) = pack8_scaled(o, inv);
+            *reinterpret_cast<uint4 *>(op + 8) = pack8_scaled(o + 8, inv);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                       // O read by everyone before the next half overwrites TMEM / Q / s_max
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+    }
+}
+
+}  // namespace
+
+namespace soccdpt {
+// qkv bf16 [B, Hs*Ws, 3C]; biasT f32 [heads][256 keys][256 queries]; window must be 16x16
+int launch_window_attention_tc(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
+                               int C, int heads, int ws, int shift, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        SOCCDPT_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        SOCCDPT_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid((unsigned)(batch * (Hs / ws) * (Ws / ws)), (unsigned)heads);
+    if (shift > 0)
+        window_attention_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(
+            static_cast<const bf16 *>(qkv), biasT, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift);
+    else
+        window_attention_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(
+            static_cast<const bf16 *>(qkv), biasT, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift);
+    return check_launch("window_attention_tc_kernel");
+}
+}  // namespace soccdpt

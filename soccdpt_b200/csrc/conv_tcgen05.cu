@@ -17,7 +17,13 @@
 //   with per-element runtime branches it ran ~170 warp-instructions per 16 columns and was as long as the
 //   whole K=2304 mainloop.
 // * persistent: grid = min(tiles, SMs); 4-stage smem ring (A 16 KB + B <=32 KB per stage).
+// * HALO variant for 3x3 convs on 128-pixel row segments: the kernel is bound by bytes ARRIVING per SM
+//   (~64 B/clk), and re-loading the 16 KB activation tile for each of the 9 taps is most of them.  Instead one
+//   TMA box {64 ch, 130 px, 3 rows} per channel block is loaded once and the nine taps are issued from it with
+//   row-offset shared-memory descriptors (matrix-base-offset field) -> 3.4x fewer activation bytes.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -42,7 +48,17 @@ constexpr int NUM_THREADS = 384;          // 4 control warps + 8 epilogue warps
 constexpr int EPI_THREADS = 256;          // two epilogue warpgroups, each owns half of the tile's columns
 // dynamic smem: ring + epilogue constants (bias 256 f32 + proj 4x256 f32 + proj bias) + barriers
 constexpr int EPI_CONST_BYTES = (256 + 4 * 256 + 4 + 128 * 4) * 4;   // bias, proj weights, proj bias, proj partials
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_CONST_BYTES + 256 + 1024 /*alignment slack*/;
+// HALO variant (3x3, W % 128 == 0): one TMA box {64 ch, 130 px, 3 rows} per channel block serves all 9 taps
+constexpr int HALO_W = BLOCK_M + 2;                      // 130 pixels per halo row
+constexpr int HALO_ROWS = 3 * HALO_W;                    // 390 rows of 128 B
+constexpr int HALO_BYTES = HALO_ROWS * BLOCK_K * 2;      // 49920 B moved by TMA
+constexpr int HALO_STAGE_BYTES = 50 * 1024;              // 1024-aligned slot
+constexpr int HALO_A_STAGES = 2;
+constexpr int HALO_B_STAGES = 3;
+constexpr int RING_BYTES_PLAIN = STAGES * STAGE_BYTES;                                           // 196608
+constexpr int RING_BYTES_HALO = HALO_A_STAGES * HALO_STAGE_BYTES + HALO_B_STAGES * B_STAGE_BYTES; // 200704
+constexpr int RING_BYTES = RING_BYTES_HALO > RING_BYTES_PLAIN ? RING_BYTES_HALO : RING_BYTES_PLAIN;
+constexpr int SMEM_BYTES = RING_BYTES + EPI_CONST_BYTES + 256 + 1024 /*alignment slack*/;
 
 struct Params {
     // tile geometry
@@ -104,6 +120,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
     return d;
 }
+// Same, for a tile that starts at an arbitrary 128-byte row of a swizzled buffer (tap offsets into the halo):
+// the "matrix base offset" field (bits [49,52)) carries (address >> 7) & 7, the row phase of the 1024-byte
+// swizzle pattern the data was written with.
+__device__ __forceinline__ uint64_t umma_desc_rows(uint32_t smem_addr) {
+    return umma_desc(smem_addr) | ((uint64_t)((smem_addr >> 7) & 7u) << 49);
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
 __device__ __forceinline__ uint32_t umma_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -138,7 +160,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// exact-erf GELU (timm Mlp act) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the
+// bf16 output rounding): 1 MUFU.RCP + 1 MUFU.EX2 + ~12 FMAs instead of ~35 instructions for erff().
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+    const float erf_abs = fmaf(-poly * t, e, 1.0f);           // erf(|x|/sqrt2)
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 // ------------------------------------------------------------------ the kernel
 // v[8*N] += bf16 values at p (N x 16 bytes)
@@ -177,20 +213,23 @@ __device__ __forceinline__ void store_bf16(const float (&v)[LEN], uint4 *p) {
 // MODE 0: y = act(acc + bias)            (no residual, no ReLU copy, no projection)
 // MODE 1: general: optional res1 / res2 / y / y_relu
 // MODE 2: fused projection only (proj_out), no y
-template <int ACT, int MODE>
+// HALO : 3x3 conv whose M tile is 128 consecutive pixels of one image row -> halo reuse (see constants above)
+template <int ACT, int MODE, bool HALO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float *s_bias = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
+    float *s_bias = reinterpret_cast<float *>(smem + RING_BYTES);
     float *s_projw = s_bias + 256;
     float *s_projb = s_projw + 4 * 256;
     uint64_t *full = reinterpret_cast<uint64_t *>(s_projb + 4 + 128 * 4);   // after the [128][4] projection partials
     uint64_t *empty = full + STAGES;
     uint64_t *acc_full = empty + STAGES;
     uint64_t *acc_empty = acc_full + ACC_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + ACC_STAGES);
+    uint64_t *a_full = acc_empty + ACC_STAGES;           // HALO: ring of halo tiles (full/empty above = weight ring)
+    uint64_t *a_empty = a_full + HALO_A_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_empty + HALO_A_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const soccdpt_conv_t &c = p.c;
@@ -202,6 +241,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_THREADS); }
+        for (int s = 0; s < HALO_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -219,12 +259,29 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, a_stage = 0;
+            uint32_t phase = 0, a_phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
                 const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+                if (HALO) {
+                    // channel-block outer, tap inner: one halo tile (A ring) feeds nine weight tiles (B ring)
+                    uint8_t *b_ring = smem + HALO_A_STAGES * HALO_STAGE_BYTES;
+                    for (int cb = 0; cb < p.k_blocks_per_tap; ++cb) {
+                        mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+                        mbar_expect_tx(&a_full[a_stage], HALO_BYTES);
+                        tma_load_4d(smem + a_stage * HALO_STAGE_BYTES, &map_a, &a_full[a_stage], cb * BLOCK_K, w0 - 1, h0 - 1, n0);
+                        if (++a_stage == HALO_A_STAGES) { a_stage = 0; a_phase ^= 1; }
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&empty[stage], phase ^ 1);
+                            mbar_expect_tx(&full[stage], p.b_bytes);
+                            tma_load_3d(b_ring + stage * B_STAGE_BYTES, &map_b, &full[stage], cb * BLOCK_K, tap, nb * p.block_n);
+                            if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    continue;
+                }
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     const int tap = kb / p.k_blocks_per_tap, cb = kb - tap * p.k_blocks_per_tap;
                     const int kh = tap / c.KW, kw = tap - kh * c.KW;
@@ -241,14 +298,41 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(p.block_n);
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, a_stage = 0;
+            uint32_t phase = 0, a_phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+                if (HALO) {
+                    const uint32_t b_ring = smem_u32(smem + HALO_A_STAGES * HALO_STAGE_BYTES);
+                    for (int cb = 0; cb < p.k_blocks_per_tap; ++cb) {
+                        const int rem = c.Cin - cb * BLOCK_K;
+                        const int ksteps = rem >= BLOCK_K ? BLOCK_K / UMMA_K : (rem + UMMA_K - 1) / UMMA_K;
+                        mbar_wait(&a_full[a_stage], a_phase);
+                        tc_fence_after();
+                        const uint32_t halo = smem_u32(smem + a_stage * HALO_STAGE_BYTES);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int kh = tap / 3, kw = tap - kh * 3;
+                            mbar_wait(&full[stage], phase);
+                            tc_fence_after();
+                            // output pixel bw of the tile reads halo row kh, pixel bw + kw: a plain row offset
+                            const uint64_t da = umma_desc_rows(halo + (uint32_t)((kh * HALO_W + kw) * (BLOCK_K * 2)));
+                            const uint64_t db = umma_desc(b_ring + stage * B_STAGE_BYTES);
+                            for (int k = 0; k < ksteps; ++k)
+                                umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                            umma_commit(&empty[stage]);
+                            if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                        umma_commit(&a_empty[a_stage]);      // halo slot reusable once all nine taps retired
+                        if (++a_stage == HALO_A_STAGES) { a_stage = 0; a_phase ^= 1; }
+                    }
+                    umma_commit(&acc_full[acc]);
+                    if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+                    continue;
+                }
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     const int cb = kb % p.k_blocks_per_tap;
                     const int rem = c.Cin - cb * BLOCK_K;
@@ -482,6 +566,9 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
             if (p.BN < 1) p.BN = 1;
         }
     }
+    // halo reuse: 3x3, full 128-pixel row segments (the 128^2 / 256^2 levels: both heads of the tiny model)
+    static const bool halo_enabled = !(getenv("SOCCDPT_CONV_HALO") && getenv("SOCCDPT_CONV_HALO")[0] == '0');
+    const bool halo = halo_enabled && c->KH == 3 && c->W % BLOCK_M == 0 && p.BW == BLOCK_M && p.BH == 1 && p.BN == 1;
     p.tiles_w = (c->W + p.BW - 1) / p.BW;
     p.tiles_h = (c->H + p.BH - 1) / p.BH;
     p.tiles_n = (c->N + p.BN - 1) / p.BN;
@@ -499,6 +586,7 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
         cuuint64_t dims[4] = {(cuuint64_t)c->Cin, (cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->N};
         cuuint64_t strides[3] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)c->W * c->Cin * 2, (cuuint64_t)c->H * c->W * c->Cin * 2};
         cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BN};
+        if (halo) { box[1] = HALO_W; box[2] = 3; }
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(c->x), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -523,21 +611,27 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
                                    "conv: the fused projection epilogue produces proj_out only");
     const int grid = p.total_tiles < soccdpt::sm_count() ? p.total_tiles : soccdpt::sm_count();
     cudaStream_t st = soccdpt::as_stream(stream);
-#define SOCC_LAUNCH(A, M)                                                                                          \
-    do {                                                                                                           \
-        static bool configured = false;                                                                            \
-        if (!configured) {                                                                                         \
-            SOCCDPT_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<A, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                              SMEM_BYTES));                                                        \
-            configured = true;                                                                                     \
-        }                                                                                                          \
-        conv_tcgen05_kernel<A, M><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);                          \
+#define SOCC_LAUNCH(A, M, HL)                                                                                           \
+    do {                                                                                                                \
+        static bool configured = false;                                                                                 \
+        if (!configured) {                                                                                              \
+            SOCCDPT_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<A, M, HL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              SMEM_BYTES));                                                             \
+            configured = true;                                                                                          \
+        }                                                                                                               \
+        conv_tcgen05_kernel<A, M, HL><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);                           \
     } while (0)
-#define SOCC_MODES(A)                      \
-    do {                                   \
-        if (mode == 0) SOCC_LAUNCH(A, 0);  \
-        else if (mode == 1) SOCC_LAUNCH(A, 1); \
-        else SOCC_LAUNCH(A, 2);            \
+#define SOCC_MODES(A)                                                    \
+    do {                                                                 \
+        if (halo) {                                                      \
+            if (mode == 0) SOCC_LAUNCH(A, 0, true);                      \
+            else if (mode == 1) SOCC_LAUNCH(A, 1, true);                 \
+            else SOCC_LAUNCH(A, 2, true);                                \
+        } else {                                                         \
+            if (mode == 0) SOCC_LAUNCH(A, 0, false);                     \
+            else if (mode == 1) SOCC_LAUNCH(A, 1, false);                \
+            else SOCC_LAUNCH(A, 2, false);                               \
+        }                                                                \
     } while (0)
     if (c->act == SOCCDPT_ACT_NONE) SOCC_MODES(0);
     else if (c->act == SOCCDPT_ACT_RELU) SOCC_MODES(1);

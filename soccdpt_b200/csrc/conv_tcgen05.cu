@@ -54,11 +54,12 @@ constexpr int HALO_ROWS = 3 * HALO_W;                    // 390 rows of 128 B
 constexpr int HALO_BYTES = HALO_ROWS * BLOCK_K * 2;      // 49920 B moved by TMA
 constexpr int HALO_STAGE_BYTES = 50 * 1024;              // 1024-aligned slot
 constexpr int HALO_A_STAGES = 2;
-constexpr int HALO_B_STAGES = 3;
+constexpr int HALO_B_BYTES = 3 * B_STAGE_BYTES;          // 96 KB weight ring, split into b_stages slots of one tap tile
+constexpr int MAX_B_STAGES = 24;
 constexpr int RING_BYTES_PLAIN = STAGES * STAGE_BYTES;                                           // 196608
-constexpr int RING_BYTES_HALO = HALO_A_STAGES * HALO_STAGE_BYTES + HALO_B_STAGES * B_STAGE_BYTES; // 200704
+constexpr int RING_BYTES_HALO = HALO_A_STAGES * HALO_STAGE_BYTES + HALO_B_BYTES;                  // 200704
 constexpr int RING_BYTES = RING_BYTES_HALO > RING_BYTES_PLAIN ? RING_BYTES_HALO : RING_BYTES_PLAIN;
-constexpr int SMEM_BYTES = RING_BYTES + EPI_CONST_BYTES + 256 + 1024 /*alignment slack*/;
+constexpr int SMEM_BYTES = RING_BYTES + EPI_CONST_BYTES + 512 /*barriers*/ + 1024 /*alignment slack*/;
 
 struct Params {
     // tile geometry
@@ -67,6 +68,7 @@ struct Params {
     int block_n;               // output channels per tile
     int k_blocks_per_tap;      // ceil(Cin / 64)
     int pad;                   // KH / 2
+    int b_stages;              // HALO: depth of the weight ring (96 KB / bytes per tap tile, <= 24)
     uint32_t a_bytes, b_bytes; // TMA transaction bytes per stage
     soccdpt_conv_t c;
 };
@@ -120,12 +122,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
     return d;
 }
-// Same, for a tile that starts at an arbitrary 128-byte row of a swizzled buffer (tap offsets into the halo):
-// the "matrix base offset" field (bits [49,52)) carries (address >> 7) & 7, the row phase of the 1024-byte
-// swizzle pattern the data was written with.
-__device__ __forceinline__ uint64_t umma_desc_rows(uint32_t smem_addr) {
-    return umma_desc(smem_addr) | ((uint64_t)((smem_addr >> 7) & 7u) << 49);
-}
+// Same, for a tile that starts at an arbitrary 128-byte row of a swizzled buffer (tap offsets into the halo).
+// MEASURED on B200: the tensor core applies the 128B swizzle on ABSOLUTE shared-memory address bits
+// (bits [4,7) ^= bits [7,10)), exactly like TMA when it wrote the data, so a row-offset start address needs
+// nothing else; setting the "matrix base offset" field (bits [49,52)) to (addr >> 7) & 7 gives WRONG results.
+__device__ __forceinline__ uint64_t umma_desc_rows(uint32_t smem_addr) { return umma_desc(smem_addr); }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
 __device__ __forceinline__ uint32_t umma_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -224,8 +225,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     float *s_projw = s_bias + 256;
     float *s_projb = s_projw + 4 * 256;
     uint64_t *full = reinterpret_cast<uint64_t *>(s_projb + 4 + 128 * 4);   // after the [128][4] projection partials
-    uint64_t *empty = full + STAGES;
-    uint64_t *acc_full = empty + STAGES;
+    uint64_t *empty = full + MAX_B_STAGES;
+    uint64_t *acc_full = empty + MAX_B_STAGES;
     uint64_t *acc_empty = acc_full + ACC_STAGES;
     uint64_t *a_full = acc_empty + ACC_STAGES;           // HALO: ring of halo tiles (full/empty above = weight ring)
     uint64_t *a_empty = a_full + HALO_A_STAGES;
@@ -239,7 +240,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < MAX_B_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_THREADS); }
         for (int s = 0; s < HALO_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         fence_barrier_init();
@@ -276,8 +277,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         for (int tap = 0; tap < 9; ++tap) {
                             mbar_wait(&empty[stage], phase ^ 1);
                             mbar_expect_tx(&full[stage], p.b_bytes);
-                            tma_load_3d(b_ring + stage * B_STAGE_BYTES, &map_b, &full[stage], cb * BLOCK_K, tap, nb * p.block_n);
-                            if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
+                            tma_load_3d(b_ring + stage * p.b_bytes, &map_b, &full[stage], cb * BLOCK_K, tap, nb * p.block_n);
+                            if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
                         }
                     }
                     continue;
@@ -320,11 +321,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             tc_fence_after();
                             // output pixel bw of the tile reads halo row kh, pixel bw + kw: a plain row offset
                             const uint64_t da = umma_desc_rows(halo + (uint32_t)((kh * HALO_W + kw) * (BLOCK_K * 2)));
-                            const uint64_t db = umma_desc(b_ring + stage * B_STAGE_BYTES);
+                            const uint64_t db = umma_desc(b_ring + stage * p.b_bytes);
                             for (int k = 0; k < ksteps; ++k)
                                 umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (cb | tap | k) != 0 ? 1u : 0u);
                             umma_commit(&empty[stage]);
-                            if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
+                            if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
                         }
                         umma_commit(&a_empty[a_stage]);      // halo slot reusable once all nine taps retired
                         if (++a_stage == HALO_A_STAGES) { a_stage = 0; a_phase ^= 1; }
@@ -580,6 +581,8 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     p.pad = c->KH / 2;
     p.a_bytes = (uint32_t)(p.BW * p.BH * p.BN) * BLOCK_K * 2;
     p.b_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+    p.b_stages = HALO_B_BYTES / (int)p.b_bytes;
+    if (p.b_stages > MAX_B_STAGES) p.b_stages = MAX_B_STAGES;
 
     CUtensorMap map_a, map_b;
     {

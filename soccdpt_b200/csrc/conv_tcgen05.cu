@@ -69,6 +69,7 @@ struct Params {
     int k_blocks_per_tap;      // ceil(Cin / 64)
     int pad;                   // KH / 2
     int b_stages;              // HALO: depth of the weight ring (96 KB / bytes per tap tile, <= 24)
+    int b_resident;            // HALO: the whole weight tensor (<= 96 KB) is loaded once per CTA and stays in smem
     uint32_t a_bytes, b_bytes; // TMA transaction bytes per stage
     soccdpt_conv_t c;
 };
@@ -138,6 +139,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint6
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Lean issue form for the single MMA thread: the two descriptors share their high words (constant per layout),
+// only the 32-bit low words (start address >> 4) move.  ~25 instructions per MMA in the issuing thread cost
+// ~150 cycles -- invisible behind a 128-cycle N=256 MMA, dominant for N=32 (16 cycles of tensor work).
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -262,6 +278,14 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             int stage = 0, a_stage = 0;
             uint32_t phase = 0, a_phase = 0;
+            if (HALO && p.b_resident && blockIdx.x < p.total_tiles) {
+                // narrow layers (e.g. 128->32: 72 KB of weights): fetch every (channel block, tap) tile once
+                uint8_t *b_ring = smem + HALO_A_STAGES * HALO_STAGE_BYTES;
+                mbar_expect_tx(&full[0], (uint32_t)(p.k_blocks_per_tap * 9) * p.b_bytes);
+                for (int cb = 0; cb < p.k_blocks_per_tap; ++cb)
+                    for (int tap = 0; tap < 9; ++tap)
+                        tma_load_3d(b_ring + (cb * 9 + tap) * p.b_bytes, &map_b, &full[0], cb * BLOCK_K, tap, 0);
+            }
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
@@ -274,6 +298,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         mbar_expect_tx(&a_full[a_stage], HALO_BYTES);
                         tma_load_4d(smem + a_stage * HALO_STAGE_BYTES, &map_a, &a_full[a_stage], cb * BLOCK_K, w0 - 1, h0 - 1, n0);
                         if (++a_stage == HALO_A_STAGES) { a_stage = 0; a_phase ^= 1; }
+                        if (p.b_resident) continue;
                         for (int tap = 0; tap < 9; ++tap) {
                             mbar_wait(&empty[stage], phase ^ 1);
                             mbar_expect_tx(&full[stage], p.b_bytes);
@@ -303,29 +328,68 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             uint32_t phase = 0, a_phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            if (HALO && p.b_resident && blockIdx.x < p.total_tiles) {
+                mbar_wait(&full[0], 0);                      // resident weights have landed
+                tc_fence_after();
+            }
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
                 if (HALO) {
                     const uint32_t b_ring = smem_u32(smem + HALO_A_STAGES * HALO_STAGE_BYTES);
+                    const uint32_t desc_hi = (uint32_t)(umma_desc(0) >> 32);
+                    uint32_t first = 0u;                     // becomes 1 after the first MMA of the tile
                     for (int cb = 0; cb < p.k_blocks_per_tap; ++cb) {
                         const int rem = c.Cin - cb * BLOCK_K;
                         const int ksteps = rem >= BLOCK_K ? BLOCK_K / UMMA_K : (rem + UMMA_K - 1) / UMMA_K;
                         mbar_wait(&a_full[a_stage], a_phase);
                         tc_fence_after();
-                        const uint32_t halo = smem_u32(smem + a_stage * HALO_STAGE_BYTES);
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int kh = tap / 3, kw = tap - kh * 3;
-                            mbar_wait(&full[stage], phase);
-                            tc_fence_after();
-                            // output pixel bw of the tile reads halo row kh, pixel bw + kw: a plain row offset
-                            const uint64_t da = umma_desc_rows(halo + (uint32_t)((kh * HALO_W + kw) * (BLOCK_K * 2)));
-                            const uint64_t db = umma_desc(b_ring + stage * p.b_bytes);
-                            for (int k = 0; k < ksteps; ++k)
-                                umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (cb | tap | k) != 0 ? 1u : 0u);
-                            umma_commit(&empty[stage]);
-                            if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+                        // descriptor low word of the halo tile; a tap is a constant row offset: output pixel bw of
+                        // the tile reads halo row kh, pixel bw + kw
+                        const uint32_t a_lo = (uint32_t)umma_desc(smem_u32(smem + a_stage * HALO_STAGE_BYTES));
+                        if (p.b_resident) {
+                            uint32_t b_lo = (uint32_t)umma_desc(b_ring + (uint32_t)(cb * 9) * p.b_bytes);
+                            const uint32_t b_step = p.b_bytes >> 4;
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint32_t at = a_lo + (uint32_t)(((tap / 3) * HALO_W + (tap % 3)) * 8);
+                                if (ksteps == 4) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        umma_f16_lo(d_tmem, at + 2 * k, b_lo + 2 * k, desc_hi, idesc, first);
+                                        first = 1u;
+                                    }
+                                } else {
+                                    for (int k = 0; k < ksteps; ++k) {
+                                        umma_f16_lo(d_tmem, at + 2 * k, b_lo + 2 * k, desc_hi, idesc, first);
+                                        first = 1u;
+                                    }
+                                }
+                                b_lo += b_step;
+                            }
+                        } else {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint32_t at = a_lo + (uint32_t)(((tap / 3) * HALO_W + (tap % 3)) * 8);
+                                mbar_wait(&full[stage], phase);
+                                tc_fence_after();
+                                const uint32_t b_lo = (uint32_t)umma_desc(b_ring + stage * p.b_bytes);
+                                if (ksteps == 4) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        umma_f16_lo(d_tmem, at + 2 * k, b_lo + 2 * k, desc_hi, idesc, first);
+                                        first = 1u;
+                                    }
+                                } else {
+                                    for (int k = 0; k < ksteps; ++k) {
+                                        umma_f16_lo(d_tmem, at + 2 * k, b_lo + 2 * k, desc_hi, idesc, first);
+                                        first = 1u;
+                                    }
+                                }
+                                umma_commit(&empty[stage]);
+                                if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+                            }
                         }
                         umma_commit(&a_empty[a_stage]);      // halo slot reusable once all nine taps retired
                         if (++a_stage == HALO_A_STAGES) { a_stage = 0; a_phase ^= 1; }
@@ -341,10 +405,14 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t da = umma_desc(sa), db = umma_desc(sa + A_STAGE_BYTES);
-                    for (int k = 0; k < ksteps; ++k) {
-                        // advance both descriptors by k * 32 B inside the 128 B swizzle row
-                        umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    const uint32_t a_lo = (uint32_t)umma_desc(sa), b_lo = a_lo + (A_STAGE_BYTES >> 4);
+                    const uint32_t desc_hi = (uint32_t)(umma_desc(0) >> 32);
+                    // advance both descriptors by k * 32 B inside the 128 B swizzle row
+                    if (ksteps == 4) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                    } else {
+                        for (int k = 0; k < ksteps; ++k) umma_f16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);              // frees the smem slot once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -570,6 +638,8 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     // halo reuse: 3x3, full 128-pixel row segments (the 128^2 / 256^2 levels: both heads of the tiny model)
     static const bool halo_enabled = !(getenv("SOCCDPT_CONV_HALO") && getenv("SOCCDPT_CONV_HALO")[0] == '0');
     const bool halo = halo_enabled && c->KH == 3 && c->W % BLOCK_M == 0 && p.BW == BLOCK_M && p.BH == 1 && p.BN == 1;
+    p.b_resident = (halo && p.block_n == c->Cout &&
+                    (long long)((c->Cin + BLOCK_K - 1) / BLOCK_K) * 9 * p.block_n * BLOCK_K * 2 <= HALO_B_BYTES) ? 1 : 0;
     p.tiles_w = (c->W + p.BW - 1) / p.BW;
     p.tiles_h = (c->H + p.BH - 1) / p.BH;
     p.tiles_n = (c->N + p.BN - 1) / p.BN;

@@ -159,6 +159,13 @@ int soccdpt_upsample_bilinear_fwd(const void *x, void *y, int N, int h, int w, i
 int soccdpt_seg_finish_fwd(const float *logits, float *seg, int N, int h, int w, int P, int act,
                            soccdpt_stream_t stream);
 
+/* depth head tail (dpt.py:209-219): Interpolate x2 (bilinear, align_corners=True) -> Conv2d(128,32,3) -> ReLU ->
+ * Conv2d(32,1,1) -> ReLU, evaluated from T = the nine 128->32 tap matrices applied at LOW resolution
+ * (T bf16 [N,h,w,9*32], channel = tap*32 + c, produced by soccdpt_conv_fwd with the re-packed weights):
+ * depth f32 [N,2h,2w] = relu(pb + pw . relu(b2 + sum_tap bilerp(T_tap)(Y+dy, X+dx))), zero outside the image */
+int soccdpt_depth_tail_fwd(const void *T, const float *b2, const float *pw, const float *pb, float *depth,
+                           int N, int h, int w, soccdpt_stream_t stream);
+
 /* dtype plumbing for the boundary: f32 <-> bf16 round-to-nearest-even, n elements */
 int soccdpt_f32_to_bf16(const float *x, void *y, long long n, soccdpt_stream_t stream);
 int soccdpt_bf16_to_f32(const void *x, float *y, long long n, soccdpt_stream_t stream);

@@ -65,6 +65,7 @@ SYMBOLS = {
     "soccdpt_patch_merge_gather_fwd": (_I, [c_void_p, c_void_p, _I, _I, _I, _I, c_void_p]),
     "soccdpt_upsample_bilinear_fwd": (_I, [c_void_p, c_void_p] + [_I] * 6 + [c_void_p]),
     "soccdpt_seg_finish_fwd": (_I, [c_void_p, c_void_p] + [_I] * 5 + [c_void_p]),
+    "soccdpt_depth_tail_fwd": (_I, [c_void_p] * 5 + [_I] * 3 + [c_void_p]),
     "soccdpt_f32_to_bf16": (_I, [c_void_p, c_void_p, _LL, c_void_p]),
     "soccdpt_bf16_to_f32": (_I, [c_void_p, c_void_p, _LL, c_void_p]),
 }

@@ -43,9 +43,9 @@ __device__ __forceinline__ int region_of(int p, int size, int ws, int shift) {
     return p < size - ws ? 0 : (p < size - shift ? 1 : 2);
 }
 
-__global__ void window_attention_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ biasT,
-                                        const float *__restrict__ scale, bf16 *__restrict__ out, int Hs, int Ws,
-                                        int C, int ws, int shift) {
+__global__ void __launch_bounds__(256)
+window_attention_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ biasT, const float *__restrict__ scale,
+                        bf16 *__restrict__ out, int Hs, int Ws, int C, int ws, int shift) {
     extern __shared__ float smem[];
     const int N = ws * ws;
     float *Ks = smem;                 // [N][32]
@@ -55,97 +55,106 @@ __global__ void window_attention_kernel(const bf16 *__restrict__ qkv, const floa
     const int nwx = Ws / ws, nwy = Hs / ws;
     const int win = blockIdx.x % (nwx * nwy), b = blockIdx.x / (nwx * nwy);
     const int head = blockIdx.y;
-    const int i = threadIdx.x;
-    const bool live = i < N;
 
-    float q[D];
-    long long tok = 0;
-    int my_reg = 0;
-    if (live) {
+    auto token_of = [&](int i, int &region) -> long long {
         const int ty = i / ws, tx = i % ws;
         const int ys = (win / nwx) * ws + ty, xs = (win % nwx) * ws + tx;   // position in the shifted image
         const int yo = (ys + shift) % Hs, xo = (xs + shift) % Ws;           // roll(-shift): shifted[y] = x[y+shift]
-        tok = ((long long)b * Hs + yo) * Ws + xo;
+        region = shift > 0 ? region_of(ys, Hs, ws, shift) * 3 + region_of(xs, Ws, ws, shift) : 0;
+        return ((long long)b * Hs + yo) * Ws + xo;
+    };
+
+    // stage normalised K and V of the whole window (a thread may own several rows: N up to 576)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        int region;
+        const long long tok = token_of(i, region);
         const bf16 *base = qkv + tok * 3 * C + head * D;
         float k[D], v[D];
-        load_head(base, q);
         load_head(base + C, k);
         load_head(base + 2 * C, v);
-        float qq = 0.f, kk = 0.f;
+        float kk = 0.f;
 #pragma unroll
-        for (int d = 0; d < D; ++d) { qq = fmaf(q[d], q[d], qq); kk = fmaf(k[d], k[d], kk); }
-        const float qs = scale[head] / fmaxf(sqrtf(qq), 1e-12f);   // F.normalize eps, logit scale folded in
-        const float ks = 1.0f / fmaxf(sqrtf(kk), 1e-12f);
+        for (int d = 0; d < D; ++d) kk = fmaf(k[d], k[d], kk);
+        const float ks = 1.0f / fmaxf(sqrtf(kk), 1e-12f);                   // F.normalize eps
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            q[d] *= qs;
             Ks[i * D + d] = k[d] * ks;
             Vs[i * D + d] = v[d];
         }
-        my_reg = shift > 0 ? region_of(ys, Hs, ws, shift) * 3 + region_of(xs, Ws, ws, shift) : 0;
-        reg[i] = my_reg;
+        reg[i] = region;
     }
     __syncthreads();
-    if (!live) return;
 
-    const float *bias = biasT + (size_t)head * N * N + i;   // biasT[h][j][i]
-    float m = -INFINITY, l = 0.f, acc[D];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        int my_reg;
+        const long long tok = token_of(i, my_reg);
+        float q[D];
+        load_head(qkv + tok * 3 * C + head * D, q);
+        float qq = 0.f;
 #pragma unroll
-    for (int d = 0; d < D; ++d) acc[d] = 0.f;
-    for (int j0 = 0; j0 < N; j0 += CH) {
-        float s[CH];
-        float cm = -INFINITY;
+        for (int d = 0; d < D; ++d) qq = fmaf(q[d], q[d], qq);
+        const float qs = scale[head] / fmaxf(sqrtf(qq), 1e-12f);            // logit scale folded in
 #pragma unroll
-        for (int jj = 0; jj < CH; ++jj) {
-            const int j = j0 + jj;
-            const float4 *kp = reinterpret_cast<const float4 *>(Ks + j * D);
-            float dot = 0.f;
+        for (int d = 0; d < D; ++d) q[d] *= qs;
+
+        const float *bias = biasT + (size_t)head * N * N + i;   // biasT[h][j][i]
+        float m = -INFINITY, l = 0.f, acc[D];
 #pragma unroll
-            for (int d4 = 0; d4 < D / 4; ++d4) {
-                const float4 kv = kp[d4];
-                dot = fmaf(q[d4 * 4 + 0], kv.x, dot);
-                dot = fmaf(q[d4 * 4 + 1], kv.y, dot);
-                dot = fmaf(q[d4 * 4 + 2], kv.z, dot);
-                dot = fmaf(q[d4 * 4 + 3], kv.w, dot);
+        for (int d = 0; d < D; ++d) acc[d] = 0.f;
+        for (int j0 = 0; j0 < N; j0 += CH) {
+            float s[CH];
+            float cm = -INFINITY;
+#pragma unroll
+            for (int jj = 0; jj < CH; ++jj) {
+                const int j = j0 + jj;
+                const float4 *kp = reinterpret_cast<const float4 *>(Ks + j * D);
+                float dot = 0.f;
+#pragma unroll
+                for (int d4 = 0; d4 < D / 4; ++d4) {
+                    const float4 kv = kp[d4];
+                    dot = fmaf(q[d4 * 4 + 0], kv.x, dot);
+                    dot = fmaf(q[d4 * 4 + 1], kv.y, dot);
+                    dot = fmaf(q[d4 * 4 + 2], kv.z, dot);
+                    dot = fmaf(q[d4 * 4 + 3], kv.w, dot);
+                }
+                dot += __ldg(bias + (size_t)j * N);
+                if (reg[j] != my_reg) dot += -100.0f;
+                s[jj] = dot;
+                cm = fmaxf(cm, dot);
             }
-            dot += __ldg(bias + (size_t)j * N);
-            if (reg[j] != my_reg) dot += -100.0f;
-            s[jj] = dot;
-            cm = fmaxf(cm, dot);
-        }
-        const float mn = fmaxf(m, cm);
-        const float corr = __expf(m - mn);
-        l *= corr;
+            const float mn = fmaxf(m, cm);
+            const float corr = __expf(m - mn);
+            l *= corr;
 #pragma unroll
-        for (int d = 0; d < D; ++d) acc[d] *= corr;
+            for (int d = 0; d < D; ++d) acc[d] *= corr;
 #pragma unroll
-        for (int jj = 0; jj < CH; ++jj) {
-            const float p = __expf(s[jj] - mn);
-            l += p;
-            const float4 *vp = reinterpret_cast<const float4 *>(Vs + (j0 + jj) * D);
+            for (int jj = 0; jj < CH; ++jj) {
+                const float p = __expf(s[jj] - mn);
+                l += p;
+                const float4 *vp = reinterpret_cast<const float4 *>(Vs + (j0 + jj) * D);
 #pragma unroll
-            for (int d4 = 0; d4 < D / 4; ++d4) {
-                const float4 vv = vp[d4];
-                acc[d4 * 4 + 0] = fmaf(p, vv.x, acc[d4 * 4 + 0]);
-                acc[d4 * 4 + 1] = fmaf(p, vv.y, acc[d4 * 4 + 1]);
-                acc[d4 * 4 + 2] = fmaf(p, vv.z, acc[d4 * 4 + 2]);
-                acc[d4 * 4 + 3] = fmaf(p, vv.w, acc[d4 * 4 + 3]);
+                for (int d4 = 0; d4 < D / 4; ++d4) {
+                    const float4 vv = vp[d4];
+                    acc[d4 * 4 + 0] = fmaf(p, vv.x, acc[d4 * 4 + 0]);
+                    acc[d4 * 4 + 1] = fmaf(p, vv.y, acc[d4 * 4 + 1]);
+                    acc[d4 * 4 + 2] = fmaf(p, vv.z, acc[d4 * 4 + 2]);
+                    acc[d4 * 4 + 3] = fmaf(p, vv.w, acc[d4 * 4 + 3]);
+                }
             }
+            m = mn;
         }
-        m = mn;
-    }
-    const float inv = 1.0f / l;
-    bf16 *op = out + tok * C + head * D;
+        const float inv = 1.0f / l;
+        bf16 *op = out + tok * C + head * D;
 #pragma unroll
-    for (int i8 = 0; i8 < D / 8; ++i8) {
-        uint4 u;
-        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+        for (int i8 = 0; i8 < D / 8; ++i8) {
+            uint4 u;
+            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(acc[i8 * 8 + 2 * k] * inv, acc[i8 * 8 + 2 * k + 1] * inv);
-        *reinterpret_cast<uint4 *>(op + i8 * 8) = u;
+            for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(acc[i8 * 8 + 2 * k] * inv, acc[i8 * 8 + 2 * k + 1] * inv);
+            *reinterpret_cast<uint4 *>(op + i8 * 8) = u;
+        }
     }
 }
-
 
 }  // namespace
 
@@ -162,7 +171,7 @@ extern "C" int soccdpt_window_attention_fwd(const void *qkv, const float *bias, 
     if (N == 256) return soccdpt::launch_window_attention_tc(qkv, bias, scale, out, batch, Hs, Ws, C, heads, ws, shift,
                                                              soccdpt::as_stream(stream));
     SOCCDPT_REQUIRE(N % CH == 0 && N <= 1024, "window_attention: window tokens must be a multiple of %d and <= 1024 (got %d)", CH, N);
-    const int threads = (N + 31) / 32 * 32;
+    const int threads = N > 256 ? 192 : (N + 31) / 32 * 32;   // larger windows: several query rows per thread
     const size_t smem = (size_t)N * D * 2 * sizeof(float) + (size_t)N * sizeof(int);
     SOCCDPT_REQUIRE(smem <= 227 * 1024, "window_attention: window too large for shared memory");
     static size_t configured = 0;

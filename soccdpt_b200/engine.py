@@ -99,8 +99,12 @@ class NetworkEngine:
                 rcu2=(_pack_conv(f.resConfUnit2.conv1.weight, dev), _f32(f.resConfUnit2.conv1.bias, dev),
                       _pack_conv(f.resConfUnit2.conv2.weight, dev), _f32(f.resConfUnit2.conv2.bias, dev)))
         oc = sc.output_conv
+        # conv 2 of the head acts on a bilinear upsample: apply its nine tap matrices at low resolution instead
+        # (rows = tap*32 + c), the gather kernel interpolates and sums them (csrc/depth_head.cu)
+        w2 = oc[2].weight.detach().float()                       # (32, 128, 3, 3)
+        w2t = w2.permute(2, 3, 0, 1).reshape(9 * w2.shape[0], w2.shape[1], 1, 1)
         W["dh"] = dict(w0=_pack_conv(oc[0].weight, dev), b0=_f32(oc[0].bias, dev),
-                       w2=_pack_conv(oc[2].weight, dev), b2=_f32(oc[2].bias, dev),
+                       w2t=_pack_conv(w2t, dev), b2=_f32(oc[2].bias, dev),
                        pw=_f32(oc[4].weight.reshape(1, -1), dev), pb=_f32(oc[4].bias, dev))
         sh = net.seg_head
         bn = sh[1]
@@ -227,11 +231,12 @@ class NetworkEngine:
         dh, sh = Wt["dh"], Wt["sh"]
         d0 = buf(B, PH, PW, F // 2)
         self._conv(plan, path, dh["w0"], B, PH, PW, F, F // 2, 3, bias=dh["b0"], y=d0)
-        d0u = buf(B, 2 * PH, 2 * PW, F // 2)
-        ops.append(_Launch("upsample", lib.soccdpt_upsample_bilinear_fwd, d0.data_ptr(), d0u.data_ptr(), B, PH, PW, 2 * PH, 2 * PW, F // 2))
+        assert dh["w2t"].shape[0] == 9 * 32, "depth head: head_features_2 must be 32"
+        taps = buf(B, PH, PW, 9 * 32)
+        self._conv(plan, d0, dh["w2t"], B, PH, PW, F // 2, 9 * 32, 1, y=taps)
         depth = buf(B, 2 * PH, 2 * PW, dtype=torch.float32)
-        self._conv(plan, d0u, dh["w2"], B, 2 * PH, 2 * PW, F // 2, 32, 3, bias=dh["b2"], act=_cabi.ACT_RELU,
-                   proj=(dh["pw"], dh["pb"], depth, True))
+        ops.append(_Launch("depth_tail", lib.soccdpt_depth_tail_fwd, taps.data_ptr(), dh["b2"].data_ptr(), dh["pw"].data_ptr(),
+                           dh["pb"].data_ptr(), depth.data_ptr(), B, PH, PW))
         P = Wt["num_classes"]
         logits = buf(B, PH, PW, P, dtype=torch.float32)
         self._conv(plan, path, sh["w0"], B, PH, PW, F, F, 3, bias=sh["b0"], act=_cabi.ACT_RELU,

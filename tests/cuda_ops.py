@@ -102,3 +102,12 @@ def window_attention(qkv, biasT, scale, B, Hs, Ws, C, heads, ws, shift):
     _cabi.check(lib.soccdpt_window_attention_fwd(qkv.data_ptr(), biasT.data_ptr(), scale.data_ptr(), out.data_ptr(), B, Hs,
                                                  Ws, C, heads, ws, shift, _s()), "window_attention")
     return out
+
+
+def depth_tail(T, b2, pw, pb):
+    lib = _cabi.load()
+    N, h, w, _ = T.shape
+    out = torch.empty((N, 2 * h, 2 * w), dtype=torch.float32, device=T.device)
+    _cabi.check(lib.soccdpt_depth_tail_fwd(T.data_ptr(), b2.data_ptr(), pw.data_ptr(), pb.data_ptr(), out.data_ptr(), N, h, w,
+                                           _s()), "depth_tail")
+    return out

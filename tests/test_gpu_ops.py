@@ -158,3 +158,20 @@ def test_conv_ref_kernel_vs_torch(N, H, W, Cin, Cout, K3):
     assert torch.allclose(yr.float().cpu(), F.relu(ref), **BF)
     if proj is not None:
         assert torch.allclose(po.cpu(), F.relu(ref @ pw.t() + pb), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("N,h,w", [(2, 16, 16), (1, 24, 40)])
+def test_depth_head_tail_equals_upsample_conv_relu_proj(N, h, w):
+    """dpt.py:209-219 restructured: tap matrices at low resolution (tcgen05 GEMM) + gather == the reference order."""
+    g = _g(12)
+    d0 = (torch.randn(N, h, w, 128, generator=g)).bfloat16()
+    w2 = torch.randn(32, 128, 3, 3, generator=g) / math.sqrt(128 * 9)
+    b2 = torch.randn(32, generator=g) * 0.1
+    pw, pb = torch.randn(1, 32, generator=g) * 0.2, torch.randn(1, generator=g) * 0.1
+    w2t = K.pack_conv_weight(w2.permute(2, 3, 0, 1).reshape(288, 128, 1, 1)).cuda()
+    T = K.conv(d0.cuda(), w2t)[0]
+    out = K.depth_tail(T, b2.cuda(), pw.reshape(-1).contiguous().cuda(), pb.cuda())
+    up = F.interpolate(d0.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
+    ref = F.relu(F.conv2d(F.relu(F.conv2d(up, w2.bfloat16().float(), b2, padding=1)), pw.view(1, 32, 1, 1), pb)).squeeze(1)
+    err = (out.cpu() - ref).abs()
+    assert err.max().item() <= 2e-2 * ref.abs().max().item() + 1e-3, (err.max().item(), ref.abs().max().item())

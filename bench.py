@@ -182,13 +182,16 @@ def conv_flops(c):
 
 
 def instrumented_pass(net, x, reps):
-    """Per-kernel CUDA-event times of one step (events bracket every launch on the launching stream)."""
+    """Per-kernel CUDA-event times of one step (events bracket every launch on the launching stream);
+    one untimed pass first, then the per-kernel MEDIAN over `reps` passes."""
     from soccdpt_b200 import _cabi
     eng = net.engine()
     plan = eng.plan_for(x.shape[0], x.device)
     stream = _cabi.current_stream()
-    agg = {}
-    for _ in range(reps):
+    samples = {}
+    meta = {}
+    PP = "postprocess(unproject_scatter+grid_expand)"
+    for rep in range(reps + 1):
         plan["x_in"].copy_(x)
         evs = []
         for op in plan["ops"]:
@@ -199,26 +202,27 @@ def instrumented_pass(net, x, reps):
             evs.append((op, s, e))
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        net.get_semantic_occupancy(plan["depth"], plan["seg"])
+        out = net.get_semantic_occupancy(plan["depth"], plan["seg"])
         e.record()
         torch.cuda.synchronize()
+        del out
+        if rep == 0:
+            continue
+        tot = {}
         for op, a, b in evs:
-            name = op.name
-            if name == "conv":
-                name = "conv_tcgen05_kernel"
-            d = agg.setdefault(name, {"ms": 0.0, "launches": 0, "flops": 0.0})
-            d["ms"] += a.elapsed_time(b)
-            d["launches"] += 1
-            if op.name == "conv":
-                d["flops"] += conv_flops(op.args[0]._obj)
-        d = agg.setdefault("postprocess(unproject_scatter+grid_expand)", {"ms": 0.0, "launches": 0, "flops": 0.0})
-        d["ms"] += s.elapsed_time(e)
-        d["launches"] += 2
-    for d in agg.values():
-        d["ms"] /= reps
-        d["launches"] //= reps
-        d["flops"] /= reps
-    return agg
+            name = "conv_tcgen05_kernel" if op.name == "conv" else op.name
+            tot[name] = tot.get(name, 0.0) + a.elapsed_time(b)
+            m = meta.setdefault(name, {"launches": 0, "flops": 0.0})
+            if rep == 1:
+                m["launches"] += 1
+                if op.name == "conv":
+                    m["flops"] += conv_flops(op.args[0]._obj)
+        tot[PP] = s.elapsed_time(e)
+        meta.setdefault(PP, {"launches": 2, "flops": 0.0})
+        for k, v in tot.items():
+            samples.setdefault(k, []).append(v)
+    return {k: {"ms": statistics.median(v), "launches": meta[k]["launches"], "flops": meta[k]["flops"]}
+            for k, v in samples.items()}
 
 
 def main():
@@ -305,7 +309,7 @@ def main():
         ms_e2e = s2.elapsed_time(e2)
         h2d, d2h = fs.h2d_bytes, fs.d2h_bytes
 
-        agg = instrumented_pass(net, x, 3) if rank == 0 else None
+        agg = instrumented_pass(net, x, 5) if rank == 0 else None
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:

@@ -126,7 +126,8 @@ int soccdpt_patch_embed_fwd(const float *x, const float *w, const float *b, cons
 
 /* timm WindowAttention (v2, cosine) incl. window partition / cyclic shift / reverse:
  *   qkv   bf16 [B, Hs*Ws, 3*C] (q|k|v, each heads x 32), biases already added by the qkv GEMM
- *   bias  f32 [heads][N][N]  = 16*sigmoid(cpb_mlp(table))[rel_idx]  (input independent, baked at load)
+ *   bias  f32 [heads][(2ws-1)^2] = 16*sigmoid(cpb_mlp(coords_table)), timm's relative-position table BEFORE the
+ *         [rel_idx] expansion (input independent, baked at load); entry (qy-ky+ws-1)*(2ws-1) + (qx-kx+ws-1)
  *   scale f32 [heads]        = exp(min(logit_scale, ln 100))
  *   out   bf16 [B, Hs*Ws, C]
  * window ws x ws (N = ws*ws tokens), shift in {0, ws/2}; the -100 shift mask is generated from

@@ -44,7 +44,7 @@ __device__ __forceinline__ int region_of(int p, int size, int ws, int shift) {
 }
 
 __global__ void __launch_bounds__(256)
-window_attention_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ biasT, const float *__restrict__ scale,
+window_attention_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ bias_tab, const float *__restrict__ scale,
                         bf16 *__restrict__ out, int Hs, int Ws, int C, int ws, int shift) {
     extern __shared__ float smem[];
     const int N = ws * ws;
@@ -97,7 +97,9 @@ window_attention_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ 
 #pragma unroll
         for (int d = 0; d < D; ++d) q[d] *= qs;
 
-        const float *bias = biasT + (size_t)head * N * N + i;   // biasT[h][j][i]
+        // cpb bias[i][j] = table[h][(qy - ky + ws - 1) * (2 ws - 1) + (qx - kx + ws - 1)]
+        const int tw = 2 * ws - 1;
+        const float *bias = bias_tab + (size_t)head * tw * tw + (i / ws + ws - 1) * tw + (i % ws) + ws - 1;
         float m = -INFINITY, l = 0.f, acc[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) acc[d] = 0.f;
@@ -117,7 +119,7 @@ window_attention_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ 
                     dot = fmaf(q[d4 * 4 + 2], kv.z, dot);
                     dot = fmaf(q[d4 * 4 + 3], kv.w, dot);
                 }
-                dot += __ldg(bias + (size_t)j * N);
+                dot += __ldg(bias - ((j / ws) * tw + (j % ws)));
                 if (reg[j] != my_reg) dot += -100.0f;
                 s[jj] = dot;
                 cm = fmaxf(cm, dot);

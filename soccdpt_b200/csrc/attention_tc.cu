@@ -28,7 +28,8 @@ constexpr int TC_SMEM_K = 8192;           // 256 rows x 64 B, SWIZZLE_64B
 constexpr int TC_SMEM_VT = 8192 + 16384;  // 4 k-blocks x (32 rows x 128 B), SWIZZLE_128B
 constexpr int TC_SMEM_P = TC_SMEM_VT + 16384;    // 4 k-blocks x (128 rows x 128 B), SWIZZLE_128B
 constexpr int TC_SMEM_MISC = TC_SMEM_P + 65536;  // region ids 256 B | row max [2][128] f32 | row sum [2][128] f32 | barrier | slot
-constexpr int TC_MISC_BYTES = 256 + 1024 + 1024 + 64;
+constexpr int TC_TAB = 31 * 31;                    // relative-position bias table of one head: (2*16-1)^2 entries
+constexpr int TC_MISC_BYTES = 256 + 1024 + 1024 + 64 + 4096;
 constexpr int TC_SMEM_BYTES = TC_SMEM_MISC + TC_MISC_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -137,7 +138,7 @@ __device__ __forceinline__ uint4 pack8_scaled(const float *f, float s) {
 
 template <bool MASK>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ biasT, const float *__restrict__ scale,
+window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ bias_tab, const float *__restrict__ scale,
                            bf16 *__restrict__ out, int Hs, int Ws, int C, int ws, int shift) {
     extern __shared__ uint8_t tc_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
@@ -146,6 +147,7 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
     float *s_sum = s_max + 256;                                              // [2][128]
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_sum + 256);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 2);
+    float *s_tab = reinterpret_cast<float *>(bar + 8);                         // [31*31] cpb bias of this head
 
     const int t = threadIdx.x, warp = t >> 5;
     const int row = t & 127;            // query row inside the half == TMEM lane
@@ -154,6 +156,7 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
     const int win = blockIdx.x % (nwx * nwy), b = blockIdx.x / (nwx * nwy);
     const int head = blockIdx.y;
 
+    for (int i = t; i < TC_TAB; i += TC_THREADS) s_tab[i] = bias_tab[(size_t)blockIdx.y * TC_TAB + i];
     if (t == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -238,15 +241,18 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
 
         // ---- pass 1 over my 128 keys: logits = S + bias (+ mask), row max, logits back to TMEM
         const int key0 = wg * 128;
-        const float *bias = biasT + ((size_t)head * TC_N + key0) * TC_N + r;   // biasT[h][key j][query i]: coalesced over i
+        // cpb bias[i][j] = table[(qy - ky + 15) * 31 + (qx - kx + 15)]: query part in a register, key part is a
+        // per-chunk constant plus a compile-time offset -> one LDS with an immediate offset per logit
+        const float *tab_q = s_tab + ((r >> 4) + 15) * 31 + (r & 15) + 15;
         float m = -INFINITY;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
             float v[32];
             tmem_ld32(t_row + (uint32_t)(key0 + c0), v);
+            const float *tab = tab_q - ((key0 + c0) >> 4) * 31;      // keys of this chunk: rows ky0, ky0 + 1
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                float x = v[j] + __ldg(bias + (size_t)(c0 + j) * TC_N);
+                float x = v[j] + tab[-((j >> 4) * 31 + (j & 15))];
                 if (MASK) x += (reg[key0 + c0 + j] != my_reg) ? -100.0f : 0.0f;
                 v[j] = x;
                 m = fmaxf(m, x);
@@ -317,8 +323,8 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
 }  // namespace
 
 namespace soccdpt {
-// qkv bf16 [B, Hs*Ws, 3C]; biasT f32 [heads][256 keys][256 queries]; window must be 16x16
-int launch_window_attention_tc(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
+// qkv bf16 [B, Hs*Ws, 3C]; bias_tab f32 [heads][31*31] relative-position table; window must be 16x16
+int launch_window_attention_tc(const void *qkv, const float *bias_tab, const float *scale, void *out, int batch, int Hs, int Ws,
                                int C, int heads, int ws, int shift, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
@@ -329,10 +335,10 @@ int launch_window_attention_tc(const void *qkv, const float *biasT, const float 
     dim3 grid((unsigned)(batch * (Hs / ws) * (Ws / ws)), (unsigned)heads);
     if (shift > 0)
         window_attention_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(
-            static_cast<const bf16 *>(qkv), biasT, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift);
+            static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift);
     else
         window_attention_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(
-            static_cast<const bf16 *>(qkv), biasT, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift);
+            static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift);
     return check_launch("window_attention_tc_kernel");
 }
 }  // namespace soccdpt

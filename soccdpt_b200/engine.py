@@ -15,7 +15,7 @@ import math
 import torch
 
 from . import _cabi
-from .model.encoder import relative_position_bias
+from .model.encoder import relative_position_bias_table
 
 
 class _Launch:
@@ -69,13 +69,13 @@ class NetworkEngine:
             for blk in layer.blocks:
                 a = blk.attn
                 C = a.qkv.weight.shape[1]
-                bias = relative_position_bias(a, blk.window_size, layer.pretrained_window)
+                bias = relative_position_bias_table(a, blk.window_size, layer.pretrained_window)
                 blocks.append(dict(
                     ws=blk.window_size, shift=blk.shift_size, heads=blk.num_heads,
                     wqkv=_bf16(a.qkv.weight, dev),
                     bqkv=_f32(torch.cat([a.q_bias.detach().float(), torch.zeros(C, device=a.q_bias.device),
                                          a.v_bias.detach().float()]), dev),
-                    biasT=_f32(bias.transpose(1, 2), dev),          # [h][key j][query i]
+                    biasT=_f32(bias, dev),                          # [h][(2ws-1)^2] relative-position table
                     scale=_f32(torch.clamp(a.logit_scale.detach().float(), max=math.log(1.0 / 0.01)).exp().reshape(-1), dev),
                     wproj=_bf16(a.proj.weight, dev), bproj=_f32(a.proj.bias, dev),
                     n1=(_f32(blk.norm1.weight, dev), _f32(blk.norm1.bias, dev)),

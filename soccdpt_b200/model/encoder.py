@@ -136,25 +136,18 @@ class SwinV2Params(nn.Module):
     forward = _no_forward
 
 
-def relative_position_bias(attn, window, pretrained_window):
-    """16*sigmoid(cpb_mlp(log-spaced coords table))[relative_position_index] -> (heads, N, N) fp32.
-    Input independent: evaluated once when weights are packed (timm WindowAttention.forward)."""
+def relative_position_bias_table(attn, window, pretrained_window):
+    """16*sigmoid(cpb_mlp(log-spaced coords table)) -> (heads, (2*window-1)**2) fp32: timm's continuous
+    relative-position bias BEFORE the relative_position_index expansion.  bias[h, i, j] of timm's
+    WindowAttention.forward is table[h, (qy-ky+window-1)*(2*window-1) + (qx-kx+window-1)] for query i=(qy,qx),
+    key j=(ky,kx).  Input independent: evaluated once when weights are packed."""
     dev = attn.qkv.weight.device
     rh = torch.arange(-(window - 1), window, dtype=torch.float32)
     table = torch.stack(torch.meshgrid([rh, rh], indexing="ij")).permute(1, 2, 0).contiguous().unsqueeze(0)
     table = table / ((pretrained_window - 1) if pretrained_window > 0 else (window - 1))
     table = table * 8
     table = torch.sign(table) * torch.log2(torch.abs(table) + 1.0) / math.log2(8)
-    ch = torch.arange(window)
-    coords = torch.flatten(torch.stack(torch.meshgrid([ch, ch], indexing="ij")), 1)
-    rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
-    rel[:, :, 0] += window - 1
-    rel[:, :, 1] += window - 1
-    rel[:, :, 0] *= 2 * window - 1
-    index = rel.sum(-1).view(-1).to(dev)
-    n = window * window
     heads = attn.logit_scale.shape[0]
     with torch.no_grad():
-        tab = attn.cpb_mlp(table.to(dev)).view(-1, heads).float()
-        bias = tab[index].view(n, n, heads).permute(2, 0, 1).contiguous()
-        return 16 * torch.sigmoid(bias)
+        tab = attn.cpb_mlp(table.to(dev)).view(-1, heads).float()       # ((2w-1)^2, heads)
+        return (16 * torch.sigmoid(tab)).t().contiguous()

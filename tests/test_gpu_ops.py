@@ -84,7 +84,7 @@ def test_window_attention_vs_timm_restatement(res, ws, target_ws, heads, shift_b
     cpb bias, shift mask, softmax, PV, reverse)."""
     ref_env.enable_shim()
     from timm.models.swin_transformer_v2 import SwinTransformerBlock
-    from soccdpt_b200.model.encoder import relative_position_bias
+    from soccdpt_b200.model.encoder import relative_position_bias_table
     C = heads * 32
     torch.manual_seed(0)
     blk = SwinTransformerBlock(C, (res, res), heads, target_ws, target_ws // 2 if shift_block else 0, 4.0, 0).eval()
@@ -103,9 +103,9 @@ def test_window_attention_vs_timm_restatement(res, ws, target_ws, heads, shift_b
         qkv = F.linear(x, a.qkv.weight, torch.cat((a.q_bias, a.k_bias, a.v_bias))).bfloat16()
         # reference path on the SAME bf16-rounded qkv: temporarily make qkv an identity on a packed input
         ref = _attn_from_qkv(blk, qkv.float(), B)
-        bias = relative_position_bias(a, ws, 0)
+        bias = relative_position_bias_table(a, ws, 0)
         scale = torch.clamp(a.logit_scale, max=math.log(100.0)).exp().reshape(-1)
-    out = K.window_attention(qkv.cuda(), bias.transpose(1, 2).contiguous().cuda(), scale.contiguous().cuda(), B, res, res, C,
+    out = K.window_attention(qkv.cuda(), bias.contiguous().cuda(), scale.contiguous().cuda(), B, res, res, C,
                              heads, ws, blk.shift_size[0])
     # bf16 operands: the tcgen05 kernel rounds the normalised, scale-multiplied q (|q| up to the logit scale) and
     # the probabilities to bf16 -> logit noise ~ 2^-9 * scale; a layout bug would give O(1) relative errors.

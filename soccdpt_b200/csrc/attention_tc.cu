@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ bias_tab, const float *__restrict__ scale,
                            bf16 *__restrict__ out, int Hs, int Ws, int C, int ws, int shift) {
     extern __shared__ uint8_t tc_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment for the 128B swizzle atoms, as an OFFSET on the __shared__ symbol: a uintptr_t round trip
+    // makes the compiler lose the address space and emit generic LD/ST for every shared-memory access
+    uint8_t *smem = tc_raw + ((1024u - (smem_u32(tc_raw) & 1023u)) & 1023u);
     uint8_t *reg = smem + TC_SMEM_MISC;                                      // [256] region ids
     float *s_max = reinterpret_cast<float *>(smem + TC_SMEM_MISC + 256);     // [2][128]
     float *s_sum = s_max + 256;                                              // [2][128]

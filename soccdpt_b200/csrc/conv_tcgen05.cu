@@ -236,7 +236,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment for the 128B swizzle atoms, as an OFFSET on the __shared__ symbol: a uintptr_t round trip
+    // makes the compiler lose the address space and emit generic LD/ST for every shared-memory access
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float *s_bias = reinterpret_cast<float *>(smem + RING_BYTES);
     float *s_projw = s_bias + 256;
     float *s_projb = s_projw + 4 * 256;

@@ -58,7 +58,7 @@ typedef struct {
 #define SOCCDPT_OCC_REFERENCE_UNION 0 /* reference semantics: OR over the batch, written to every b */
 #define SOCCDPT_OCC_PER_FRAME 1       /* extension: each frame gets only its own voxels */
 
-/* bytes of scratch (bit-packed voxel mask) the two calls below need */
+/* bytes of scratch the two calls below need: bit-packed voxel mask (+ per-row / per-column resize tables) */
 size_t soccdpt_voxel_workspace_bytes(const soccdpt_geometry_t *g, int batch, int mode);
 
 /* Replaces SOccDPT.get_semantic_occupancy from the clamp onwards + points_to_occupancy_grid

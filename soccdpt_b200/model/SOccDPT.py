@@ -120,11 +120,11 @@ class SOccDPT(BaseModel):
         inv_up = torch.empty((B, H, Wd), dtype=torch.float32, device=dev)
         seg_up = torch.empty((B, C, H, Wd), dtype=torch.float32, device=dev)
         points = torch.empty((B, H, Wd, 3), dtype=torch.float32, device=dev)
-        grid, ws, need = None, None, 0
+        grid = None
         if self.compute_occ:
             G = self.grid_size
             grid = torch.empty((B, G[0], G[1], G[2], C), dtype=torch.float32, device=dev)
-            ws, need = self._workspace(geom, B, mode, dev)
+        ws, need = self._workspace(geom, B, mode, dev)      # voxel mask + resize tables
         rc = lib.soccdpt_postprocess_fwd(
             _cabi.ptr(inv_depth), _cabi.ptr(segmentation), B, h, w, ctypes_byref(geom), _cabi.ptr(inv_up), _cabi.ptr(seg_up),
             _cabi.ptr(points), _cabi.ptr(grid), mode, _cabi.ptr(ws), need, _cabi.current_stream())

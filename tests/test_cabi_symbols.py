@@ -44,8 +44,10 @@ def test_version_and_error_paths(lib):
     assert lib.soccdpt_voxel_workspace_bytes(None, 1, 0) == 0
     g.num_classes = 3
     g.grid[0], g.grid[1], g.grid[2] = 256, 256, 32
-    assert lib.soccdpt_voxel_workspace_bytes(ctypes.byref(g), 4, 0) == 256 * 256 * 32 // 8 * 4
-    assert lib.soccdpt_voxel_workspace_bytes(ctypes.byref(g), 4, 1) == 4 * 256 * 256 * 32 // 8 * 4
+    g.height, g.width = 1080, 1920
+    tables = 1920 * 32 + 1080 * 48
+    assert lib.soccdpt_voxel_workspace_bytes(ctypes.byref(g), 4, 0) == 256 * 256 * 32 // 8 * 4 + tables
+    assert lib.soccdpt_voxel_workspace_bytes(ctypes.byref(g), 4, 1) == 4 * 256 * 256 * 32 // 8 * 4 + tables
 
 
 def test_product_never_imports_oracle(repo_root):

@@ -87,3 +87,27 @@ def test_base_384_state_dict_keys_equal_reference_live(tmp_path):
     for k, v in ref.state_dict().items():
         if k.endswith("attn_mask"):
             assert torch.equal(v, mine.state_dict()[k])
+
+
+def test_checkpoint_round_trip_like_reference(net, tmp_path):
+    """both on-disk layouts the reference writes / reads load through the same path
+    (raw state_dict, train_SOccDPT.py:437-449; {"optimizer","model"} wrapper, base_model.py:15-17)."""
+    sd = GU.tiny_state_dict(1)
+    raw, wrapped = tmp_path / "checkpoint_epoch_1.pth", tmp_path / "wrapped.pth"
+    torch.save(sd, raw)
+    torch.save({"optimizer": {"state": {}}, "model": sd}, wrapped)
+    yml = net.camera_intrinsics_yaml
+    for path in (raw, wrapped):
+        m = load_model(arch=SOccDPT_versions[3],
+                       model_kwargs=dict(load_depth=False, num_classes=3, sigmoid=True, compute_occ=True,
+                                         camera_intrinsics_yaml=yml, model_type="dpt_swin2_tiny_256"),
+                       device=torch.device("cpu"), model_path=str(path), model_type="dpt_swin2_tiny_256")
+        got = m.state_dict()
+        for k in ("depth_net.pretrained.model.layers.2.blocks.3.attn.qkv.weight", "seg_head.1.running_var",
+                  "depth_net.scratch.refinenet2.resConfUnit1.conv2.bias", "pretrained.model.patch_embed.proj.weight"):
+            assert torch.equal(got[k], sd[k]), k
+    # a checkpoint with foreign / missing keys loads with strict=False semantics (prints, never raises)
+    partial = {k: v for k, v in sd.items() if "seg_head" not in k}
+    partial["unknown.key"] = torch.zeros(1)
+    torch.save(partial, tmp_path / "partial.pth")
+    net.load_net(str(tmp_path / "partial.pth"))

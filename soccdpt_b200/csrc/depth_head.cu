@@ -5,7 +5,7 @@
 //     T[n, y, x, tap*32 + c] = sum_k W2[c, k, tap] * d0[n, y, x, k]          one GEMM, N = 9*32 = 288 (tcgen05 kernel)
 //     out[n, Y, X]           = relu( pb + sum_c pw[c] * relu( b2[c] + sum_tap bilerp(T[..., tap*32 + c])(Y+dy, X+dx) ) )
 // with taps that fall outside the upsampled image contributing zero (the conv's zero padding).  This kernel is
-// the second line: per output pixel 9 taps x 4 corners x 32 channels gathered from T (bf16, L1/L2 resident),
+// the second line, evaluated separably (vertical pass into a shared-memory row buffer, then horizontal pass),
 // fp32 accumulation.  It replaces a 1.07 GB (B=64) upsampled intermediate and a narrow N=32 implicit GEMM that
 // is bound by the tensor core's A-operand read; FLOPs drop 4x.
 #include "common.cuh"
@@ -17,71 +17,93 @@ constexpr int CO = 32;          // head_features_2
 constexpr int TAPS = 9;
 constexpr int TC = TAPS * CO;   // 288 channels of T
 
-__device__ __forceinline__ void fma8(float (&acc)[CO], int c0, const uint4 &u, float w) {
-    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 t = __bfloat1622float2(p[i]);
-        acc[c0 + 2 * i] = fmaf(w, t.x, acc[c0 + 2 * i]);
-        acc[c0 + 2 * i + 1] = fmaf(w, t.y, acc[c0 + 2 * i + 1]);
-    }
-}
+constexpr int VC = 3 * CO;      // 96 values per source column: (dx, c)
+constexpr int VP = VC + 4;      // smem pitch in floats (400 B): conflict-free float4 reads across neighbouring columns
 
-// one thread per output pixel; blocks are 16x16 output tiles so that the ~11x11 source pixels they touch
-// (70 KB of T) stay in L1
+// One CTA per output row (n, Y).  The bilinear interpolation and the zero padding of the 3x3 conv are both
+// separable, so the row is produced in two passes instead of 9 taps x 4 corners per pixel:
+//   pass A  V[x][dx*32+c] = sum_{dy: 0 <= Y+dy-1 < H} lerp_y(T[y0|y1][x][(dy*3+dx)*32 + c])      (w x 96 fp32 in smem)
+//   pass B  out[X]        = relu(pb + sum_c pw[c] relu(b2[c] + sum_{dx: 0 <= X+dx-1 < W} lerp_x(V[x0|x1][dx*32+c])))
+// 2.4x fewer FMAs than the direct gather and every T element of the three source row pairs is read once per row.
 __global__ void __launch_bounds__(256)
 depth_tail_kernel(const bf16 *__restrict__ T, const float *__restrict__ b2, const float *__restrict__ pw,
                   const float *__restrict__ pb, float *__restrict__ out, int N, int h, int w) {
+    extern __shared__ __align__(16) float V[];       // [w][VP]
     __shared__ float s_b2[CO], s_pw[CO];
     if (threadIdx.x < CO) {
         s_b2[threadIdx.x] = b2[threadIdx.x];
         s_pw[threadIdx.x] = pw[threadIdx.x];
     }
-    __syncthreads();
     const int H = 2 * h, W = 2 * w;
-    const int tiles_x = (W + 15) / 16, tiles_y = (H + 15) / 16;
-    const int tile = blockIdx.x % (tiles_x * tiles_y), n = blockIdx.x / (tiles_x * tiles_y);
-    const int X = (tile % tiles_x) * 16 + (threadIdx.x & 15), Y = (tile / tiles_x) * 16 + (threadIdx.x >> 4);
-    if (X >= W || Y >= H) return;
+    const int Y = blockIdx.x % H, n = blockIdx.x / H;
     const float sh = (float)(h - 1) / (float)(H - 1), sw = (float)(w - 1) / (float)(W - 1);   // align_corners=True
     const bf16 *Tn = T + (size_t)n * h * w * TC;
 
-    float acc[CO];
-#pragma unroll
-    for (int c = 0; c < CO; ++c) acc[c] = s_b2[c];
+    // ---- pass A: vertical interpolation + sum over the tap rows dy
+    int y0[3], y1[3];
+    float wy0[3], wy1[3];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
         const int Yt = Y + dy - 1;
-        if (Yt < 0 || Yt >= H) continue;                    // zero padding of the 3x3 conv
-        const float fy = sh * (float)Yt;
-        const int y0 = (int)fy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
-        const float ly = fy - (float)y0;
+        const bool ok = Yt >= 0 && Yt < H;                    // zero padding of the 3x3 conv
+        const float fy = sh * (float)(ok ? Yt : 0);
+        y0[dy] = (int)fy;
+        y1[dy] = y0[dy] + (y0[dy] < h - 1 ? 1 : 0);
+        const float ly = fy - (float)y0[dy];
+        wy0[dy] = ok ? 1.0f - ly : 0.0f;
+        wy1[dy] = ok ? ly : 0.0f;
+    }
+    for (int item = threadIdx.x; item < w * (VC / 8); item += 256) {
+        const int x = item / (VC / 8), q = item - x * (VC / 8);   // 8 consecutive (dx, c) values
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(Tn + ((size_t)y0[dy] * w + x) * TC + dy * VC) + q);
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(Tn + ((size_t)y1[dy] * w + x) * TC + dy * VC) + q);
+            const __nv_bfloat162 *pa = reinterpret_cast<const __nv_bfloat162 *>(&a);
+            const __nv_bfloat162 *pb2 = reinterpret_cast<const __nv_bfloat162 *>(&b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 fa = __bfloat1622float2(pa[i]), fb = __bfloat1622float2(pb2[i]);
+                acc[2 * i] = fmaf(wy0[dy], fa.x, fmaf(wy1[dy], fb.x, acc[2 * i]));
+                acc[2 * i + 1] = fmaf(wy0[dy], fa.y, fmaf(wy1[dy], fb.y, acc[2 * i + 1]));
+            }
+        }
+        float4 *dst = reinterpret_cast<float4 *>(V + x * VP + q * 8);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncthreads();
+
+    // ---- pass B: horizontal interpolation + sum over the tap columns dx, bias, ReLU, 32 -> 1, ReLU
+    const float pbias = pb[0];
+    for (int X = threadIdx.x; X < W; X += 256) {
+        float acc[CO];
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[c] = s_b2[c];
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
             const int Xt = X + dx - 1;
             if (Xt < 0 || Xt >= W) continue;
             const float fx = sw * (float)Xt;
             const int x0 = (int)fx, x1 = x0 + (x0 < w - 1 ? 1 : 0);
-            const float lx = fx - (float)x0;
-            const int tap = dy * 3 + dx;
-            const uint4 *p00 = reinterpret_cast<const uint4 *>(Tn + ((size_t)y0 * w + x0) * TC + tap * CO);
-            const uint4 *p01 = reinterpret_cast<const uint4 *>(Tn + ((size_t)y0 * w + x1) * TC + tap * CO);
-            const uint4 *p10 = reinterpret_cast<const uint4 *>(Tn + ((size_t)y1 * w + x0) * TC + tap * CO);
-            const uint4 *p11 = reinterpret_cast<const uint4 *>(Tn + ((size_t)y1 * w + x1) * TC + tap * CO);
-            const float w00 = (1.0f - ly) * (1.0f - lx), w01 = (1.0f - ly) * lx, w10 = ly * (1.0f - lx), w11 = ly * lx;
+            const float lx = fx - (float)x0, l0 = 1.0f - lx;
+            const float4 *v0 = reinterpret_cast<const float4 *>(V + x0 * VP + dx * CO);
+            const float4 *v1 = reinterpret_cast<const float4 *>(V + x1 * VP + dx * CO);
 #pragma unroll
-            for (int q = 0; q < CO / 8; ++q) {
-                fma8(acc, q * 8, __ldg(p00 + q), w00);
-                fma8(acc, q * 8, __ldg(p01 + q), w01);
-                fma8(acc, q * 8, __ldg(p10 + q), w10);
-                fma8(acc, q * 8, __ldg(p11 + q), w11);
+            for (int q = 0; q < CO / 4; ++q) {
+                const float4 a = v0[q], b = v1[q];
+                acc[4 * q + 0] = fmaf(l0, a.x, fmaf(lx, b.x, acc[4 * q + 0]));
+                acc[4 * q + 1] = fmaf(l0, a.y, fmaf(lx, b.y, acc[4 * q + 1]));
+                acc[4 * q + 2] = fmaf(l0, a.z, fmaf(lx, b.z, acc[4 * q + 2]));
+                acc[4 * q + 3] = fmaf(l0, a.w, fmaf(lx, b.w, acc[4 * q + 3]));
             }
         }
-    }
-    float s = pb[0];
+        float s = pbias;
 #pragma unroll
-    for (int c = 0; c < CO; ++c) s = fmaf(s_pw[c], fmaxf(acc[c], 0.0f), s);
-    out[((size_t)n * H + Y) * W + X] = fmaxf(s, 0.0f);
+        for (int c = 0; c < CO; ++c) s = fmaf(s_pw[c], fmaxf(acc[c], 0.0f), s);
+        out[((size_t)n * H + Y) * W + X] = fmaxf(s, 0.0f);
+    }
 }
 
 }  // namespace
@@ -90,8 +112,14 @@ extern "C" int soccdpt_depth_tail_fwd(const void *T, const float *b2, const floa
                                       int N, int h, int w, soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(T && b2 && pw && pb && depth, "depth_tail: NULL pointer");
     SOCCDPT_REQUIRE(N >= 1 && h >= 2 && w >= 2, "depth_tail: bad shape %dx%dx%d", N, h, w);
-    const int tiles = ((2 * w + 15) / 16) * ((2 * h + 15) / 16);
-    depth_tail_kernel<<<(unsigned)(tiles * N), 256, 0, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(T), b2, pw, pb,
-                                                                                      depth, N, h, w);
+    const size_t smem = (size_t)w * VP * sizeof(float);
+    SOCCDPT_REQUIRE(smem <= 200 * 1024, "depth_tail: row buffer of %zu bytes does not fit shared memory (w=%d)", smem, w);
+    static size_t configured = 0;
+    if (smem > configured) {
+        SOCCDPT_CUDA(cudaFuncSetAttribute(depth_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    depth_tail_kernel<<<(unsigned)(N * 2 * h), 256, smem, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(T), b2, pw, pb,
+                                                                                       depth, N, h, w);
     return soccdpt::check_launch("depth_tail_kernel");
 }

@@ -59,7 +59,10 @@ constexpr int MAX_B_STAGES = 24;
 constexpr int RING_BYTES_PLAIN = STAGES * STAGE_BYTES;                                           // 196608
 constexpr int RING_BYTES_HALO = HALO_A_STAGES * HALO_STAGE_BYTES + HALO_B_BYTES;                  // 200704
 constexpr int RING_BYTES = RING_BYTES_HALO > RING_BYTES_PLAIN ? RING_BYTES_HALO : RING_BYTES_PLAIN;
-constexpr int SMEM_BYTES = RING_BYTES + EPI_CONST_BYTES + 512 /*barriers*/ + 1024 /*alignment slack*/;
+// output staging for the TMA-store epilogue: one [128 rows][32 cols] bf16 tile (64-byte rows, SWIZZLE_64B) per warpgroup
+constexpr int STAGING_BYTES = 128 * 64;
+constexpr int SMEM_BYTES = RING_BYTES + 2 * STAGING_BYTES + EPI_CONST_BYTES + 512 /*barriers*/ + 1024 /*alignment slack*/;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct Params {
     // tile geometry
@@ -111,6 +114,14 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows are 128 B,
 // 8-row groups are 1024 B apart (SBO), version 1 (Blackwell), layout type 2.
@@ -227,6 +238,25 @@ __device__ __forceinline__ void store_bf16(const float (&v)[LEN], uint4 *p) {
     }
 }
 
+// Epilogue store of one 32-column chunk through shared memory + TMA: thread `row` writes its 64-byte row into the
+// 64B-swizzled staging tile (conflict-free), the warpgroup synchronises, one thread issues the bulk tensor store
+// (coalesced 64-byte row segments, clipped at the tensor bounds by the TMA unit).
+template <bool RELU>
+__device__ __forceinline__ void stage_row32(uint8_t *stage, int row, const float (&v)[32]) {
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+        uint4 u;
+        __nv_bfloat162 *b2 = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = RELU ? fmaxf(v[c4 * 8 + 2 * k], 0.0f) : v[c4 * 8 + 2 * k];
+            const float b = RELU ? fmaxf(v[c4 * 8 + 2 * k + 1], 0.0f) : v[c4 * 8 + 2 * k + 1];
+            b2[k] = __floats2bfloat162_rn(a, b);
+        }
+        *reinterpret_cast<uint4 *>(stage + row * 64 + ((c4 ^ ((row >> 1) & 3)) << 4)) = u;
+    }
+}
+
 // MODE 0: y = act(acc + bias)            (no residual, no ReLU copy, no projection)
 // MODE 1: general: optional res1 / res2 / y / y_relu
 // MODE 2: fused projection only (proj_out), no y
@@ -234,12 +264,14 @@ __device__ __forceinline__ void store_bf16(const float (&v)[LEN], uint4 *p) {
 template <int ACT, int MODE, bool HALO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_yr,
                     const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms, as an OFFSET on the __shared__ symbol: a uintptr_t round trip
     // makes the compiler lose the address space and emit generic LD/ST for every shared-memory access
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float *s_bias = reinterpret_cast<float *>(smem + RING_BYTES);
+    uint8_t *s_stage = smem + RING_BYTES;                 // 2 x 8 KB, 1024-byte aligned
+    float *s_bias = reinterpret_cast<float *>(smem + RING_BYTES + 2 * STAGING_BYTES);
     float *s_projw = s_bias + 256;
     float *s_projb = s_projw + 4 * 256;
     uint64_t *full = reinterpret_cast<uint64_t *>(s_projb + 4 + 128 * 4);   // after the [128][4] projection partials
@@ -497,15 +529,35 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         for (int j = 0; j < 32; ++j) sacc = fmaf(pw[j], v[j], sacc);
                         proj[q] = sacc;
                     }
-                } else if (valid) {
-                    const long long o = obase + col;
-                    if (MODE == 1) {
+                } else {
+                    if (MODE == 1 && valid) {
+                        const long long o = obase + col;
                         if (res1) add_bf16<4>(v, reinterpret_cast<const uint4 *>(res1 + o));
                         if (res2) add_bf16<4>(v, reinterpret_cast<const uint4 *>(res2 + o));
-                        if (y) store_bf16<4, false>(v, reinterpret_cast<uint4 *>(y + o));
-                        if (y_relu) store_bf16<4, true>(v, reinterpret_cast<uint4 *>(y_relu + o));
-                    } else {
-                        store_bf16<4, false>(v, reinterpret_cast<uint4 *>(y + o));
+                    }
+                    uint8_t *stage = s_stage + wg * STAGING_BYTES;
+                    const int bar_id = 3 + wg;                      // named barrier of this warpgroup (128 threads)
+                    if (MODE == 0 || y) {
+                        if (row == 0) tma_store_wait_read();        // previous bulk store has finished reading the tile
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                        stage_row32<false>(stage, row, v);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                        if (row == 0) {
+                            tma_store_4d(&map_y, stage, cout0 + col, tw * p.BW, th * p.BH, tn * p.BN);
+                            tma_store_commit();
+                        }
+                    }
+                    if (MODE == 1 && y_relu) {
+                        if (row == 0) tma_store_wait_read();
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                        stage_row32<true>(stage, row, v);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                        if (row == 0) {
+                            tma_store_4d(&map_yr, stage, cout0 + col, tw * p.BW, th * p.BH, tn * p.BN);
+                            tma_store_commit();
+                        }
                     }
                 }
             }
@@ -563,6 +615,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
+        if (row == 0) tma_store_wait_all();        // staged tiles must outlive the bulk stores reading them
     }
 
     tc_fence_before();
@@ -681,6 +734,21 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
         SOCCDPT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed with %d (Cout=%d taps=%d Cin=%d)", (int)r, c->Cout, taps, c->Cin);
     }
 
+    // output maps for the TMA-store epilogue: same pixel box as the A tile, 32 channels, 64-byte swizzle
+    CUtensorMap map_y = map_a, map_yr = map_a;
+    for (int which = 0; which < 2; ++which) {
+        void *dst = which == 0 ? c->y : c->y_relu;
+        if (!dst) continue;
+        SOCCDPT_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "conv: outputs must be 16-byte aligned");
+        cuuint64_t dims[4] = {(cuuint64_t)c->Cout, (cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->N};
+        cuuint64_t strides[3] = {(cuuint64_t)c->Cout * 2, (cuuint64_t)c->W * c->Cout * 2, (cuuint64_t)c->H * c->W * c->Cout * 2};
+        cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BN};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(which == 0 ? &map_y : &map_yr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dst, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SOCCDPT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+    }
     const int mode = c->proj_n > 0 ? 2 : ((c->res1 || c->res2 || c->y_relu || !c->y) ? 1 : 0);
     if (mode == 2) SOCCDPT_REQUIRE(c->y == nullptr && c->y_relu == nullptr && !c->res1 && !c->res2,
                                    "conv: the fused projection epilogue produces proj_out only");
@@ -694,7 +762,7 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
                                               SMEM_BYTES));                                                             \
             configured = true;                                                                                          \
         }                                                                                                               \
-        conv_tcgen05_kernel<A, M, HL><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);                           \
+        conv_tcgen05_kernel<A, M, HL><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, map_y, map_yr, p);                           \
     } while (0)
 #define SOCC_MODES(A)                                                    \
     do {                                                                 \

@@ -470,9 +470,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         bf16 *y = static_cast<bf16 *>(c.y);
         bf16 *y_relu = static_cast<bf16 *>(c.y_relu);
         const int m_valid = p.BW * p.BH * p.BN;
-        // column split in 16-column units: warpgroup 0 takes the first ceil(n/2)
-        const int units = p.block_n >> 4, u_split = (units + 1) >> 1;
-        const int col_begin = wg == 0 ? 0 : u_split * 16, col_end = wg == 0 ? u_split * 16 : p.block_n;
+        // column split in whole 32-column chunks (the TMA-store granule): warpgroup 0 takes ceil(chunks/2) of them,
+        // warpgroup 1 the rest plus a possible 16-column tail (N = 144, 16)
+        const int c_split = (((p.block_n >> 5) + 1) >> 1) << 5;
+        const int col_begin = wg == 0 ? 0 : c_split, col_end = wg == 0 ? c_split : p.block_n;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);

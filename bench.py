@@ -332,6 +332,13 @@ def main():
     e2e_value = frames_total / (ms_e2e * 1e-3)
 
     conv = agg["conv_tcgen05_kernel"]
+    traffic = None          # DRAM bytes of all conv launches of one step, from the committed ncu capture of this command
+    tp = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            t = json.load(f)
+        if t.get("batch") == B:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
     step_kernel_ms = sum(d["ms"] for d in agg.values())
     pp = agg["postprocess(unproject_scatter+grid_expand)"]
@@ -359,7 +366,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_tcgen05_kernel", "achieved": conv_tflops, "peak": tf_sustained,
-                     "unit": "TFLOP/s", "frac": conv_tflops / tf_sustained, "traffic": None,
+                     "unit": "TFLOP/s", "frac": conv_tflops / tf_sustained, "traffic": traffic,
+                     "traffic_note": "sum of dram__bytes_read+write over the 76 conv launches of one step (profiles/r1_conv_traffic.json)",
                      "launches_per_step": conv["launches"], "ms_per_step": conv["ms"],
                      "share_of_step_kernel_time": conv["ms"] / step_kernel_ms, "peak_source": peak_kind + " (sustained bf16)"},
         "roofline_voxeliser": {"bound": "hbm", "kernel": "unproject_scatter_kernel+grid_expand_kernel", "achieved": pp_gbs,

@@ -118,9 +118,37 @@ def make_net_case(ref_loader, ref_model):
             f.write(f"{k} {tuple(net.state_dict()[k].shape)}\n")
 
 
+def make_hybrid_case(ref_loader, ref_model):
+    """dpt_hybrid_384 through the reference with the in-memory `value` repair (ref_env.py)."""
+    yml = write_calib_yaml("/tmp/soccdpt_golden_full.yaml", FULL)
+    mt = "dpt_hybrid_384"
+    net = ref_loader.load_model(
+        arch=ref_model.SOccDPT_versions[3],
+        model_kwargs=dict(load_depth=False, num_classes=3, sigmoid=True, compute_occ=True,
+                          camera_intrinsics_yaml=yml, model_type=mt),
+        device=torch.device("cpu"), model_path=None, model_type=mt).eval()
+    sd = seeded_state_dict(net.state_dict(), 0)
+    net.load_state_dict(sd, strict=True)
+    x = synthetic_frames(1, 384, 0)
+    with torch.no_grad():
+        depth, path_1 = net.depth_net.forward(x)
+        seg = net.seg_head(path_1)
+        inv_up, seg_up, pts, grid = net(x)
+    np.savez_compressed(
+        os.path.join(GOLD, "net_hybrid_b1.npz"), depth=depth.numpy().astype(np.float16), seg=seg.numpy().astype(np.float16),
+        depth_sha=sha(depth.numpy()), seg_sha=sha(seg.numpy()), occupied=occupied(grid),
+        path1_mean_std_absmax=np.array([path_1.mean(), path_1.std(), path_1.abs().max()], np.float64),
+        n_state_keys=len(sd), torch_version=torch.__version__)
+    print("net_hybrid_b1: depth", tuple(depth.shape), float(depth.min()), float(depth.max()), "occupied", int(grid[0].sum()))
+    with open(os.path.join(GOLD, "state_keys_hybrid.txt"), "w") as f:
+        for k in net.state_dict().keys():
+            f.write(f"{k} {tuple(net.state_dict()[k].shape)}\n")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref_loader, ref_model = ref_env.import_reference()
     torch.manual_seed(0)
     make_voxel_cases(ref_model)
     make_net_case(ref_loader, ref_model)
+    make_hybrid_case(ref_loader, ref_model)

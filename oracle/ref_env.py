@@ -21,13 +21,40 @@ def enable_shim():
         sys.path.insert(0, SHIM_ROOT)
 
 
-def import_reference():
-    """Returns the reference's ``SOccDPT.model`` sub-modules (loader, SOccDPT)."""
+def _install_repaired_vit_module():
+    """The reference's hybrid constructor raises ``NameError: name 'value' is not defined``
+    (SOccDPT/model/backbones/vit.py:181-182, 222-223: the Sequential is bound to ``_`` but ``exec`` assigns
+    ``value``; the intended line survives as a comment right above).  The one-token repair is applied to the
+    module's source text IN MEMORY before it is imported -- nothing of the reference is copied into this repo."""
+    import importlib.util
+    import types
+    name = "SOccDPT.model.backbones.vit"
+    if name in sys.modules:
+        return
+    import SOccDPT.model.backbones  # noqa: F401  (package object; its __init__ is empty)
+    path = os.path.join(REFERENCE_ROOT, "SOccDPT", "model", "backbones", "vit.py")
+    with open(path) as f:
+        src = f.read()
+    patched = src.replace("        _ = nn.Sequential(", "        value = nn.Sequential(")
+    assert patched != src and patched.count("value = nn.Sequential(") >= 2, "reference vit.py no longer matches the repair"
+    mod = types.ModuleType(name)
+    mod.__file__ = path
+    mod.__package__ = "SOccDPT.model.backbones"
+    sys.modules[name] = mod
+    exec(compile(patched, path, "exec"), mod.__dict__)
+    setattr(sys.modules["SOccDPT.model.backbones"], "vit", mod)
+
+
+def import_reference(repair_hybrid=True):
+    """Returns the reference's ``SOccDPT.model`` sub-modules (loader, SOccDPT).
+    The hybrid repair (see above) is installed by default; it only touches the two broken lines."""
     if not reference_available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
     enable_shim()
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
+    if repair_hybrid:
+        _install_repaired_vit_module()
     import SOccDPT.model.loader as ref_loader  # noqa: E402
     import SOccDPT.model.SOccDPT as ref_model  # noqa: E402
     return ref_loader, ref_model

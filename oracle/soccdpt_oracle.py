@@ -45,6 +45,8 @@ ENCODERS = {
     # model_type: (timm name, hooks, stage channels)
     "dpt_swin2_tiny_256": ("swinv2_tiny_window16_256", (1, 1, 5, 1), (96, 192, 384, 768)),
     "dpt_swin2_base_384": ("swinv2_base_window12to24_192to384_22kft1k", (1, 1, 17, 1), (128, 256, 512, 1024)),
+    # ViT-B/16 + ResNetV2-50 stem; hooks: stages[0], stages[1], blocks[8], blocks[11] (dpt.py:86, vit.py:164-171)
+    "dpt_hybrid_384": ("vit_base_resnet50_384", (0, 1, 8, 11), (256, 512, 768, 768)),
 }
 
 
@@ -179,10 +181,47 @@ class OracleV3:
         self.sigmoid = sigmoid
         self.geom = geom if geom is not None else Geometry()
         self.compute_occ = compute_occ
+        self.hybrid = model_type == "dpt_hybrid_384"
+
+    @torch.no_grad()
+    def _hybrid_taps(self, x):
+        """forward_vit -> forward_adapted_unflatten(pretrained, x, "forward_flex") (vit.py:19-85, utils.py:84-133)
+        with the post-processing of _make_vit_b_rn50_backbone (vit.py:179-219, readout = "project")."""
+        m, sd, pp = self.encoder, self.sd, "depth_net.pretrained.act_postprocess"
+        b, c, h, w = x.shape
+        gh, gw = h // 16, w // 16
+        # _resize_pos_embed (vit.py:23-41)
+        tok_pe, grid_pe = m.pos_embed[:, :1], m.pos_embed[0, 1:]
+        gs = int(math.sqrt(len(grid_pe)))
+        grid_pe = F.interpolate(grid_pe.reshape(1, gs, gs, -1).permute(0, 3, 1, 2), size=(gh, gw), mode="bilinear")
+        pos = torch.cat([tok_pe, grid_pe.permute(0, 2, 3, 1).reshape(1, gh * gw, -1)], dim=1)
+        bb = m.patch_embed.backbone
+        s0 = bb.stages[0](bb.stem(x))          # hook "1": (B,256,h/4,w/4)
+        s1 = bb.stages[1](s0)                  # hook "2": (B,512,h/8,w/8)
+        s2 = bb.stages[2](s1)
+        t = m.patch_embed.proj(s2).flatten(2).transpose(1, 2)
+        t = torch.cat((m.cls_token.expand(b, -1, -1), t), dim=1) + pos
+        hooked = {}
+        for i, blk in enumerate(m.blocks):
+            t = blk(t)
+            if i in self.hooks[2:]:
+                hooked[i] = t
+
+        def readout(tk, idx):                  # ProjectReadout (utils.py:27-40) + Transpose + Unflatten + 1x1 conv
+            feats = torch.cat((tk[:, 1:], tk[:, 0].unsqueeze(1).expand_as(tk[:, 1:])), -1)
+            y = F.gelu(F.linear(feats, sd[f"{pp}{idx}.0.project.0.weight"], sd[f"{pp}{idx}.0.project.0.bias"]))
+            y = y.transpose(1, 2).unflatten(2, (gh, gw))
+            return F.conv2d(y, sd[f"{pp}{idx}.3.weight"], sd[f"{pp}{idx}.3.bias"])
+
+        l3 = readout(hooked[self.hooks[2]], 3)
+        l4 = F.conv2d(readout(hooked[self.hooks[3]], 4), sd[f"{pp}4.4.weight"], sd[f"{pp}4.4.bias"], stride=2, padding=1)
+        return [s0, s1, l3, l4]
 
     @torch.no_grad()
     def encoder_taps(self, x):
         """forward_default (utils.py:64-81) + act_postprocess (swin_common.py:38-52): 4 NCHW maps."""
+        if self.hybrid:
+            return self._hybrid_taps(x)
         m = self.encoder
         t = m.pos_drop(m.patch_embed(x))
         taps = []

@@ -19,6 +19,7 @@ cross-checked against HuggingFace ``transformers.Swinv2Model`` in
 ``tests/test_oracle_swinv2_vs_hf.py``.
 """
 from .models.swin_transformer_v2 import SwinTransformerV2
+from .models.vision_transformer_hybrid import vit_base_resnet50_384
 
 __version__ = "0.6.12+soccdpt-oracle-shim"
 
@@ -41,4 +42,6 @@ def create_model(model_name, pretrained=False, **kwargs):
         return SwinTransformerV2(
             img_size=img, window_size=ws, embed_dim=dim, depths=depths,
             num_heads=heads, pretrained_window_sizes=pws, **kwargs)
+    if model_name in ("vit_base_resnet50_384", "vit_base_r50_s16_384"):
+        return vit_base_resnet50_384(**kwargs)
     raise RuntimeError(f"timm shim: model '{model_name}' is not restated")

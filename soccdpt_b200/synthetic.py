@@ -31,13 +31,13 @@ def write_calib_yaml(path, calib=None):
     return path
 
 
-_ALIAS = "pretrained.model."
-_CANON = "depth_net.pretrained.model."
+_ALIAS = "pretrained."
+_CANON = "depth_net.pretrained."
 
 
 def seeded_state_dict(state_dict, seed=0):
     """Returns a new dict with the same keys/shapes, values drawn deterministically (sorted key
-    order, one CPU generator).  ``pretrained.model.*`` keys alias ``depth_net.pretrained.model.*``."""
+    order, one CPU generator).  ``pretrained.*`` keys alias ``depth_net.pretrained.*`` (same module registered twice)."""
     g = torch.Generator().manual_seed(seed)
     out = {}
     for k in sorted(state_dict.keys()):

@@ -51,3 +51,25 @@ def test_voxel_oracle_equals_reference_live(name, tmp_path):
     for a, b in zip(r, o):
         assert _eq(a, b)
     assert np.array_equal(net.occupancy_shape, geom.occupancy_shape)
+
+
+def test_hybrid_oracle_equals_repaired_reference(tmp_path):
+    """the reference's dpt_hybrid_384 constructor raises NameError as shipped; with the one-token
+    repair applied in memory (oracle/ref_env.py) the oracle restatement is bit-equal to it on all four outputs."""
+    ref_loader, ref_model = ref_env.import_reference()
+    yml = write_calib_yaml(str(tmp_path / "calib.yaml"))
+    mt = "dpt_hybrid_384"
+    net = ref_loader.load_model(
+        arch=ref_model.SOccDPT_versions[3],
+        model_kwargs=dict(load_depth=False, num_classes=3, sigmoid=True, compute_occ=True,
+                          camera_intrinsics_yaml=yml, model_type=mt),
+        device=torch.device("cpu"), model_path=None, model_type=mt).eval()
+    sd = seeded_state_dict(net.state_dict(), 2)
+    net.load_state_dict(sd, strict=True)
+    orc = O.OracleV3(sd, mt)
+    x = synthetic_frames(1, 384, 3)
+    with torch.no_grad():
+        ref = net(x)
+    out = orc(x)
+    for r, o in zip(ref, out):
+        assert _eq(r, o)

@@ -88,8 +88,8 @@ int soccdpt_postprocess_fwd(const float *inv_depth, const float *seg, int batch,
  *   depth head                  SOccDPT/model/dpt.py:199-219      (incl. the fused 32->1 projection)
  *   seg head                    SOccDPT/model/SOccDPT.py:660-674  (BN folded, fused 256->3 projection)
  *   timm qkv/proj/fc1/fc2/reduction linears (K=1x1 over a (1,1,M,K) "image")
- * y[n,h,w,:] = act( sum_{kh,kw,c} x[n,h+kh-KH/2,w+kw-KW/2,c] * wgt[:,kh,kw,c] + bias ) + res1 + res2
- * stride 1, zero padding KH/2 / KW/2, fp32 accumulation, bf16 storage. */
+ * y[n,h,w,:] = act( sum_{kh,kw,c} x[n,h*s+kh-pad,w*s+kw-pad,c]   (pad = KH/2 - pad_trim) * wgt[:,kh,kw,c] + bias ) + res1 + res2
+ * stride s in {1,2}, zero padding (pad before, whatever is needed after), fp32 accumulation, bf16 storage. */
 #define SOCCDPT_ACT_NONE 0
 #define SOCCDPT_ACT_RELU 1
 #define SOCCDPT_ACT_GELU 2 /* exact erf GELU (timm Mlp) */
@@ -110,6 +110,10 @@ typedef struct {
     float *proj_out;      /* f32 [N*H*W][proj_n] */
     int proj_n;           /* 1..4 */
     int proj_relu;        /* ReLU on the projection */
+    int stride;           /* 1 or 2 (0 is read as 1); outputs are [N, ceil(H/stride), ceil(W/stride), Cout] */
+    int pad_trim;         /* rows/columns of zero padding REMOVED before the first row/column: the padding in front is
+                             KH/2 - pad_trim (0 = symmetric torch padding).  TF-"SAME" 3x3 stride-2 convs on even
+                             inputs (timm StdConv2dSame) pad 0 in front / 1 behind: pad_trim = 1. */
 } soccdpt_conv_t;
 
 /* tcgen05 / TMEM / TMA kernel (the product path) */
@@ -170,6 +174,34 @@ int soccdpt_depth_tail_fwd(const void *T, const float *b2, const float *pw, cons
 /* dtype plumbing for the boundary: f32 <-> bf16 round-to-nearest-even, n elements */
 int soccdpt_f32_to_bf16(const float *x, void *y, long long n, soccdpt_stream_t stream);
 int soccdpt_bf16_to_f32(const void *x, float *y, long long n, soccdpt_stream_t stream);
+
+/* ---- ViT-hybrid encoder only (dpt_hybrid_384 = timm vit_base_resnet50_384; reference
+ * SOccDPT/model/backbones/vit.py:245-258 builds it, :44-85 forward_flex runs it, :147-242 post-processes the taps) */
+
+/* ResNetV2 stem: StdConv2dSame(3, 64, 7, stride 2) on the f32 NCHW frame; w f32 [64][3][7][7] ALREADY weight-standardised.
+ * y bf16 NHWC [batch, ceil(H/2), ceil(W/2), 64] */
+int soccdpt_stem_conv7_fwd(const float *x, const float *w, void *y, int batch, int H, int W, soccdpt_stream_t stream);
+
+/* GroupNormAct(32 groups) on NHWC bf16 [batch, HW, C]: y = [relu]( gn(x) * gamma + beta [+ shortcut] ).
+ * stats_scratch: batch*64 doubles of device memory (zeroed by the call).  C % 64 == 0. */
+int soccdpt_groupnorm_fwd(const void *x, const float *gamma, const float *beta, const void *shortcut, void *y, int batch,
+                          int HW, int C, float eps, int relu, void *stats_scratch, soccdpt_stream_t stream);
+
+/* MaxPool2dSame(3, stride 2), NHWC bf16 [batch,H,W,C] -> [batch, ceil(H/2), ceil(W/2), C] (padding value -inf) */
+int soccdpt_maxpool3s2_fwd(const void *x, void *y, int batch, int H, int W, int C, soccdpt_stream_t stream);
+
+/* tokens bf16 [batch, 1+L, D] = cat(cls f32 [D], patches bf16 [batch, L, D]) + pos f32 [1+L, D]
+ * (reference vit.py:66-80; the position embedding is used at its native 24x24 grid: 384x384 frames only) */
+int soccdpt_vit_tokens_fwd(const void *patches, const float *cls, const float *pos, void *tokens, int batch, int L, int D,
+                           soccdpt_stream_t stream);
+
+/* ProjectReadout input (reference backbones/utils.py:27-40): feats bf16 [batch, L, 2D] = cat(tokens[:,1:], tokens[:,0] expanded) */
+int soccdpt_readout_concat_fwd(const void *tokens, void *feats, int batch, int L, int D, soccdpt_stream_t stream);
+
+/* Global multi-head attention of the ViT blocks: qkv bf16 [batch, N, 3*heads*64] (q | k | v), out bf16 [batch, N, heads*64],
+ * softmax(q k^T / sqrt(64)) v with fp32 softmax.  head_dim must be 64. */
+int soccdpt_global_attention_fwd(const void *qkv, void *out, int batch, int N, int heads, int head_dim,
+                                 soccdpt_stream_t stream);
 
 #ifdef __cplusplus
 }

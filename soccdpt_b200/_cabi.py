@@ -40,7 +40,7 @@ class Conv(ctypes.Structure):
         ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cin", ctypes.c_int),
         ("Cout", ctypes.c_int), ("KH", ctypes.c_int), ("KW", ctypes.c_int), ("act", ctypes.c_int),
         ("proj_w", c_void_p), ("proj_b", c_void_p), ("proj_out", c_void_p),
-        ("proj_n", ctypes.c_int), ("proj_relu", ctypes.c_int),
+        ("proj_n", ctypes.c_int), ("proj_relu", ctypes.c_int), ("stride", ctypes.c_int), ("pad_trim", ctypes.c_int),
     ]
 
 
@@ -68,6 +68,12 @@ SYMBOLS = {
     "soccdpt_depth_tail_fwd": (_I, [c_void_p] * 5 + [_I] * 3 + [c_void_p]),
     "soccdpt_f32_to_bf16": (_I, [c_void_p, c_void_p, _LL, c_void_p]),
     "soccdpt_bf16_to_f32": (_I, [c_void_p, c_void_p, _LL, c_void_p]),
+    "soccdpt_stem_conv7_fwd": (_I, [c_void_p] * 3 + [_I] * 3 + [c_void_p]),
+    "soccdpt_groupnorm_fwd": (_I, [c_void_p] * 5 + [_I] * 3 + [_F, _I, c_void_p, c_void_p]),
+    "soccdpt_maxpool3s2_fwd": (_I, [c_void_p] * 2 + [_I] * 4 + [c_void_p]),
+    "soccdpt_vit_tokens_fwd": (_I, [c_void_p] * 4 + [_I] * 3 + [c_void_p]),
+    "soccdpt_readout_concat_fwd": (_I, [c_void_p] * 2 + [_I] * 3 + [c_void_p]),
+    "soccdpt_global_attention_fwd": (_I, [c_void_p] * 2 + [_I] * 4 + [c_void_p]),
 }
 
 

@@ -70,7 +70,8 @@ struct Params {
     int tiles_w, tiles_h, tiles_n, n_blocks, total_tiles;
     int block_n;               // output channels per tile
     int k_blocks_per_tap;      // ceil(Cin / 64)
-    int pad;                   // KH / 2
+    int pad;                   // zero padding before the first row / column
+    int stride, Ho, Wo;        // output grid = ceil(input / stride)
     int b_stages;              // HALO: depth of the weight ring (96 KB / bytes per tap tile, <= 24)
     int b_resident;            // HALO: the whole weight tensor (<= 96 KB) is loaded once per CTA and stays in smem
     uint32_t a_bytes, b_bytes; // TMA transaction bytes per stage
@@ -348,7 +349,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
                     uint8_t *sa = smem + stage * STAGE_BYTES;
-                    tma_load_4d(sa, &map_a, &full[stage], cb * BLOCK_K, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+                    tma_load_4d(sa, &map_a, &full[stage], cb * BLOCK_K, w0 * p.stride + kw - p.pad, h0 * p.stride + kh - p.pad, n0);
                     tma_load_3d(sa + A_STAGE_BYTES, &map_b, &full[stage], cb * BLOCK_K, tap, nb * p.block_n);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -492,8 +493,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             // row -> pixel
             const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
             const int wx = tw * p.BW + bw, hy = th * p.BH + bh, ni = tn * p.BN + bn;
-            const bool valid = (row < m_valid) && (wx < c.W) && (hy < c.H) && (ni < c.N);
-            const long long pix = ((long long)ni * c.H + hy) * c.W + wx;
+            const bool valid = (row < m_valid) && (wx < p.Wo) && (hy < p.Ho) && (ni < c.N);
+            const long long pix = ((long long)ni * p.Ho + hy) * p.Wo + wx;
             const long long obase = pix * c.Cout + cout0;
 
             mbar_wait(&acc_full[acc], acc_phase);
@@ -672,39 +673,43 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     p.block_n = pick_block_n(c->Cout);
     SOCCDPT_REQUIRE(p.block_n >= 16, "conv: no valid N tile for Cout=%d", c->Cout);
     if (c->proj_n > 0) SOCCDPT_REQUIRE(p.block_n == c->Cout, "conv: fused projection needs the whole Cout in one tile");
-    // M tile = box of output pixels {BW, BH, BN}
-    if (c->W >= BLOCK_M) {
-        p.BW = (c->W % BLOCK_M == 0) ? BLOCK_M : largest_divisor_leq(c->W, BLOCK_M);
+    p.stride = c->stride > 1 ? c->stride : 1;
+    p.pad = c->KH / 2 - c->pad_trim;
+    p.Ho = (c->H + p.stride - 1) / p.stride;
+    p.Wo = (c->W + p.stride - 1) / p.stride;
+    // M tile = box of OUTPUT pixels {BW, BH, BN}
+    if (p.Wo >= BLOCK_M) {
+        p.BW = (p.Wo % BLOCK_M == 0) ? BLOCK_M : largest_divisor_leq(p.Wo, BLOCK_M);
         if (p.BW < 64) p.BW = BLOCK_M;   // poor divisor: use full tiles, mask the tail
         p.BH = 1;
         p.BN = 1;
     } else {
-        p.BW = c->W;
-        const int rows = BLOCK_M / c->W;
-        if (c->H >= rows) {
-            p.BH = largest_divisor_leq(c->H, rows);
+        p.BW = p.Wo;
+        const int rows = BLOCK_M / p.Wo;
+        if (p.Ho >= rows) {
+            p.BH = largest_divisor_leq(p.Ho, rows);
             p.BN = 1;
         } else {
-            p.BH = c->H;
-            p.BN = BLOCK_M / (c->W * c->H);
+            p.BH = p.Ho;
+            p.BN = BLOCK_M / (p.Wo * p.Ho);
             if (p.BN > c->N) p.BN = c->N;
             if (p.BN < 1) p.BN = 1;
         }
     }
     // halo reuse: 3x3, full 128-pixel row segments (the 128^2 / 256^2 levels: both heads of the tiny model)
     static const bool halo_enabled = !(getenv("SOCCDPT_CONV_HALO") && getenv("SOCCDPT_CONV_HALO")[0] == '0');
-    const bool halo = halo_enabled && c->KH == 3 && c->W % BLOCK_M == 0 && p.BW == BLOCK_M && p.BH == 1 && p.BN == 1;
+    const bool halo = halo_enabled && c->KH == 3 && p.stride == 1 && p.pad == 1 && c->W % BLOCK_M == 0 && p.BW == BLOCK_M &&
+                      p.BH == 1 && p.BN == 1;
     p.b_resident = (halo && p.block_n == c->Cout &&
                     (long long)((c->Cin + BLOCK_K - 1) / BLOCK_K) * 9 * p.block_n * BLOCK_K * 2 <= HALO_B_BYTES) ? 1 : 0;
-    p.tiles_w = (c->W + p.BW - 1) / p.BW;
-    p.tiles_h = (c->H + p.BH - 1) / p.BH;
+    p.tiles_w = (p.Wo + p.BW - 1) / p.BW;
+    p.tiles_h = (p.Ho + p.BH - 1) / p.BH;
     p.tiles_n = (c->N + p.BN - 1) / p.BN;
     p.n_blocks = c->Cout / p.block_n;
     const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
     SOCCDPT_REQUIRE(total < (1ll << 31), "conv: too many tiles");
     p.total_tiles = (int)total;
     p.k_blocks_per_tap = (c->Cin + BLOCK_K - 1) / BLOCK_K;
-    p.pad = c->KH / 2;
     p.a_bytes = (uint32_t)(p.BW * p.BH * p.BN) * BLOCK_K * 2;
     p.b_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
     p.b_stages = HALO_B_BYTES / (int)p.b_bytes;
@@ -714,9 +719,11 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     {
         cuuint64_t dims[4] = {(cuuint64_t)c->Cin, (cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->N};
         cuuint64_t strides[3] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)c->W * c->Cin * 2, (cuuint64_t)c->H * c->W * c->Cin * 2};
-        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BN};
+        // stride 2: the box spans stride*BW input pixels and the traversal stride keeps every second one
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(p.BW * p.stride), (cuuint32_t)(p.BH * p.stride), (cuuint32_t)p.BN};
         if (halo) { box[1] = HALO_W; box[2] = 3; }
-        cuuint32_t estr[4] = {1, 1, 1, 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)p.stride, (cuuint32_t)p.stride, 1};
+        SOCCDPT_REQUIRE(box[1] <= 256 && box[2] <= 256, "conv: tile too wide for a strided TMA box");
         CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(c->x), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -741,8 +748,8 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
         void *dst = which == 0 ? c->y : c->y_relu;
         if (!dst) continue;
         SOCCDPT_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "conv: outputs must be 16-byte aligned");
-        cuuint64_t dims[4] = {(cuuint64_t)c->Cout, (cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->N};
-        cuuint64_t strides[3] = {(cuuint64_t)c->Cout * 2, (cuuint64_t)c->W * c->Cout * 2, (cuuint64_t)c->H * c->W * c->Cout * 2};
+        cuuint64_t dims[4] = {(cuuint64_t)c->Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)c->N};
+        cuuint64_t strides[3] = {(cuuint64_t)c->Cout * 2, (cuuint64_t)p.Wo * c->Cout * 2, (cuuint64_t)p.Ho * p.Wo * c->Cout * 2};
         cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BN};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(which == 0 ? &map_y : &map_yr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dst, dims, strides, box, estr,

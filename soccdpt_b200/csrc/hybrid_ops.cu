@@ -1,0 +1,363 @@
+// Kernels that only the ViT-hybrid encoder (dpt_hybrid_384: timm vit_base_resnet50_384) needs:
+//   stem conv 7x7 stride 2 with TF-"SAME" padding (StdConv2dSame, weights standardised at pack time),
+//   GroupNorm(32) [+ shortcut add] [+ ReLU] on NHWC bf16, MaxPool2dSame 3x3 stride 2, ViT token assembly
+//   (cls token + position embedding), ProjectReadout concat, and global multi-head attention (577 tokens, d = 64).
+// Reference call sites: SOccDPT/model/backbones/vit.py:44-85 (forward_flex), :147-242 (post-processing),
+// SOccDPT/model/backbones/utils.py:27-40 (ProjectReadout); the arithmetic itself is timm 0.6.12's.
+#include "common.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ void unpack8(const uint4 &u, float f[8]) {
+    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(p[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float f[8]) {
+    uint4 u;
+    __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return u;
+}
+
+// ------------------------------------------------------------------ stem: conv 7x7 s2, 3 -> 64, SAME padding
+// x f32 NCHW [B,3,H,W] -> y bf16 NHWC [B,H/2,W/2,64].  Block = 4 output pixels x 64 channels; the standardised
+// weights live in shared memory as [147][64].
+__global__ void __launch_bounds__(256)
+stem_conv7_kernel(const float *__restrict__ x, const float *__restrict__ w, bf16 *__restrict__ y, int B, int H, int W) {
+    __shared__ float sw[147 * 64];
+    __shared__ float patch[4][148];
+    for (int i = threadIdx.x; i < 147 * 64; i += 256) {
+        const int co = i / 147, k = i - co * 147;       // w is [64][3][7][7]
+        sw[k * 64 + co] = w[i];
+    }
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    const int pad_h = max((Ho - 1) * 2 + 7 - H, 0) / 2, pad_w = max((Wo - 1) * 2 + 7 - W, 0) / 2;   // SAME: floor(total/2) first
+    const long long total = (long long)B * Ho * Wo;
+    const int lp = threadIdx.x >> 6, co = threadIdx.x & 63;
+    for (long long base = (long long)blockIdx.x * 4; base < total; base += (long long)gridDim.x * 4) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * 147; i += 256) {
+            const int pp = i / 147, k = i - pp * 147;
+            const long long pix = base + pp;
+            float v = 0.0f;
+            if (pix < total) {
+                const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+                const int ci = k / 49, ky = (k % 49) / 7, kx = k % 7;
+                const int iy = oy * 2 + ky - pad_h, ix = ox * 2 + kx - pad_w;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long long)n * 3 + ci) * H + iy) * W + ix];
+            }
+            patch[pp][k] = v;
+        }
+        __syncthreads();
+        const long long pix = base + lp;
+        if (pix < total) {
+            float acc = 0.0f;
+#pragma unroll 7
+            for (int k = 0; k < 147; ++k) acc = fmaf(patch[lp][k], sw[k * 64 + co], acc);
+            y[pix * 64 + co] = __float2bfloat16_rn(acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ GroupNorm(32 groups), NHWC bf16
+// pass 1: per-(image, group) sum / sum of squares: every block reduces a slab of pixels for all groups in shared
+// memory, then one double atomicAdd per (group, statistic).  pass 2: normalise (+ shortcut) (+ ReLU).
+__global__ void __launch_bounds__(256)
+groupnorm_stats_kernel(const bf16 *__restrict__ x, double *__restrict__ stats, int HW, int C, int slabs) {
+    __shared__ float s_sum[32], s_sq[32];
+    if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+    __syncthreads();
+    const int n = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const int chunks = C / 8, cpg = C / 32;               // channels per group (>= 2)
+    const long long items = (long long)HW * chunks;
+    const long long per = (items + slabs - 1) / slabs;
+    const long long i0 = slab * per, i1 = min(items, i0 + per);
+    const bf16 *xn = x + (long long)n * HW * C;
+    for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+        const int ck = (int)(i % chunks);
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4 *>(xn + (i / chunks) * C + ck * 8), f);
+        if (cpg >= 8) {                                    // the 8 values belong to one group
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s += f[k]; q = fmaf(f[k], f[k], q); }
+            const int g = (ck * 8) / cpg;
+            atomicAdd(&s_sum[g], s);
+            atomicAdd(&s_sq[g], q);
+        } else {                                           // cpg in {2, 4}: several groups inside the chunk
+#pragma unroll
+            for (int k0 = 0; k0 < 8; k0 += 2) {
+                const int g = (ck * 8 + k0) / cpg;
+                atomicAdd(&s_sum[g], f[k0] + f[k0 + 1]);
+                atomicAdd(&s_sq[g], fmaf(f[k0], f[k0], f[k0 + 1] * f[k0 + 1]));
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        atomicAdd(&stats[((long long)n * 32 + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x]);
+        atomicAdd(&stats[((long long)n * 32 + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+groupnorm_apply_kernel(const bf16 *__restrict__ x, const double *__restrict__ stats, const float *__restrict__ gamma,
+                       const float *__restrict__ beta, const bf16 *__restrict__ shortcut, bf16 *__restrict__ y, long long total_chunks,
+                       int HW, int C, float eps, int relu) {
+    const int chunks = C / 8, cpg = C / 32;
+    const double cnt = (double)HW * cpg;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total_chunks; i += (long long)gridDim.x * 256) {
+        const int ck = (int)(i % chunks);
+        const long long pix = i / chunks;
+        const int n = (int)(pix / HW);
+        float f[8], r[8];
+        unpack8(*reinterpret_cast<const uint4 *>(x + pix * C + ck * 8), f);
+        if (shortcut) unpack8(*reinterpret_cast<const uint4 *>(shortcut + pix * C + ck * 8), r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = ck * 8 + k, g = c / cpg;
+            const double m = stats[((long long)n * 32 + g) * 2] / cnt;
+            const double var = stats[((long long)n * 32 + g) * 2 + 1] / cnt - m * m;
+            const float rstd = rsqrtf(fmaxf((float)var, 0.0f) + eps);
+            float v = (f[k] - (float)m) * rstd * gamma[c] + beta[c];
+            if (shortcut) v += r[k];
+            f[k] = relu ? fmaxf(v, 0.0f) : v;
+        }
+        *reinterpret_cast<uint4 *>(y + pix * C + ck * 8) = pack8(f);
+    }
+}
+
+// ------------------------------------------------------------------ MaxPool2dSame 3x3 s2, NHWC bf16 (pad value -inf)
+__global__ void __launch_bounds__(256)
+maxpool3_s2_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, int B, int H, int W, int C) {
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, chunks = C / 8;
+    const int pad_h = max((Ho - 1) * 2 + 3 - H, 0) / 2, pad_w = max((Wo - 1) * 2 + 3 - W, 0) / 2;
+    const long long total = (long long)B * Ho * Wo * chunks;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int ck = (int)(i % chunks);
+        const long long o = i / chunks;
+        const int ox = (int)(o % Wo), oy = (int)((o / Wo) % Ho), n = (int)(o / ((long long)Wo * Ho));
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * 2 + ky - pad_h;
+            if (iy < 0 || iy >= H) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * 2 + kx - pad_w;
+                if (ix < 0 || ix >= W) continue;
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4 *>(x + (((long long)n * H + iy) * W + ix) * C + ck * 8), f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+            }
+        }
+        *reinterpret_cast<uint4 *>(y + o * C + ck * 8) = pack8(m);
+    }
+}
+
+// ------------------------------------------------------------------ ViT tokens: [cls | patch tokens] + pos_embed
+// patches bf16 [B,L,D] (patch_embed.proj output), cls f32 [D], pos f32 [1+L][D] -> tokens bf16 [B,1+L,D]
+__global__ void __launch_bounds__(256)
+vit_tokens_kernel(const bf16 *__restrict__ patches, const float *__restrict__ cls, const float *__restrict__ pos,
+                  bf16 *__restrict__ tokens, int B, int L, int D) {
+    const long long total = (long long)B * (L + 1) * D;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int d = (int)(i % D);
+        const int t = (int)((i / D) % (L + 1));
+        const int b = (int)(i / ((long long)D * (L + 1)));
+        const float v = t == 0 ? cls[d] : __bfloat162float(patches[((long long)b * L + t - 1) * D + d]);
+        tokens[i] = __float2bfloat16_rn(v + pos[(long long)t * D + d]);
+    }
+}
+
+// ------------------------------------------------------------------ ProjectReadout input: cat(tok[1:], cls.expand)
+// tokens bf16 [B,1+L,D] -> feats bf16 [B,L,2D]
+__global__ void __launch_bounds__(256)
+readout_concat_kernel(const bf16 *__restrict__ tokens, bf16 *__restrict__ feats, int B, int L, int D) {
+    const int chunks = D / 8;
+    const long long total = (long long)B * L * 2 * chunks;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int ck = (int)(i % (2 * chunks));
+        const long long row = i / (2 * chunks);
+        const int l = (int)(row % L), b = (int)(row / L);
+        const bf16 *src = ck < chunks ? tokens + ((long long)b * (L + 1) + 1 + l) * D + ck * 8
+                                      : tokens + ((long long)b * (L + 1)) * D + (ck - chunks) * 8;
+        *reinterpret_cast<uint4 *>(feats + row * 2 * D + ck * 8) = *reinterpret_cast<const uint4 *>(src);
+    }
+}
+
+// ------------------------------------------------------------------ global multi-head attention, head dim 64
+// qkv bf16 [B,N,3*H*64] (q|k|v), out bf16 [B,N,H*64]; softmax(q k^T / 8) v.  One CTA per (image, head, 128 queries);
+// K and V of the head are staged in shared memory as bf16; one thread per query, chunked online softmax in fp32.
+constexpr int GD = 64, GCH = 8;
+__global__ void __launch_bounds__(128)
+global_attention_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int N, int heads, float scale) {
+    extern __shared__ __align__(16) uint8_t ga_smem[];
+    bf16 *Ks = reinterpret_cast<bf16 *>(ga_smem);            // [Npad][64]
+    const int Npad = (N + GCH - 1) / GCH * GCH;
+    bf16 *Vs = Ks + (size_t)Npad * GD;
+    const int b = blockIdx.x / heads, head = blockIdx.x % heads;
+    const int C = heads * GD;
+    const bf16 *base = qkv + (long long)b * N * 3 * C + head * GD;
+    for (int i = threadIdx.x; i < Npad * (GD / 8); i += 128) {
+        const int r = i / (GD / 8), ck = i % (GD / 8);
+        uint4 k4 = make_uint4(0, 0, 0, 0), v4 = make_uint4(0, 0, 0, 0);
+        if (r < N) {
+            k4 = *reinterpret_cast<const uint4 *>(base + (long long)r * 3 * C + C + ck * 8);
+            v4 = *reinterpret_cast<const uint4 *>(base + (long long)r * 3 * C + 2 * C + ck * 8);
+        }
+        *reinterpret_cast<uint4 *>(Ks + r * GD + ck * 8) = k4;
+        *reinterpret_cast<uint4 *>(Vs + r * GD + ck * 8) = v4;
+    }
+    __syncthreads();
+    const int qi = blockIdx.y * 128 + threadIdx.x;
+    if (qi >= N) return;
+    float q[GD], acc[GD];
+#pragma unroll
+    for (int ck = 0; ck < GD / 8; ++ck) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4 *>(base + (long long)qi * 3 * C + ck * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { q[ck * 8 + k] = f[k] * scale; acc[ck * 8 + k] = 0.f; }
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int j0 = 0; j0 < Npad; j0 += GCH) {
+        float s[GCH];
+        float cm = -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < GCH; ++jj) {
+            const uint4 *kp = reinterpret_cast<const uint4 *>(Ks + (j0 + jj) * GD);
+            float dot = 0.f;
+#pragma unroll
+            for (int ck = 0; ck < GD / 8; ++ck) {
+                float f[8];
+                unpack8(kp[ck], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dot = fmaf(q[ck * 8 + k], f[k], dot);
+            }
+            s[jj] = (j0 + jj < N) ? dot : -INFINITY;           // padded keys never contribute
+            cm = fmaxf(cm, s[jj]);
+        }
+        const float mn = fmaxf(m, cm);
+        const float corr = __expf(m - mn);
+        l *= corr;
+#pragma unroll
+        for (int d = 0; d < GD; ++d) acc[d] *= corr;
+#pragma unroll
+        for (int jj = 0; jj < GCH; ++jj) {
+            const float p = __expf(s[jj] - mn);
+            l += p;
+            const uint4 *vp = reinterpret_cast<const uint4 *>(Vs + (j0 + jj) * GD);
+#pragma unroll
+            for (int ck = 0; ck < GD / 8; ++ck) {
+                float f[8];
+                unpack8(vp[ck], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[ck * 8 + k] = fmaf(p, f[k], acc[ck * 8 + k]);
+            }
+        }
+        m = mn;
+    }
+    const float inv = 1.0f / l;
+    bf16 *op = out + ((long long)b * N + qi) * C + head * GD;
+#pragma unroll
+    for (int ck = 0; ck < GD / 8; ++ck) {
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = acc[ck * 8 + k] * inv;
+        *reinterpret_cast<uint4 *>(op + ck * 8) = pack8(f);
+    }
+}
+
+int grid_for(long long items) {
+    long long blocks = (items + 255) / 256;
+    const long long cap = (long long)soccdpt::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" {
+
+int soccdpt_stem_conv7_fwd(const float *x, const float *w, void *y, int batch, int H, int W, soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(x && w && y && batch >= 1 && H >= 7 && W >= 7, "stem_conv7: bad arguments");
+    const long long pix = (long long)batch * ((H + 1) / 2) * ((W + 1) / 2);
+    long long blocks = (pix + 3) / 4;
+    const long long cap = (long long)soccdpt::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    stem_conv7_kernel<<<(unsigned)blocks, 256, 0, soccdpt::as_stream(stream)>>>(x, w, static_cast<bf16 *>(y), batch, H, W);
+    return soccdpt::check_launch("stem_conv7_kernel");
+}
+
+int soccdpt_groupnorm_fwd(const void *x, const float *gamma, const float *beta, const void *shortcut, void *y, int batch,
+                          int HW, int C, float eps, int relu, void *stats_scratch, soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(x && gamma && beta && y && stats_scratch, "groupnorm: NULL pointer");
+    SOCCDPT_REQUIRE(batch >= 1 && HW >= 1 && C % 64 == 0, "groupnorm: C must be a multiple of 64 (32 groups x >= 2 channels), got %d", C);
+    cudaStream_t st = soccdpt::as_stream(stream);
+    double *stats = static_cast<double *>(stats_scratch);           // [batch][32][2]
+    SOCCDPT_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * batch * 64, st));
+    int slabs = (int)(((long long)HW * (C / 8) + 256 * 32 - 1) / (256 * 32));   // ~32 chunks per thread
+    if (slabs < 1) slabs = 1;
+    if (slabs > 512) slabs = 512;
+    groupnorm_stats_kernel<<<(unsigned)(batch * slabs), 256, 0, st>>>(static_cast<const bf16 *>(x), stats, HW, C, slabs);
+    int rc = soccdpt::check_launch("groupnorm_stats_kernel");
+    if (rc) return rc;
+    const long long total = (long long)batch * HW * (C / 8);
+    groupnorm_apply_kernel<<<grid_for(total), 256, 0, st>>>(static_cast<const bf16 *>(x), stats, gamma, beta,
+                                                            static_cast<const bf16 *>(shortcut), static_cast<bf16 *>(y), total, HW, C,
+                                                            eps, relu);
+    return soccdpt::check_launch("groupnorm_apply_kernel");
+}
+
+int soccdpt_maxpool3s2_fwd(const void *x, void *y, int batch, int H, int W, int C, soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(x && y && batch >= 1 && H >= 2 && W >= 2 && C % 8 == 0, "maxpool: bad arguments");
+    const long long items = (long long)batch * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+    maxpool3_s2_kernel<<<grid_for(items), 256, 0, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(x), static_cast<bf16 *>(y),
+                                                                              batch, H, W, C);
+    return soccdpt::check_launch("maxpool3_s2_kernel");
+}
+
+int soccdpt_vit_tokens_fwd(const void *patches, const float *cls, const float *pos, void *tokens, int batch, int L, int D,
+                           soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(patches && cls && pos && tokens && batch >= 1 && L >= 1 && D >= 8, "vit_tokens: bad arguments");
+    vit_tokens_kernel<<<grid_for((long long)batch * (L + 1) * D), 256, 0, soccdpt::as_stream(stream)>>>(
+        static_cast<const bf16 *>(patches), cls, pos, static_cast<bf16 *>(tokens), batch, L, D);
+    return soccdpt::check_launch("vit_tokens_kernel");
+}
+
+int soccdpt_readout_concat_fwd(const void *tokens, void *feats, int batch, int L, int D, soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(tokens && feats && batch >= 1 && L >= 1 && D % 8 == 0, "readout_concat: bad arguments");
+    readout_concat_kernel<<<grid_for((long long)batch * L * 2 * (D / 8)), 256, 0, soccdpt::as_stream(stream)>>>(
+        static_cast<const bf16 *>(tokens), static_cast<bf16 *>(feats), batch, L, D);
+    return soccdpt::check_launch("readout_concat_kernel");
+}
+
+int soccdpt_global_attention_fwd(const void *qkv, void *out, int batch, int N, int heads, int head_dim,
+                                 soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(qkv && out && batch >= 1 && N >= 1 && heads >= 1, "global_attention: bad arguments");
+    SOCCDPT_REQUIRE(head_dim == GD, "global_attention: head_dim must be 64 (got %d)", head_dim);
+    const int Npad = (N + GCH - 1) / GCH * GCH;
+    const size_t smem = (size_t)Npad * GD * 2 * sizeof(bf16);
+    SOCCDPT_REQUIRE(smem <= 220 * 1024, "global_attention: %d tokens do not fit shared memory", N);
+    static size_t configured = 0;
+    if (smem > configured) {
+        SOCCDPT_CUDA(cudaFuncSetAttribute(global_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)(batch * heads), (unsigned)((N + 127) / 128));
+    global_attention_kernel<<<grid, 128, smem, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(qkv), static_cast<bf16 *>(out),
+                                                                            N, heads, 1.0f / sqrtf((float)head_dim));
+    return soccdpt::check_launch("global_attention_kernel");
+}
+}

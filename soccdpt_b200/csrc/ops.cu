@@ -41,10 +41,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 // the tcgen05 kernel (conv_tcgen05.cu) -- used by the tests as an on-device cross-check.
 __global__ void __launch_bounds__(256) conv_ref_kernel(const soccdpt_conv_t c) {
     const int lane = threadIdx.x & 31;
+    const int st = c.stride > 1 ? c.stride : 1, pad = c.KH / 2 - c.pad_trim;
+    const int Ho = (c.H + st - 1) / st, Wo = (c.W + st - 1) / st;
     const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const long long total = (long long)c.N * c.H * c.W;
+    const long long total = (long long)c.N * Ho * Wo;
     if (pix >= total) return;
-    const int w0 = (int)(pix % c.W), h0 = (int)((pix / c.W) % c.H), n = (int)(pix / ((long long)c.W * c.H));
+    const int w0 = (int)(pix % Wo), h0 = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
     const bf16 *x = static_cast<const bf16 *>(c.x);
     const bf16 *wgt = static_cast<const bf16 *>(c.wgt);
     const int taps = c.KH * c.KW;
@@ -52,10 +54,10 @@ __global__ void __launch_bounds__(256) conv_ref_kernel(const soccdpt_conv_t c) {
     for (int co = lane; co < c.Cout; co += 32) {
         float acc = 0.0f;
         for (int kh = 0; kh < c.KH; ++kh) {
-            const int hh = h0 + kh - c.KH / 2;
+            const int hh = h0 * st + kh - pad;
             if (hh < 0 || hh >= c.H) continue;
             for (int kw = 0; kw < c.KW; ++kw) {
-                const int ww = w0 + kw - c.KW / 2;
+                const int ww = w0 * st + kw - pad;
                 if (ww < 0 || ww >= c.W) continue;
                 const bf16 *xp = x + (((long long)n * c.H + hh) * c.W + ww) * c.Cin;
                 const bf16 *wp = wgt + ((long long)co * taps + kh * c.KW + kw) * c.Cin;
@@ -356,6 +358,8 @@ int validate_conv(const soccdpt_conv_t *c) {
     SOCCDPT_REQUIRE(c->Cout >= 8 && c->Cout % 8 == 0, "conv: Cout must be a multiple of 8 (got %d)", c->Cout);
     SOCCDPT_REQUIRE((c->KH == 1 || c->KH == 3) && c->KW == c->KH, "conv: kernel must be 1x1 or 3x3");
     SOCCDPT_REQUIRE(c->act >= 0 && c->act <= 2, "conv: bad activation %d", c->act);
+    SOCCDPT_REQUIRE(c->stride >= 0 && c->stride <= 2, "conv: stride must be 1 or 2 (got %d)", c->stride);
+    SOCCDPT_REQUIRE(c->pad_trim >= 0 && c->pad_trim <= c->KH / 2, "conv: pad_trim must be in [0, KH/2] (got %d)", c->pad_trim);
     SOCCDPT_REQUIRE(c->proj_n >= 0 && c->proj_n <= 4, "conv: proj_n must be in [0,4]");
     if (c->proj_n > 0) {
         SOCCDPT_REQUIRE(c->proj_w && c->proj_b && c->proj_out, "conv: projection pointers are NULL");
@@ -371,7 +375,8 @@ extern "C" {
 int soccdpt_conv_ref_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream) {
     int rc = soccdpt::validate_conv(c);
     if (rc) return rc;
-    const long long pix = (long long)c->N * c->H * c->W;
+    const int st = c->stride > 1 ? c->stride : 1;
+    const long long pix = (long long)c->N * ((c->H + st - 1) / st) * ((c->W + st - 1) / st);
     conv_ref_kernel<<<(unsigned)((pix + 7) / 8), 256, 0, soccdpt::as_stream(stream)>>>(*c);
     return soccdpt::check_launch("conv_ref_kernel");
 }

@@ -10,7 +10,8 @@ def _s():
     return _cabi.current_stream()
 
 
-def conv(x, w, bias=None, act=0, res1=None, res2=None, want_y=True, want_relu=False, proj=None, impl="tcgen05"):
+def conv(x, w, bias=None, act=0, res1=None, res2=None, want_y=True, want_relu=False, proj=None, impl="tcgen05",
+         stride=1, pad_trim=0):
     """x (N,H,W,Cin) bf16; w (Cout,KH*KW,Cin) bf16 packed. Returns (y, y_relu, proj_out)."""
     lib = _cabi.load()
     N, H, W, Cin = x.shape
@@ -21,15 +22,17 @@ def conv(x, w, bias=None, act=0, res1=None, res2=None, want_y=True, want_relu=Fa
     c.bias = bias.data_ptr() if bias is not None else None
     c.res1 = res1.data_ptr() if res1 is not None else None
     c.res2 = res2.data_ptr() if res2 is not None else None
-    y = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device=x.device) if want_y else None
-    yr = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device=x.device) if want_relu else None
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    c.stride, c.pad_trim = stride, pad_trim
+    y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device) if want_y else None
+    yr = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device) if want_relu else None
     c.y = y.data_ptr() if y is not None else None
     c.y_relu = yr.data_ptr() if yr is not None else None
     c.N, c.H, c.W, c.Cin, c.Cout, c.KH, c.KW, c.act = N, H, W, Cin, Cout, K, K, act
     po = None
     if proj is not None:
         pw, pb, relu = proj
-        po = torch.empty((N, H, W, pw.shape[0]), dtype=torch.float32, device=x.device)
+        po = torch.empty((N, Ho, Wo, pw.shape[0]), dtype=torch.float32, device=x.device)
         c.proj_w, c.proj_b, c.proj_out, c.proj_n, c.proj_relu = pw.data_ptr(), pb.data_ptr(), po.data_ptr(), pw.shape[0], int(relu)
     fn = lib.soccdpt_conv_fwd if impl == "tcgen05" else lib.soccdpt_conv_ref_fwd
     _cabi.check(fn(ctypes.byref(c), _s()), "conv")
@@ -110,4 +113,56 @@ def depth_tail(T, b2, pw, pb):
     out = torch.empty((N, 2 * h, 2 * w), dtype=torch.float32, device=T.device)
     _cabi.check(lib.soccdpt_depth_tail_fwd(T.data_ptr(), b2.data_ptr(), pw.data_ptr(), pb.data_ptr(), out.data_ptr(), N, h, w,
                                            _s()), "depth_tail")
+    return out
+
+
+# ---- ViT-hybrid encoder kernels
+def stem_conv7(x, w):
+    lib = _cabi.load()
+    B, _, H, W = x.shape
+    y = torch.empty((B, (H + 1) // 2, (W + 1) // 2, 64), dtype=torch.bfloat16, device=x.device)
+    _cabi.check(lib.soccdpt_stem_conv7_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), B, H, W, _s()), "stem_conv7")
+    return y
+
+
+def groupnorm(x, gamma, beta, shortcut=None, relu=True, eps=1e-5):
+    lib = _cabi.load()
+    B, H, W, C = x.shape
+    y = torch.empty_like(x)
+    scratch = torch.empty(B * 64, dtype=torch.float64, device=x.device)
+    _cabi.check(lib.soccdpt_groupnorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                          shortcut.data_ptr() if shortcut is not None else None, y.data_ptr(), B, H * W, C,
+                                          eps, int(relu), scratch.data_ptr(), _s()), "groupnorm")
+    return y
+
+
+def maxpool3s2(x):
+    lib = _cabi.load()
+    B, H, W, C = x.shape
+    y = torch.empty((B, (H + 1) // 2, (W + 1) // 2, C), dtype=torch.bfloat16, device=x.device)
+    _cabi.check(lib.soccdpt_maxpool3s2_fwd(x.data_ptr(), y.data_ptr(), B, H, W, C, _s()), "maxpool")
+    return y
+
+
+def vit_tokens(patches, cls, pos):
+    lib = _cabi.load()
+    B, L, D = patches.shape
+    t = torch.empty((B, L + 1, D), dtype=torch.bfloat16, device=patches.device)
+    _cabi.check(lib.soccdpt_vit_tokens_fwd(patches.data_ptr(), cls.data_ptr(), pos.data_ptr(), t.data_ptr(), B, L, D, _s()), "vit_tokens")
+    return t
+
+
+def readout_concat(tokens):
+    lib = _cabi.load()
+    B, L1, D = tokens.shape
+    f = torch.empty((B, L1 - 1, 2 * D), dtype=torch.bfloat16, device=tokens.device)
+    _cabi.check(lib.soccdpt_readout_concat_fwd(tokens.data_ptr(), f.data_ptr(), B, L1 - 1, D, _s()), "readout_concat")
+    return f
+
+
+def global_attention(qkv, heads):
+    lib = _cabi.load()
+    B, N, C3 = qkv.shape
+    out = torch.empty((B, N, C3 // 3), dtype=torch.bfloat16, device=qkv.device)
+    _cabi.check(lib.soccdpt_global_attention_fwd(qkv.data_ptr(), out.data_ptr(), B, N, heads, C3 // 3 // heads, _s()), "global_attention")
     return out

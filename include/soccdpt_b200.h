@@ -190,10 +190,16 @@ int soccdpt_groupnorm_fwd(const void *x, const float *gamma, const float *beta, 
 /* MaxPool2dSame(3, stride 2), NHWC bf16 [batch,H,W,C] -> [batch, ceil(H/2), ceil(W/2), C] (padding value -inf) */
 int soccdpt_maxpool3s2_fwd(const void *x, void *y, int batch, int H, int W, int C, soccdpt_stream_t stream);
 
-/* tokens bf16 [batch, 1+L, D] = cat(cls f32 [D], patches bf16 [batch, L, D]) + pos f32 [1+L, D]
+/* tokens bf16 [batch, 1+L, D] (+ optional f32 copy) = cat(cls f32 [D], patches bf16 [batch, L, D]) + pos f32 [1+L, D]
  * (reference vit.py:66-80; the position embedding is used at its native 24x24 grid: 384x384 frames only) */
-int soccdpt_vit_tokens_fwd(const void *patches, const float *cls, const float *pos, void *tokens, int batch, int L, int D,
-                           soccdpt_stream_t stream);
+int soccdpt_vit_tokens_fwd(const void *patches, const float *cls, const float *pos, void *tokens, float *tokens_f32, int batch,
+                           int L, int D, soccdpt_stream_t stream);
+
+/* Pre-norm residual step of a timm ViT block (x = x + branch(LN(x)), eps 1e-6): master f32 [rows, C] += t (bf16, may be
+ * NULL); y = LayerNorm(master) bf16 (NULL: skipped); stream_bf16 = bf16(master) (NULL: skipped; the hooked block outputs
+ * of reference vit.py:179-219).  C <= 1024. */
+int soccdpt_prenorm_fwd(const void *t, float *master, const float *gamma, const float *beta, void *y, void *stream_bf16,
+                        long long rows, int C, float eps, soccdpt_stream_t stream);
 
 /* ProjectReadout input (reference backbones/utils.py:27-40): feats bf16 [batch, L, 2D] = cat(tokens[:,1:], tokens[:,0] expanded) */
 int soccdpt_readout_concat_fwd(const void *tokens, void *feats, int batch, int L, int D, soccdpt_stream_t stream);

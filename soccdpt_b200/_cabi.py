@@ -71,7 +71,8 @@ SYMBOLS = {
     "soccdpt_stem_conv7_fwd": (_I, [c_void_p] * 3 + [_I] * 3 + [c_void_p]),
     "soccdpt_groupnorm_fwd": (_I, [c_void_p] * 5 + [_I] * 3 + [_F, _I, c_void_p, c_void_p]),
     "soccdpt_maxpool3s2_fwd": (_I, [c_void_p] * 2 + [_I] * 4 + [c_void_p]),
-    "soccdpt_vit_tokens_fwd": (_I, [c_void_p] * 4 + [_I] * 3 + [c_void_p]),
+    "soccdpt_vit_tokens_fwd": (_I, [c_void_p] * 5 + [_I] * 3 + [c_void_p]),
+    "soccdpt_prenorm_fwd": (_I, [c_void_p] * 6 + [_LL, _I, _F, c_void_p]),
     "soccdpt_readout_concat_fwd": (_I, [c_void_p] * 2 + [_I] * 3 + [c_void_p]),
     "soccdpt_global_attention_fwd": (_I, [c_void_p] * 2 + [_I] * 4 + [c_void_p]),
 }

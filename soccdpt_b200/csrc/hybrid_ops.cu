@@ -168,14 +168,16 @@ maxpool3_s2_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, int B, int 
 // patches bf16 [B,L,D] (patch_embed.proj output), cls f32 [D], pos f32 [1+L][D] -> tokens bf16 [B,1+L,D]
 __global__ void __launch_bounds__(256)
 vit_tokens_kernel(const bf16 *__restrict__ patches, const float *__restrict__ cls, const float *__restrict__ pos,
-                  bf16 *__restrict__ tokens, int B, int L, int D) {
+                  bf16 *__restrict__ tokens, float *__restrict__ tokens_f32, int B, int L, int D) {
     const long long total = (long long)B * (L + 1) * D;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int d = (int)(i % D);
         const int t = (int)((i / D) % (L + 1));
         const int b = (int)(i / ((long long)D * (L + 1)));
         const float v = t == 0 ? cls[d] : __bfloat162float(patches[((long long)b * L + t - 1) * D + d]);
-        tokens[i] = __float2bfloat16_rn(v + pos[(long long)t * D + d]);
+        const float o = v + pos[(long long)t * D + d];
+        tokens[i] = __float2bfloat16_rn(o);
+        if (tokens_f32) tokens_f32[i] = o;
     }
 }
 
@@ -278,6 +280,66 @@ global_attention_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, in
     }
 }
 
+// ------------------------------------------------------------------ pre-norm residual step of a ViT block
+// master (fp32 residual stream) += t (bf16 branch output, optional);  y = LayerNorm(master) (optional);
+// stream_bf16 = bf16(master) (optional: the hooked block outputs).  One warp per row, the row stays in registers.
+template <int ITERS>
+__global__ void __launch_bounds__(256)
+prenorm_kernel(const bf16 *__restrict__ t, float *__restrict__ master, const float *__restrict__ gamma,
+               const float *__restrict__ beta, bf16 *__restrict__ y, bf16 *__restrict__ stream_bf16, long long rows, int C, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;                                    // whole warps leave together
+    const int chunks = C / 8;
+    float4 *mp = reinterpret_cast<float4 *>(master + row * C);
+    float f[ITERS][8];
+    float s = 0.0f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int k = lane + it * 32;
+        if (k < chunks) {
+            const float4 a = mp[2 * k], b = mp[2 * k + 1];
+            f[it][0] = a.x; f[it][1] = a.y; f[it][2] = a.z; f[it][3] = a.w;
+            f[it][4] = b.x; f[it][5] = b.y; f[it][6] = b.z; f[it][7] = b.w;
+            if (t) {
+                float r[8];
+                unpack8(*reinterpret_cast<const uint4 *>(t + row * C + k * 8), r);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[it][i] += r[i];
+                mp[2 * k] = make_float4(f[it][0], f[it][1], f[it][2], f[it][3]);
+                mp[2 * k + 1] = make_float4(f[it][4], f[it][5], f[it][6], f[it][7]);
+            }
+            if (stream_bf16) *reinterpret_cast<uint4 *>(stream_bf16 + row * C + k * 8) = pack8(f[it]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += f[it][i];
+        }
+    }
+    if (!y) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.0f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it)
+        if (lane + it * 32 < chunks) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q += (f[it][i] - mean) * (f[it][i] - mean);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int k = lane + it * 32;
+        if (k < chunks) {
+            float o8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o8[i] = (f[it][i] - mean) * rstd * gamma[k * 8 + i] + beta[k * 8 + i];
+            *reinterpret_cast<uint4 *>(y + row * C + k * 8) = pack8(o8);
+        }
+    }
+}
+
 int grid_for(long long items) {
     long long blocks = (items + 255) / 256;
     const long long cap = (long long)soccdpt::sm_count() * 16;
@@ -328,11 +390,11 @@ int soccdpt_maxpool3s2_fwd(const void *x, void *y, int batch, int H, int W, int 
     return soccdpt::check_launch("maxpool3_s2_kernel");
 }
 
-int soccdpt_vit_tokens_fwd(const void *patches, const float *cls, const float *pos, void *tokens, int batch, int L, int D,
-                           soccdpt_stream_t stream) {
+int soccdpt_vit_tokens_fwd(const void *patches, const float *cls, const float *pos, void *tokens, float *tokens_f32, int batch,
+                           int L, int D, soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(patches && cls && pos && tokens && batch >= 1 && L >= 1 && D >= 8, "vit_tokens: bad arguments");
     vit_tokens_kernel<<<grid_for((long long)batch * (L + 1) * D), 256, 0, soccdpt::as_stream(stream)>>>(
-        static_cast<const bf16 *>(patches), cls, pos, static_cast<bf16 *>(tokens), batch, L, D);
+        static_cast<const bf16 *>(patches), cls, pos, static_cast<bf16 *>(tokens), tokens_f32, batch, L, D);
     return soccdpt::check_launch("vit_tokens_kernel");
 }
 
@@ -359,5 +421,20 @@ int soccdpt_global_attention_fwd(const void *qkv, void *out, int batch, int N, i
     global_attention_kernel<<<grid, 128, smem, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(qkv), static_cast<bf16 *>(out),
                                                                             N, heads, 1.0f / sqrtf((float)head_dim));
     return soccdpt::check_launch("global_attention_kernel");
+}
+
+int soccdpt_prenorm_fwd(const void *t, float *master, const float *gamma, const float *beta, void *y, void *stream_bf16,
+                        long long rows, int C, float eps, soccdpt_stream_t stream) {
+    SOCCDPT_REQUIRE(master && rows >= 1 && C >= 8 && C % 8 == 0 && C <= 1024, "prenorm: bad arguments (C = %d)", C);
+    SOCCDPT_REQUIRE(!y || (gamma && beta), "prenorm: LayerNorm output requested without gamma/beta");
+    cudaStream_t st = soccdpt::as_stream(stream);
+    const unsigned blocks = (unsigned)((rows + 7) / 8);
+    const bf16 *tp = static_cast<const bf16 *>(t);
+    bf16 *yp = static_cast<bf16 *>(y), *sp = static_cast<bf16 *>(stream_bf16);
+    if (C <= 256) prenorm_kernel<1><<<blocks, 256, 0, st>>>(tp, master, gamma, beta, yp, sp, rows, C, eps);
+    else if (C <= 512) prenorm_kernel<2><<<blocks, 256, 0, st>>>(tp, master, gamma, beta, yp, sp, rows, C, eps);
+    else if (C <= 768) prenorm_kernel<3><<<blocks, 256, 0, st>>>(tp, master, gamma, beta, yp, sp, rows, C, eps);
+    else prenorm_kernel<4><<<blocks, 256, 0, st>>>(tp, master, gamma, beta, yp, sp, rows, C, eps);
+    return soccdpt::check_launch("prenorm_kernel");
 }
 }

@@ -8,6 +8,10 @@ Kernel schedule per frame batch (reference call sites in include/soccdpt_b200.h)
   decoder: layerN_rn conv3x3, residual conv units (bias/ReLU/residual fused in the GEMM epilogue),
   out_conv 1x1 evaluated BEFORE the bilinear upsample (they commute, 4x fewer FLOPs) ->
   depth head (32->1 projection fused in the epilogue) and seg head (BN folded, 256->3 fused).
+ViT-hybrid encoder (dpt_hybrid_384) instead of the Swin part:
+  stem conv7x7/2 -> GroupNorm+ReLU -> max-pool -> 16 ResNetV2 bottlenecks (weight-standardised convs as implicit GEMMs,
+  GroupNorm (+shortcut) (+ReLU) kernels) -> 1x1 patch projection -> cls/pos tokens -> 12 pre-norm ViT blocks
+  (fp32 residual stream, global attention) -> ProjectReadout GEMM (+GELU) + 1x1 / stride-2 3x3 convs on blocks 8 and 11.
 """
 import ctypes
 import math
@@ -15,7 +19,7 @@ import math
 import torch
 
 from . import _cabi
-from .model.encoder import relative_position_bias_table
+from .model.encoder import SwinV2Params, relative_position_bias_table
 
 
 class _Launch:
@@ -61,6 +65,60 @@ class NetworkEngine:
         net = self.net
         enc = net.depth_net.pretrained.model
         W = {"stages": []}
+        self.hybrid = not isinstance(enc, SwinV2Params)
+        if self.hybrid:
+            W["hy"] = self._pack_hybrid(dev)
+        else:
+            self._pack_swin(W, enc, dev)
+        self._pack_decoder(W, dev)
+        return W
+
+    @staticmethod
+    def _std_weight(conv):
+        """timm StdConv2dSame: per-output-channel standardisation with the biased variance, eps 1e-8 (fp32)."""
+        w = conv.weight.detach().float()
+        flat = w.reshape(w.shape[0], -1)
+        mean = flat.mean(1, keepdim=True)
+        var = flat.var(1, unbiased=False, keepdim=True)
+        return ((flat - mean) * torch.rsqrt(var + conv.eps)).reshape_as(w)
+
+    def _pack_hybrid(self, dev):
+        pre = self.net.depth_net.pretrained
+        enc = pre.model
+        bb = enc.patch_embed.backbone
+        gn = lambda n: (_f32(n.weight, dev), _f32(n.bias, dev))
+        H = dict(stem_w=_f32(self._std_weight(bb.stem.conv), dev), stem_n=gn(bb.stem.norm), stages=[])
+        for stage in bb.stages:
+            blocks = []
+            for blk in stage.blocks:
+                d = dict(stride=blk.stride, cin=blk.conv1.weight.shape[1], mid=blk.conv1.weight.shape[0],
+                         cout=blk.conv3.weight.shape[0],
+                         w1=_pack_conv(self._std_weight(blk.conv1), dev), n1=gn(blk.norm1),
+                         w2=_pack_conv(self._std_weight(blk.conv2), dev), n2=gn(blk.norm2),
+                         w3=_pack_conv(self._std_weight(blk.conv3), dev), n3=gn(blk.norm3), down=None)
+                if blk.downsample is not None:
+                    d["down"] = (_pack_conv(self._std_weight(blk.downsample.conv), dev), gn(blk.downsample.norm))
+                blocks.append(d)
+            H["stages"].append(blocks)
+        H["proj"] = (_pack_conv(enc.patch_embed.proj.weight, dev), _f32(enc.patch_embed.proj.bias, dev))
+        H["cls"] = _f32(enc.cls_token.reshape(-1), dev)
+        H["pos"] = _f32(enc.pos_embed[0], dev)
+        H["heads"] = enc.num_heads
+        H["blocks"] = [dict(n1=gn(b.norm1), wqkv=_bf16(b.attn.qkv.weight, dev), bqkv=_f32(b.attn.qkv.bias, dev),
+                            wproj=_bf16(b.attn.proj.weight, dev), bproj=_f32(b.attn.proj.bias, dev), n2=gn(b.norm2),
+                            w1=_bf16(b.mlp.fc1.weight, dev), b1=_f32(b.mlp.fc1.bias, dev),
+                            w2=_bf16(b.mlp.fc2.weight, dev), b2=_f32(b.mlp.fc2.bias, dev)) for b in enc.blocks]
+        H["hooks"] = tuple(enc.hooks)
+        for idx in (3, 4):
+            pp = getattr(pre, f"act_postprocess{idx}")
+            d = dict(wr=_bf16(pp[0].project[0].weight, dev), br=_f32(pp[0].project[0].bias, dev),
+                     w1=_pack_conv(pp[3].weight, dev), b1=_f32(pp[3].bias, dev))
+            if idx == 4:
+                d["w2"], d["b2"] = _pack_conv(pp[4].weight, dev), _f32(pp[4].bias, dev)
+            H[f"pp{idx}"] = d
+        return H
+
+    def _pack_swin(self, W, enc, dev):
         pe = enc.patch_embed
         W["pe"] = (_f32(pe.proj.weight.reshape(pe.proj.weight.shape[0], -1), dev), _f32(pe.proj.bias, dev),
                    _f32(pe.norm.weight, dev), _f32(pe.norm.bias, dev))
@@ -87,6 +145,9 @@ class NetworkEngine:
                 ds = dict(w=_bf16(layer.downsample.reduction.weight, dev),
                           n=(_f32(layer.downsample.norm.weight, dev), _f32(layer.downsample.norm.bias, dev)))
             W["stages"].append(dict(dim=layer.dim, res=layer.input_resolution, blocks=blocks, down=ds))
+
+    def _pack_decoder(self, W, dev):
+        net = self.net
         sc = net.depth_net.scratch
         W["rn"] = [_pack_conv(getattr(sc, f"layer{i}_rn").weight, dev) for i in (1, 2, 3, 4)]
         W["fusion"] = {}
@@ -115,12 +176,12 @@ class NetworkEngine:
                        pw=_f32(sh[4].weight.reshape(sh[4].weight.shape[0], -1), dev), pb=_f32(sh[4].bias, dev))
         W["num_classes"] = sh[4].weight.shape[0]
         W["seg_act"] = 0 if isinstance(sh[6], torch.nn.Sigmoid) else 1
-        return W
 
     # ------------------------------------------------------------------ plan construction
     def _conv(self, plan, x, w, N, H, Wd, Cin, Cout, K, bias=None, act=_cabi.ACT_NONE, res1=None, res2=None, y=None,
-              y_relu=None, proj=None):
+              y_relu=None, proj=None, stride=1, pad_trim=0):
         c = _cabi.Conv()
+        c.stride, c.pad_trim = stride, pad_trim
         c.x, c.wgt = x.data_ptr(), w.data_ptr()
         c.bias = bias.data_ptr() if bias is not None else None
         c.res1 = res1.data_ptr() if res1 is not None else None
@@ -136,22 +197,8 @@ class NetworkEngine:
         plan["keep"].append(c)
         plan["ops"].append(_Launch("conv", fn, ctypes.byref(c)))
 
-    def _build_plan(self, B, dev):
-        Wt = self._weights
-        lib = self.lib
-        plan = {"ops": [], "keep": [], "B": B}
-        ops = plan["ops"]
-
-        def buf(*shape, dtype=torch.bfloat16):
-            t = torch.empty(shape, device=dev, dtype=dtype)
-            plan["keep"].append(t)
-            return t
-
-        enc = self.net.depth_net.pretrained.model
-        img = enc.img_size
-        plan["img"] = img
-        x_in = buf(B, 3, img, img, dtype=torch.float32)
-        plan["x_in"] = x_in
+    def _plan_swin(self, plan, buf, x_in, B, img):
+        Wt, lib, ops = self._weights, self.lib, plan["ops"]
         stages = Wt["stages"]
         E = stages[0]["dim"]
         g0 = img // 4
@@ -192,6 +239,128 @@ class NetworkEngine:
                                    st["down"]["n"][0].data_ptr(), st["down"]["n"][1].data_ptr(), nxt.data_ptr(), M2, 2 * C,
                                    ctypes.c_float(1e-5)))
                 cur = nxt
+        return taps
+
+    def _plan_hybrid(self, plan, buf, x_in, B, img):
+        """timm vit_base_resnet50_384 forward_flex + the reference's tap post-processing (vit.py:44-85, 179-219)."""
+        Hy, lib, ops = self._weights["hy"], self.lib, plan["ops"]
+        gn_scratch = buf(B * 64, dtype=torch.float64)
+
+        def gn(x, n, HW, C, relu, shortcut=None, y=None):
+            ops.append(_Launch("groupnorm", lib.soccdpt_groupnorm_fwd, x.data_ptr(), n[0].data_ptr(), n[1].data_ptr(),
+                               shortcut.data_ptr() if shortcut is not None else None, (y if y is not None else x).data_ptr(),
+                               B, HW, C, ctypes.c_float(1e-5), int(relu), gn_scratch.data_ptr()))
+
+        # ---- ResNetV2 stem: StdConv 7x7/2 (SAME) -> GroupNorm + ReLU -> MaxPool 3x3/2 (SAME)
+        H1 = (img + 1) // 2
+        s0 = buf(B, H1, H1, 64)
+        ops.append(_Launch("stem_conv7", lib.soccdpt_stem_conv7_fwd, x_in.data_ptr(), Hy["stem_w"].data_ptr(), s0.data_ptr(), B, img, img))
+        gn(s0, Hy["stem_n"], H1 * H1, 64, True)
+        Hc = (H1 + 1) // 2
+        cur = buf(B, Hc, Hc, 64)
+        ops.append(_Launch("maxpool", lib.soccdpt_maxpool3s2_fwd, s0.data_ptr(), cur.data_ptr(), B, H1, H1, 64))
+
+        # ---- bottleneck stages (non pre-activation): out = relu(gn3(conv3(gn2(conv2(gn1(conv1 x))))) + shortcut)
+        stage_out = []
+        for blocks in Hy["stages"]:
+            for b in blocks:
+                st, cin, mid, cout = b["stride"], b["cin"], b["mid"], b["cout"]
+                Ho = (Hc + st - 1) // st
+                shortcut = cur
+                if b["down"] is not None:
+                    shortcut = buf(B, Ho, Ho, cout)
+                    self._conv(plan, cur, b["down"][0], B, Hc, Hc, cin, cout, 1, y=shortcut, stride=st)
+                    gn(shortcut, b["down"][1], Ho * Ho, cout, False)
+                a = buf(B, Hc, Hc, mid)
+                self._conv(plan, cur, b["w1"], B, Hc, Hc, cin, mid, 1, y=a)
+                gn(a, b["n1"], Hc * Hc, mid, True)
+                c2 = buf(B, Ho, Ho, mid)
+                # TF "SAME" on an even input: stride 2 pads 0 in front / 1 behind, stride 1 pads 1 / 1
+                assert st == 1 or Hc % 2 == 0
+                self._conv(plan, a, b["w2"], B, Hc, Hc, mid, mid, 3, y=c2, stride=st, pad_trim=1 if st == 2 else 0)
+                gn(c2, b["n2"], Ho * Ho, mid, True)
+                c3 = buf(B, Ho, Ho, cout)
+                self._conv(plan, c2, b["w3"], B, Ho, Ho, mid, cout, 1, y=c3)
+                gn(c3, b["n3"], Ho * Ho, cout, True, shortcut=shortcut)
+                cur, Hc = c3, Ho
+            stage_out.append((cur, Hc, Hc, blocks[-1]["cout"]))
+
+        # ---- patch projection (1x1 conv == linear), cls token + position embedding
+        feat, g, _, Cf = stage_out[2]
+        D, L = Hy["proj"][0].shape[0], g * g
+        assert Hy["pos"].shape[0] == L + 1, "dpt_hybrid_384: the position embedding is used at its native grid (384x384 frames)"
+        patches = buf(B, L, D)
+        self._conv(plan, feat, Hy["proj"][0], 1, 1, B * L, Cf, D, 1, bias=Hy["proj"][1], y=patches)
+        N = L + 1
+        M = B * N
+        xn = buf(M, D)                                  # bf16 tokens, then LayerNorm outputs (GEMM operand)
+        master = buf(M, D, dtype=torch.float32)         # fp32 residual stream
+        ops.append(_Launch("vit_tokens", lib.soccdpt_vit_tokens_fwd, patches.data_ptr(), Hy["cls"].data_ptr(), Hy["pos"].data_ptr(),
+                           xn.data_ptr(), master.data_ptr(), B, L, D))
+        qkv, att, tmp, hid = buf(M, 3 * D), buf(M, D), buf(M, D), buf(M, 4 * D)
+        heads = Hy["heads"]
+        hooked = {}
+        pending = None                                  # branch output not yet added to the residual stream
+        eps = ctypes.c_float(1e-6)
+
+        def prenorm(t, n, y, stream_copy=None):
+            ops.append(_Launch("prenorm", lib.soccdpt_prenorm_fwd, t.data_ptr() if t is not None else None, master.data_ptr(),
+                               n[0].data_ptr() if n is not None else None, n[1].data_ptr() if n is not None else None,
+                               y.data_ptr() if y is not None else None,
+                               stream_copy.data_ptr() if stream_copy is not None else None, M, D, eps))
+
+        nblk = len(Hy["blocks"])
+        for i, b in enumerate(Hy["blocks"]):
+            hook_prev = hooked.get(i - 1)               # the previous block's output is complete after this add
+            prenorm(pending, b["n1"], xn, hook_prev)
+            self._conv(plan, xn, b["wqkv"], 1, 1, M, D, 3 * D, 1, bias=b["bqkv"], y=qkv)
+            ops.append(_Launch("global_attention", lib.soccdpt_global_attention_fwd, qkv.data_ptr(), att.data_ptr(), B, N, heads, D // heads))
+            self._conv(plan, att, b["wproj"], 1, 1, M, D, D, 1, bias=b["bproj"], y=tmp)
+            prenorm(tmp, b["n2"], xn)
+            self._conv(plan, xn, b["w1"], 1, 1, M, D, 4 * D, 1, bias=b["b1"], act=_cabi.ACT_GELU, y=hid)
+            self._conv(plan, hid, b["w2"], 1, 1, M, 4 * D, D, 1, bias=b["b2"], y=tmp)
+            pending = tmp
+            if i in Hy["hooks"][2:]:
+                hooked[i] = buf(B, N, D)
+            if i == nblk - 1:                           # last add; the final LayerNorm is computed-and-discarded upstream
+                prenorm(pending, None, None, hooked.get(i))
+
+        # ---- tap post-processing: ProjectReadout (cat with cls, Linear + GELU) -> 1x1 conv [-> 3x3 stride-2 conv]
+        def readout(tok, w):
+            feats = buf(B, L, 2 * D)
+            ops.append(_Launch("readout_concat", lib.soccdpt_readout_concat_fwd, tok.data_ptr(), feats.data_ptr(), B, L, D))
+            r = buf(B, g, g, D)
+            self._conv(plan, feats, w["wr"], 1, 1, B * L, 2 * D, D, 1, bias=w["br"], act=_cabi.ACT_GELU, y=r)
+            o = buf(B, g, g, w["w1"].shape[0])
+            self._conv(plan, r, w["w1"], B, g, g, D, w["w1"].shape[0], 1, bias=w["b1"], y=o)
+            return o
+
+        h3, h4 = Hy["hooks"][2], Hy["hooks"][3]
+        l3 = readout(hooked[h3], Hy["pp3"])
+        l4a = readout(hooked[h4], Hy["pp4"])
+        C4 = Hy["pp4"]["w2"].shape[0]
+        g4 = (g + 1) // 2
+        l4 = buf(B, g4, g4, C4)
+        self._conv(plan, l4a, Hy["pp4"]["w2"], B, g, g, l4a.shape[-1], C4, 3, bias=Hy["pp4"]["b2"], y=l4, stride=2)
+        return [stage_out[0], stage_out[1], (l3, g, g, l3.shape[-1]), (l4, g4, g4, C4)]
+
+    def _build_plan(self, B, dev):
+        Wt = self._weights
+        lib = self.lib
+        plan = {"ops": [], "keep": [], "B": B}
+        ops = plan["ops"]
+
+        def buf(*shape, dtype=torch.bfloat16):
+            t = torch.empty(shape, device=dev, dtype=dtype)
+            plan["keep"].append(t)
+            return t
+
+        enc = self.net.depth_net.pretrained.model
+        img = enc.img_size
+        plan["img"] = img
+        x_in = buf(B, 3, img, img, dtype=torch.float32)
+        plan["x_in"] = x_in
+        taps = self._plan_hybrid(plan, buf, x_in, B, img) if self.hybrid else self._plan_swin(plan, buf, x_in, B, img)
         plan["taps"] = taps
 
         # ---------------- decoder (dpt.py:152-172)

@@ -4,9 +4,11 @@ import torch.nn as nn
 
 from .base_model import BaseModel
 from .encoder import SWIN_CONFIGS, SwinV2Params, _no_forward
+from .vit_hybrid import VIT_HYBRID_CONFIGS, HybridPretrained
 
 # backbone -> stage channels fed to scratch.layerN_rn (blocks.py:64-78)
-BACKBONE_CHANNELS = {"swin2t16_256": (96, 192, 384, 768), "swin2b24_384": (128, 256, 512, 1024)}
+BACKBONE_CHANNELS = {"swin2t16_256": (96, 192, 384, 768), "swin2b24_384": (128, 256, 512, 1024),
+                     "vitb_rn50_384": (256, 512, 768, 768)}
 
 
 class _RCUParams(nn.Module):
@@ -44,10 +46,10 @@ class DPTDepthModel(BaseModel):
     def __init__(self, path=None, non_negative=True, backbone="swin2t16_256", features=256, return_features=True,
                  **kwargs):
         super().__init__()
-        assert backbone in SWIN_CONFIGS, f"Backbone '{backbone}' not implemented"
+        assert backbone in SWIN_CONFIGS or backbone in VIT_HYBRID_CONFIGS, f"Backbone '{backbone}' not implemented"
         assert non_negative, "the fused depth-head epilogue implements non_negative=True (dpt.py:217)"
         self.backbone, self.features, self.return_features = backbone, features, return_features
-        self.pretrained = _Pretrained(backbone)
+        self.pretrained = _Pretrained(backbone) if backbone in SWIN_CONFIGS else HybridPretrained(backbone)
         ch = BACKBONE_CHANNELS[backbone]
         scratch = nn.Module()
         for i, c in enumerate(ch):

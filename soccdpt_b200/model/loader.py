@@ -9,6 +9,7 @@ from .base_model import BaseModel
 _BACKBONES = {
     "dpt_swin2_base_384": "swin2b24_384",
     "dpt_swin2_tiny_256": "swin2t16_256",
+    "dpt_hybrid_384": "vitb_rn50_384",
 }
 # (net_w, net_h) exactly as the reference returns them (loader.py:177-199): 256x256 even for swin2_base_384
 _INPUT_SIZES = {"dpt_swin2_base_384": (256, 256), "dpt_swin2_tiny_256": (256, 256), "dpt_hybrid_384": (384, 384)}

@@ -35,9 +35,12 @@ _ALIAS = "pretrained."
 _CANON = "depth_net.pretrained."
 
 
-def seeded_state_dict(state_dict, seed=0):
+def seeded_state_dict(state_dict, seed=0, residual_gain=1.0):
     """Returns a new dict with the same keys/shapes, values drawn deterministically (sorted key
-    order, one CPU generator).  ``pretrained.*`` keys alias ``depth_net.pretrained.*`` (same module registered twice)."""
+    order, one CPU generator).  ``pretrained.*`` keys alias ``depth_net.pretrained.*`` (same module registered twice).
+    ``residual_gain`` scales the last GroupNorm (``norm3``) of every ResNetV2 bottleneck of the hybrid encoder: 1.0 is
+    plain random init (numerically chaotic under bf16 storage, see tests/test_gpu_network_hybrid.py), 0.1 damps the
+    residual branches the way trained weights / timm's ``zero_init_last`` do."""
     g = torch.Generator().manual_seed(seed)
     out = {}
     for k in sorted(state_dict.keys()):
@@ -70,6 +73,8 @@ def seeded_state_dict(state_dict, seed=0):
             t = torch.randn(shape, generator=g) * 0.02
         # keep the synthetic inverse depth in ~[0.03, 0.3] (depth 3-30 m) so that unprojected points
         # land inside the 128 m x 128 m x 48 m occupancy volume instead of the never-filled k=0 plane
+        if residual_gain != 1.0 and (k.endswith(".norm3.weight") or k.endswith(".norm3.bias")):
+            t = t * residual_gain
         if k.endswith("scratch.output_conv.4.weight"):
             t = t * 0.03
         if k.endswith("scratch.output_conv.4.bias"):

@@ -148,8 +148,25 @@ def vit_tokens(patches, cls, pos):
     lib = _cabi.load()
     B, L, D = patches.shape
     t = torch.empty((B, L + 1, D), dtype=torch.bfloat16, device=patches.device)
-    _cabi.check(lib.soccdpt_vit_tokens_fwd(patches.data_ptr(), cls.data_ptr(), pos.data_ptr(), t.data_ptr(), B, L, D, _s()), "vit_tokens")
+    t32 = torch.empty((B, L + 1, D), dtype=torch.float32, device=patches.device)
+    _cabi.check(lib.soccdpt_vit_tokens_fwd(patches.data_ptr(), cls.data_ptr(), pos.data_ptr(), t.data_ptr(), t32.data_ptr(),
+                                           B, L, D, _s()), "vit_tokens")
+    assert torch.equal(t32.bfloat16(), t)
     return t
+
+
+def prenorm(t, master, gamma, beta, want_y=True, want_stream=False, eps=1e-6):
+    """master (rows,C) f32 updated in place; returns (y, stream_bf16)."""
+    lib = _cabi.load()
+    rows, C = master.shape
+    y = torch.empty((rows, C), dtype=torch.bfloat16, device=master.device) if want_y else None
+    sb = torch.empty((rows, C), dtype=torch.bfloat16, device=master.device) if want_stream else None
+    _cabi.check(lib.soccdpt_prenorm_fwd(t.data_ptr() if t is not None else None, master.data_ptr(),
+                                        gamma.data_ptr() if gamma is not None else None,
+                                        beta.data_ptr() if beta is not None else None,
+                                        y.data_ptr() if y is not None else None, sb.data_ptr() if sb is not None else None,
+                                        rows, C, eps, _s()), "prenorm")
+    return y, sb
 
 
 def readout_concat(tokens):

@@ -89,6 +89,26 @@ def test_base_384_state_dict_keys_equal_reference_live(tmp_path):
             assert torch.equal(v, mine.state_dict()[k])
 
 
+def test_hybrid_state_dict_keys_equal_reference(tmp_path):
+    """dpt_hybrid_384 builds with the key set / order / shapes of the (repaired) reference constructor,
+    recorded by oracle/make_golden.py in tests/golden/state_keys_hybrid.txt."""
+    ref = {}
+    with open(os.path.join(GU.GOLD, "state_keys_hybrid.txt")) as f:
+        for line in f:
+            k, shp = line.rstrip("\n").split(" ", 1)
+            ref[k] = ast.literal_eval(shp)
+    yml = write_calib_yaml(str(tmp_path / "c.yaml"))
+    mt = "dpt_hybrid_384"
+    mine = load_model(arch=SOccDPT_versions[3],
+                      model_kwargs=dict(load_depth=False, num_classes=3, sigmoid=True, compute_occ=True,
+                                        camera_intrinsics_yaml=yml, model_type=mt),
+                      device=torch.device("cpu"), model_path=None, model_type=mt)
+    got = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    assert list(got.keys()) == list(ref.keys())
+    assert got == ref
+    assert mine.pretrained is mine.depth_net.pretrained
+
+
 def test_checkpoint_round_trip_like_reference(net, tmp_path):
     """both on-disk layouts the reference writes / reads load through the same path
     (raw state_dict, train_SOccDPT.py:437-449; {"optimizer","model"} wrapper, base_model.py:15-17)."""

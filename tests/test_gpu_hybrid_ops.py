@@ -68,6 +68,26 @@ def test_vit_tokens_and_readout():
     assert torch.equal(f, torch.cat([t[:, 1:], t[:, :1].expand(B, L, D)], -1))
 
 
+@pytest.mark.parametrize("C", [768, 256, 1024, 136])
+def test_prenorm(C):
+    torch.manual_seed(6)
+    rows = 1154 + 3
+    m = torch.randn(rows, C, device="cuda") * 3
+    t = torch.randn(rows, C, device="cuda").bfloat16()
+    g, b = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    m0 = m.clone()
+    y, sb = K.prenorm(t, m, g, b, want_stream=True)
+    ref_m = m0 + t.float()
+    assert torch.equal(m, ref_m) and torch.equal(sb, ref_m.bfloat16())
+    ref = F.layer_norm(ref_m, (C,), g, b, 1e-6)
+    assert (y.float() - ref).abs().max() <= 1e-2 * max(1.0, ref.abs().max().item())
+    m2 = m.clone()
+    y2, sb2 = K.prenorm(None, m2, g, b)                     # no branch: LN only, master untouched
+    assert torch.equal(m2, m) and torch.equal(y2, y) and sb2 is None
+    _, sb3 = K.prenorm(t, m2, None, None, want_y=False, want_stream=True)
+    assert torch.equal(m2, m + t.float()) and torch.equal(sb3, m2.bfloat16())
+
+
 @pytest.mark.parametrize("B,N,heads", [(2, 577, 12), (1, 100, 3), (3, 128, 2)])
 def test_global_attention(B, N, heads):
     torch.manual_seed(4)

@@ -183,7 +183,7 @@ int soccdpt_bf16_to_f32(const void *x, float *y, long long n, soccdpt_stream_t s
 int soccdpt_stem_conv7_fwd(const float *x, const float *w, void *y, int batch, int H, int W, soccdpt_stream_t stream);
 
 /* GroupNormAct(32 groups) on NHWC bf16 [batch, HW, C]: y = [relu]( gn(x) * gamma + beta [+ shortcut] ).
- * stats_scratch: batch*64 doubles of device memory (zeroed by the call).  C % 64 == 0. */
+ * stats_scratch: batch*64 doubles of device memory (zeroed by the call).  C = 64, 128 or a multiple of 256. */
 int soccdpt_groupnorm_fwd(const void *x, const float *gamma, const float *beta, const void *shortcut, void *y, int batch,
                           int HW, int C, float eps, int relu, void *stats_scratch, soccdpt_stream_t stream);
 

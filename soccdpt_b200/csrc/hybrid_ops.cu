@@ -6,6 +6,11 @@
 // SOccDPT/model/backbones/utils.py:27-40 (ProjectReadout); the arithmetic itself is timm 0.6.12's.
 #include "common.cuh"
 
+namespace soccdpt {
+int global_attention_tc_max_tokens();
+int launch_global_attention_tc(const void *qkv, void *out, int batch, int N, int heads, cudaStream_t st);
+}  // namespace soccdpt
+
 namespace {
 
 using bf16 = __nv_bfloat16;
@@ -28,48 +33,75 @@ __device__ __forceinline__ uint4 pack8(const float f[8]) {
 }
 
 // ------------------------------------------------------------------ stem: conv 7x7 s2, 3 -> 64, SAME padding
-// x f32 NCHW [B,3,H,W] -> y bf16 NHWC [B,H/2,W/2,64].  Block = 4 output pixels x 64 channels; the standardised
-// weights live in shared memory as [147][64].
+// x f32 NCHW [B,3,H,W] -> y bf16 NHWC [B,H/2,W/2,64].  One CTA = 64 consecutive output pixels of one output row x 64
+// channels; the 3 x 7 x 133 input patch and the standardised weights ([147][64]) live in shared memory, every thread
+// owns 4 pixels x 4 channels (4 patch loads + one float4 weight load per 16 FMAs).
+constexpr int ST_PX = 64, ST_COLS = ST_PX * 2 + 5;
 __global__ void __launch_bounds__(256)
 stem_conv7_kernel(const float *__restrict__ x, const float *__restrict__ w, bf16 *__restrict__ y, int B, int H, int W) {
-    __shared__ float sw[147 * 64];
-    __shared__ float patch[4][148];
+    __shared__ __align__(16) float sw[147 * 64];
+    __shared__ float patch[21][ST_COLS + 1];
     for (int i = threadIdx.x; i < 147 * 64; i += 256) {
         const int co = i / 147, k = i - co * 147;       // w is [64][3][7][7]
         sw[k * 64 + co] = w[i];
     }
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     const int pad_h = max((Ho - 1) * 2 + 7 - H, 0) / 2, pad_w = max((Wo - 1) * 2 + 7 - W, 0) / 2;   // SAME: floor(total/2) first
-    const long long total = (long long)B * Ho * Wo;
-    const int lp = threadIdx.x >> 6, co = threadIdx.x & 63;
-    for (long long base = (long long)blockIdx.x * 4; base < total; base += (long long)gridDim.x * 4) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < 4 * 147; i += 256) {
-            const int pp = i / 147, k = i - pp * 147;
-            const long long pix = base + pp;
-            float v = 0.0f;
-            if (pix < total) {
-                const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
-                const int ci = k / 49, ky = (k % 49) / 7, kx = k % 7;
-                const int iy = oy * 2 + ky - pad_h, ix = ox * 2 + kx - pad_w;
-                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long long)n * 3 + ci) * H + iy) * W + ix];
+    const int segs = (Wo + ST_PX - 1) / ST_PX;
+    const int seg = blockIdx.x % segs, oy = (blockIdx.x / segs) % Ho, n = blockIdx.x / (segs * Ho);
+    const int ox0 = seg * ST_PX;
+    for (int i = threadIdx.x; i < 21 * ST_COLS; i += 256) {
+        const int r = i / ST_COLS, c = i - r * ST_COLS;     // r = ci * 7 + ky
+        const int ci = r / 7, ky = r - ci * 7;
+        const int iy = oy * 2 + ky - pad_h, ix = ox0 * 2 + c - pad_w;
+        patch[r][c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[(((long long)n * 3 + ci) * H + iy) * W + ix] : 0.0f;
+    }
+    __syncthreads();
+    const int pg = threadIdx.x >> 4, cg = threadIdx.x & 15;  // pixels pg*4 .. pg*4+3, channels cg*4 .. cg*4+3
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+#pragma unroll 1
+    for (int r = 0; r < 21; ++r) {
+        const float *pr = &patch[r][pg * 8];
+        const float *wr = sw + r * 7 * 64 + cg * 4;
+        float in[13];
+#pragma unroll
+        for (int c = 0; c < 13; ++c) in[c] = pr[c];          // 4 pixels x stride 2 + 7 taps - 2
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+            const float4 wv = *reinterpret_cast<const float4 *>(wr + kx * 64);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v = in[2 * i + kx];
+                acc[i][0] = fmaf(v, wv.x, acc[i][0]);
+                acc[i][1] = fmaf(v, wv.y, acc[i][1]);
+                acc[i][2] = fmaf(v, wv.z, acc[i][2]);
+                acc[i][3] = fmaf(v, wv.w, acc[i][3]);
             }
-            patch[pp][k] = v;
         }
-        __syncthreads();
-        const long long pix = base + lp;
-        if (pix < total) {
-            float acc = 0.0f;
-#pragma unroll 7
-            for (int k = 0; k < 147; ++k) acc = fmaf(patch[lp][k], sw[k * 64 + co], acc);
-            y[pix * 64 + co] = __float2bfloat16_rn(acc);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ox = ox0 + pg * 4 + i;
+        if (ox < Wo) {
+            uint2 o;
+            __nv_bfloat162 lo = __floats2bfloat162_rn(acc[i][0], acc[i][1]), hi = __floats2bfloat162_rn(acc[i][2], acc[i][3]);
+            o.x = *reinterpret_cast<uint32_t *>(&lo);
+            o.y = *reinterpret_cast<uint32_t *>(&hi);
+            *reinterpret_cast<uint2 *>(y + (((long long)n * Ho + oy) * Wo + ox) * 64 + cg * 4) = o;
         }
     }
 }
 
 // ------------------------------------------------------------------ GroupNorm(32 groups), NHWC bf16
-// pass 1: per-(image, group) sum / sum of squares: every block reduces a slab of pixels for all groups in shared
-// memory, then one double atomicAdd per (group, statistic).  pass 2: normalise (+ shortcut) (+ ReLU).
+// pass 1: per-(image, group) sum / sum of squares.  C / 8 divides 256 for every width of the model, so a thread meets the
+// same 8 channels on every step of its stride-256 loop and keeps their (at most 4) group sums in registers; one
+// shared-memory atomic per thread and group at the end, then one double atomicAdd per (block, group, statistic).
+// pass 2: normalise (+ shortcut) (+ ReLU); mean / rstd are derived once per 16-byte chunk, not per element.
+template <int SUB>   // channels of one group inside a 16-byte chunk: 8 (cpg >= 8), 4 or 2
 __global__ void __launch_bounds__(256)
 groupnorm_stats_kernel(const bf16 *__restrict__ x, double *__restrict__ stats, int HW, int C, int slabs) {
     __shared__ float s_sum[32], s_sq[32];
@@ -78,26 +110,44 @@ groupnorm_stats_kernel(const bf16 *__restrict__ x, double *__restrict__ stats, i
     const int n = blockIdx.x / slabs, slab = blockIdx.x % slabs;
     const int chunks = C / 8, cpg = C / 32;               // channels per group (>= 2)
     const long long items = (long long)HW * chunks;
-    const long long per = (items + slabs - 1) / slabs;
+    long long per = (items + slabs - 1) / slabs;
+    per = (per + 255) / 256 * 256;                         // slab starts stay multiples of 256 (and so of `chunks`)
     const long long i0 = slab * per, i1 = min(items, i0 + per);
     const bf16 *xn = x + (long long)n * HW * C;
-    for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
-        const int ck = (int)(i % chunks);
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4 *>(xn + (i / chunks) * C + ck * 8), f);
-        if (cpg >= 8) {                                    // the 8 values belong to one group
-            float s = 0.f, q = 0.f;
+    constexpr int NG = 8 / SUB;
+    if (256 % chunks == 0) {
+        const int ck = threadIdx.x % chunks;
+        float s[NG], q[NG];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { s += f[k]; q = fmaf(f[k], f[k], q); }
-            const int g = (ck * 8) / cpg;
-            atomicAdd(&s_sum[g], s);
-            atomicAdd(&s_sq[g], q);
-        } else {                                           // cpg in {2, 4}: several groups inside the chunk
+        for (int k = 0; k < NG; ++k) s[k] = q[k] = 0.f;
+        // pointer walk: every step advances 256 / chunks pixels
+        const bf16 *xp = xn + ((i0 + threadIdx.x) / chunks) * C + ck * 8;
+        const long long step = (long long)(256 / chunks) * C;
+        const int iters = i1 > i0 + threadIdx.x ? (int)((i1 - i0 - threadIdx.x + 255) / 256) : 0;
+#pragma unroll 4
+        for (int it = 0; it < iters; ++it, xp += step) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4 *>(xp)), f);
 #pragma unroll
-            for (int k0 = 0; k0 < 8; k0 += 2) {
-                const int g = (ck * 8 + k0) / cpg;
-                atomicAdd(&s_sum[g], f[k0] + f[k0 + 1]);
-                atomicAdd(&s_sq[g], fmaf(f[k0], f[k0], f[k0 + 1] * f[k0 + 1]));
+            for (int k = 0; k < 8; ++k) { s[k / SUB] += f[k]; q[k / SUB] = fmaf(f[k], f[k], q[k / SUB]); }
+        }
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            atomicAdd(&s_sum[(ck * 8 + k * SUB) / cpg], s[k]);
+            atomicAdd(&s_sq[(ck * 8 + k * SUB) / cpg], q[k]);
+        }
+    } else {                                               // generic widths: per-chunk shared-memory atomics
+        for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+            const int ck = (int)(i % chunks);
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4 *>(xn + (i / chunks) * C + ck * 8), f);
+#pragma unroll
+            for (int k0 = 0; k0 < 8; k0 += SUB) {
+                float s = 0.f, q = 0.f;
+#pragma unroll
+                for (int k = k0; k < k0 + SUB; ++k) { s += f[k]; q = fmaf(f[k], f[k], q); }
+                atomicAdd(&s_sum[(ck * 8 + k0) / cpg], s);
+                atomicAdd(&s_sq[(ck * 8 + k0) / cpg], q);
             }
         }
     }
@@ -108,28 +158,36 @@ groupnorm_stats_kernel(const bf16 *__restrict__ x, double *__restrict__ stats, i
     }
 }
 
+template <int SUB>
 __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(const bf16 *__restrict__ x, const double *__restrict__ stats, const float *__restrict__ gamma,
                        const float *__restrict__ beta, const bf16 *__restrict__ shortcut, bf16 *__restrict__ y, long long total_chunks,
                        int HW, int C, float eps, int relu) {
     const int chunks = C / 8, cpg = C / 32;
-    const double cnt = (double)HW * cpg;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total_chunks; i += (long long)gridDim.x * 256) {
-        const int ck = (int)(i % chunks);
-        const long long pix = i / chunks;
-        const int n = (int)(pix / HW);
+    const double inv_cnt = 1.0 / ((double)HW * cpg);
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < (unsigned)total_chunks; i += gridDim.x * 256u) {   // 32-bit index math
+        const unsigned upix = i / (unsigned)chunks;
+        const int ck = (int)(i - upix * (unsigned)chunks);
+        const long long pix = upix;
+        const int n = (int)(upix / (unsigned)HW);
         float f[8], r[8];
-        unpack8(*reinterpret_cast<const uint4 *>(x + pix * C + ck * 8), f);
-        if (shortcut) unpack8(*reinterpret_cast<const uint4 *>(shortcut + pix * C + ck * 8), r);
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(x + pix * C + ck * 8)), f);
+        if (shortcut) unpack8(__ldg(reinterpret_cast<const uint4 *>(shortcut + pix * C + ck * 8)), r);
+        const float4 g0 = *reinterpret_cast<const float4 *>(gamma + ck * 8), g1 = *reinterpret_cast<const float4 *>(gamma + ck * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4 *>(beta + ck * 8), b1 = *reinterpret_cast<const float4 *>(beta + ck * 8 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int c = ck * 8 + k, g = c / cpg;
-            const double m = stats[((long long)n * 32 + g) * 2] / cnt;
-            const double var = stats[((long long)n * 32 + g) * 2 + 1] / cnt - m * m;
-            const float rstd = rsqrtf(fmaxf((float)var, 0.0f) + eps);
-            float v = (f[k] - (float)m) * rstd * gamma[c] + beta[c];
-            if (shortcut) v += r[k];
-            f[k] = relu ? fmaxf(v, 0.0f) : v;
+        for (int k0 = 0; k0 < 8; k0 += SUB) {
+            const double2 st = *reinterpret_cast<const double2 *>(stats + ((long long)n * 32 + (ck * 8 + k0) / cpg) * 2);
+            const double md = st.x * inv_cnt;
+            const float m = (float)md, rstd = rsqrtf(fmaxf((float)(st.y * inv_cnt - md * md), 0.0f) + eps);
+#pragma unroll
+            for (int k = k0; k < k0 + SUB; ++k) {
+                float v = (f[k] - m) * rstd * gg[k] + bb[k];
+                if (shortcut) v += r[k];
+                f[k] = relu ? fmaxf(v, 0.0f) : v;
+            }
         }
         *reinterpret_cast<uint4 *>(y + pix * C + ck * 8) = pack8(f);
     }
@@ -198,6 +256,7 @@ readout_concat_kernel(const bf16 *__restrict__ tokens, bf16 *__restrict__ feats,
 }
 
 // ------------------------------------------------------------------ global multi-head attention, head dim 64
+// Fallback for N > 640 tokens (the tcgen05 kernel in global_attention_tc.cu covers the model's 577).
 // qkv bf16 [B,N,3*H*64] (q|k|v), out bf16 [B,N,H*64]; softmax(q k^T / 8) v.  One CTA per (image, head, 128 queries);
 // K and V of the head are staged in shared memory as bf16; one thread per query, chunked online softmax in fp32.
 constexpr int GD = 64, GCH = 8;
@@ -354,10 +413,9 @@ extern "C" {
 
 int soccdpt_stem_conv7_fwd(const float *x, const float *w, void *y, int batch, int H, int W, soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(x && w && y && batch >= 1 && H >= 7 && W >= 7, "stem_conv7: bad arguments");
-    const long long pix = (long long)batch * ((H + 1) / 2) * ((W + 1) / 2);
-    long long blocks = (pix + 3) / 4;
-    const long long cap = (long long)soccdpt::sm_count() * 8;
-    if (blocks > cap) blocks = cap;
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    const long long blocks = (long long)batch * Ho * ((Wo + ST_PX - 1) / ST_PX);
+    SOCCDPT_REQUIRE(blocks < (1ll << 31), "stem_conv7: too many tiles");
     stem_conv7_kernel<<<(unsigned)blocks, 256, 0, soccdpt::as_stream(stream)>>>(x, w, static_cast<bf16 *>(y), batch, H, W);
     return soccdpt::check_launch("stem_conv7_kernel");
 }
@@ -365,20 +423,30 @@ int soccdpt_stem_conv7_fwd(const float *x, const float *w, void *y, int batch, i
 int soccdpt_groupnorm_fwd(const void *x, const float *gamma, const float *beta, const void *shortcut, void *y, int batch,
                           int HW, int C, float eps, int relu, void *stats_scratch, soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(x && gamma && beta && y && stats_scratch, "groupnorm: NULL pointer");
-    SOCCDPT_REQUIRE(batch >= 1 && HW >= 1 && C % 64 == 0, "groupnorm: C must be a multiple of 64 (32 groups x >= 2 channels), got %d", C);
+    SOCCDPT_REQUIRE(batch >= 1 && HW >= 1 && (C == 64 || C == 128 || (C >= 256 && C % 256 == 0)),
+                    "groupnorm: 32 groups of 2, 4 or a multiple of 8 channels (C = 64, 128 or a multiple of 256), got %d", C);
     cudaStream_t st = soccdpt::as_stream(stream);
     double *stats = static_cast<double *>(stats_scratch);           // [batch][32][2]
     SOCCDPT_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * batch * 64, st));
     int slabs = (int)(((long long)HW * (C / 8) + 256 * 32 - 1) / (256 * 32));   // ~32 chunks per thread
     if (slabs < 1) slabs = 1;
     if (slabs > 512) slabs = 512;
-    groupnorm_stats_kernel<<<(unsigned)(batch * slabs), 256, 0, st>>>(static_cast<const bf16 *>(x), stats, HW, C, slabs);
-    int rc = soccdpt::check_launch("groupnorm_stats_kernel");
-    if (rc) return rc;
+    const bf16 *xp = static_cast<const bf16 *>(x), *sp = static_cast<const bf16 *>(shortcut);
+    bf16 *yp = static_cast<bf16 *>(y);
     const long long total = (long long)batch * HW * (C / 8);
-    groupnorm_apply_kernel<<<grid_for(total), 256, 0, st>>>(static_cast<const bf16 *>(x), stats, gamma, beta,
-                                                            static_cast<const bf16 *>(shortcut), static_cast<bf16 *>(y), total, HW, C,
-                                                            eps, relu);
+    SOCCDPT_REQUIRE(total < (1ll << 31), "groupnorm: tensor too large for one call (%lld chunks)", total);
+    const unsigned g1 = (unsigned)(batch * slabs), g2 = (unsigned)grid_for(total);
+#define SOCC_GN(SUB)                                                                                          \
+    do {                                                                                                      \
+        groupnorm_stats_kernel<SUB><<<g1, 256, 0, st>>>(xp, stats, HW, C, slabs);                             \
+        int rc = soccdpt::check_launch("groupnorm_stats_kernel");                                             \
+        if (rc) return rc;                                                                                    \
+        groupnorm_apply_kernel<SUB><<<g2, 256, 0, st>>>(xp, stats, gamma, beta, sp, yp, total, HW, C, eps, relu); \
+    } while (0)
+    if (C == 64) SOCC_GN(2);
+    else if (C == 128) SOCC_GN(4);
+    else SOCC_GN(8);
+#undef SOCC_GN
     return soccdpt::check_launch("groupnorm_apply_kernel");
 }
 
@@ -409,6 +477,9 @@ int soccdpt_global_attention_fwd(const void *qkv, void *out, int batch, int N, i
                                  soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(qkv && out && batch >= 1 && N >= 1 && heads >= 1, "global_attention: bad arguments");
     SOCCDPT_REQUIRE(head_dim == GD, "global_attention: head_dim must be 64 (got %d)", head_dim);
+    if (N <= soccdpt::global_attention_tc_max_tokens())      // tcgen05 kernel (global_attention_tc.cu)
+        return soccdpt::launch_global_attention_tc(qkv, out, batch, N, heads, soccdpt::as_stream(stream));
+    // longer sequences: CUDA-core kernel with K / V of one head resident in shared memory
     const int Npad = (N + GCH - 1) / GCH * GCH;
     const size_t smem = (size_t)Npad * GD * 2 * sizeof(bf16);
     SOCCDPT_REQUIRE(smem <= 220 * 1024, "global_attention: %d tokens do not fit shared memory", N);

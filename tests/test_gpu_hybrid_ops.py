@@ -29,7 +29,7 @@ def test_stem_conv7(hw):
     assert (y - ref).abs().max() <= 8e-3 * ref.abs().max()
 
 
-@pytest.mark.parametrize("C", [64, 128, 256, 1024])
+@pytest.mark.parametrize("C", [64, 128, 256, 1024, 768])
 @pytest.mark.parametrize("shortcut,relu", [(False, True), (True, True), (False, False)])
 def test_groupnorm(C, shortcut, relu):
     torch.manual_seed(1)
@@ -88,15 +88,17 @@ def test_prenorm(C):
     assert torch.equal(m2, m + t.float()) and torch.equal(sb3, m2.bfloat16())
 
 
-@pytest.mark.parametrize("B,N,heads", [(2, 577, 12), (1, 100, 3), (3, 128, 2)])
+@pytest.mark.parametrize("B,N,heads", [(2, 577, 12), (1, 100, 3), (3, 128, 2), (1, 640, 2), (2, 257, 4), (1, 7, 1),
+                                       (1, 700, 2)])   # 700 > 640 tokens: CUDA-core fallback
 def test_global_attention(B, N, heads):
     torch.manual_seed(4)
-    qkv = torch.randn(B, N, 3 * heads * 64, device="cuda").bfloat16()
+    qkv = (torch.randn(B, N, 3 * heads * 64, device="cuda") * 1.5).bfloat16()
     out = K.global_attention(qkv, heads).float()
     q, k, v = qkv.float().reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
     ref = ((q @ k.transpose(-2, -1)) * 0.125).softmax(-1) @ v
     ref = ref.transpose(1, 2).reshape(B, N, heads * 64)
-    assert (out - ref).abs().max() <= 1e-2
+    # P is rounded to bf16 for the tensor core and the output to bf16: |err| <~ 2^-8 |v|max
+    assert (out - ref).abs().max() <= 2.5e-2 and (out - ref).abs().mean() <= 2e-3
 
 
 @pytest.mark.parametrize("impl", ["tcgen05", "ref"])

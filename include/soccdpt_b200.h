@@ -171,6 +171,12 @@ int soccdpt_seg_finish_fwd(const float *logits, float *seg, int N, int h, int w,
 int soccdpt_depth_tail_fwd(const void *T, const float *b2, const float *pw, const float *pb, float *depth,
                            int N, int h, int w, soccdpt_stream_t stream);
 
+/* Diagnostic: sweeps all 2^32 fp32 bit patterns on the device and counts where the fast exact-arithmetic sequences of the
+ * voxeliser differ from the IEEE operation they replace (the reference's torch ops, SOccDPT.py:288-316, 393-437):
+ * mismatches[0]: MUFU.RCP + Newton step vs correctly rounded 1/x; mismatches[1..5]: fp64-reciprocal division by fx, fy,
+ * occ_shape[0..2] vs correctly rounded x / c.  All six must be 0.  Synchronises the stream; ~0.1 s. */
+int soccdpt_selftest_exact_math(const soccdpt_geometry_t *g, unsigned long long mismatches[6], soccdpt_stream_t stream);
+
 /* dtype plumbing for the boundary: f32 <-> bf16 round-to-nearest-even, n elements */
 int soccdpt_f32_to_bf16(const float *x, void *y, long long n, soccdpt_stream_t stream);
 int soccdpt_bf16_to_f32(const void *x, float *y, long long n, soccdpt_stream_t stream);

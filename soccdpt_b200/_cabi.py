@@ -56,6 +56,7 @@ SYMBOLS = {
                                   c_void_p, _SZ, c_void_p]),
     "soccdpt_postprocess_fwd": (_I, [c_void_p, c_void_p, _I, _I, _I, ctypes.POINTER(Geometry), c_void_p, c_void_p,
                                      c_void_p, c_void_p, _I, c_void_p, _SZ, c_void_p]),
+    "soccdpt_selftest_exact_math": (_I, [ctypes.POINTER(Geometry), ctypes.POINTER(ctypes.c_ulonglong * 6), c_void_p]),
     "soccdpt_conv_fwd": (_I, [ctypes.POINTER(Conv), c_void_p]),
     "soccdpt_conv_ref_fwd": (_I, [ctypes.POINTER(Conv), c_void_p]),
     "soccdpt_patch_embed_fwd": (_I, [c_void_p] * 7 + [_I] * 4 + [c_void_p]),

@@ -13,6 +13,10 @@ from soccdpt_b200.synthetic import write_calib_yaml
 pytestmark = pytest.mark.gpu
 
 
+GU_SMALL = {"Camera.fx": 104.2, "Camera.fy": 104.6, "Camera.cx": 81.5, "Camera.cy": 46.8, "Camera.k1": 0.0, "Camera.k2": 0.0,
+            "Camera.p1": 0.0, "Camera.p2": 0.0, "Camera.width": 160, "Camera.height": 90}
+
+
 def _bits(t):
     return (t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)).view(np.uint32)
 
@@ -100,6 +104,22 @@ def test_fused_resize_path_matches_oracle(tmp_path):
         # against the oracle only a handful of boundary-straddling voxels may differ
         diff = (out[3].cpu() != ref[3]).sum().item()
         assert diff <= 0.002 * max(1, int(ref[3].sum().item())), diff
+
+
+@pytest.mark.parametrize("calib,scale", [(O.SYNTHETIC_CALIB, (2.0, 2.0, 0.666)), (GU_SMALL, (2.0, 2.0, 0.666)),
+                                         (dict(O.SYNTHETIC_CALIB, **{"Camera.fx": 1277.0, "Camera.fy": 911.3}), (1.0, 3.0, 0.25))])
+def test_fast_exact_arithmetic_is_ieee_on_all_inputs(tmp_path, calib, scale):
+    """The straight-line fast paths of the exact stage (reciprocal by MUFU.RCP + Newton step; division by the calibration
+    constants as an fp64 multiply) agree with correctly rounded IEEE 1/x and x/c on EVERY fp32 input they accept: exhaustive
+    sweep of the 2^32 bit patterns on the device (soccdpt_selftest_exact_math)."""
+    import ctypes
+    from soccdpt_b200 import _cabi
+    geom = O.Geometry(calib=calib, scale=scale)
+    net = _net(tmp_path, calib, geom, scale)
+    g = net._geometry()
+    out = (ctypes.c_ulonglong * 6)()
+    _cabi.check(_cabi.load().soccdpt_selftest_exact_math(ctypes.byref(g), ctypes.byref(out), _cabi.current_stream()), "selftest")
+    assert list(out) == [0] * 6, list(out)
 
 
 def test_full_size_batch_properties(tmp_path):

@@ -279,30 +279,37 @@ patch_merge_gather_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, int 
 }
 
 // ------------------------------------------------------------------ bilinear, align_corners=True, NHWC bf16
+// blockIdx.y = output row (n, Y): the vertical taps / weights are block-uniform; a thread owns 8 channels of one output
+// pixel.  32-bit index math only (the first version spent five emulated 64-bit divisions per 16 output bytes).
 __global__ void __launch_bounds__(256)
-upsample_bilinear_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, int N, int h, int w, int H, int W, int C) {
-    const int chunks = C / 8;
-    const long long total = (long long)N * H * W * chunks;
+upsample_bilinear_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, unsigned rows, int h, int w, int H, int W, int C) {
+    const unsigned chunks = (unsigned)C / 8u;
+    for (unsigned row = blockIdx.y; row < rows; row += gridDim.y) {
+    const unsigned n = row / (unsigned)H, Y = row - n * (unsigned)H;
     const float sh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.0f;
     const float sw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.0f;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const int ck = (int)(i % chunks);
-        const long long o = i / chunks;
-        const int X = (int)(o % W), Y = (int)((o / W) % H), n = (int)(o / ((long long)W * H));
-        const float fy = sh * (float)Y, fx = sw * (float)X;
-        const int y0 = (int)fy, x0 = (int)fx;
-        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-        const float ly = fy - (float)y0, lx = fx - (float)x0;
-        const bf16 *base = x + (long long)n * h * w * C + ck * 8;
+    const float fy = sh * (float)Y;
+    const int y0 = (int)fy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
+    const float ly = fy - (float)y0;
+    const bf16 *r0 = x + ((size_t)n * h + y0) * w * C, *r1 = x + ((size_t)n * h + y1) * w * C;
+    bf16 *yr = y + (size_t)row * W * C;
+    const unsigned items = (unsigned)W * chunks;
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < items; i += gridDim.x * 256u) {
+        const unsigned X = i / chunks, ck = i - X * chunks;
+        const float fx = sw * (float)X;
+        const int x0 = (int)fx, x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float lx = fx - (float)x0;
+        const unsigned o0 = (unsigned)x0 * (unsigned)C + ck * 8u, o1 = (unsigned)x1 * (unsigned)C + ck * 8u;
         float a[8], b[8], c2[8], d[8], r[8];
-        unpack8(*reinterpret_cast<const uint4 *>(base + ((long long)y0 * w + x0) * C), a);
-        unpack8(*reinterpret_cast<const uint4 *>(base + ((long long)y0 * w + x1) * C), b);
-        unpack8(*reinterpret_cast<const uint4 *>(base + ((long long)y1 * w + x0) * C), c2);
-        unpack8(*reinterpret_cast<const uint4 *>(base + ((long long)y1 * w + x1) * C), d);
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(r0 + o0)), a);
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(r0 + o1)), b);
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(r1 + o0)), c2);
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(r1 + o1)), d);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             r[k] = (1.0f - ly) * ((1.0f - lx) * a[k] + lx * b[k]) + ly * ((1.0f - lx) * c2[k] + lx * d[k]);
-        *reinterpret_cast<uint4 *>(y + o * C + ck * 8) = pack8(r);
+        *reinterpret_cast<uint4 *>(yr + (size_t)i * 8u) = pack8(r);
+    }
     }
 }
 
@@ -422,9 +429,11 @@ int soccdpt_patch_merge_gather_fwd(const void *x, void *y, int batch, int H, int
 int soccdpt_upsample_bilinear_fwd(const void *x, void *y, int N, int h, int w, int H, int W, int C,
                                   soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(x && y && N >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && C % 8 == 0, "upsample: bad arguments");
-    const long long items = (long long)N * H * W * (C / 8);
-    upsample_bilinear_kernel<<<grid_for(items), 256, 0, soccdpt::as_stream(stream)>>>(
-        static_cast<const bf16 *>(x), static_cast<bf16 *>(y), N, h, w, H, W, C);
+    SOCCDPT_REQUIRE((long long)N * H < (1ll << 31) && (long long)W * C < (1ll << 31), "upsample: tensor too large");
+    const unsigned per_row = (unsigned)(((long long)W * (C / 8) + 255) / 256), rows = (unsigned)N * (unsigned)H;
+    dim3 grid(per_row < 64u ? per_row : 64u, rows < 65535u ? rows : 65535u);
+    upsample_bilinear_kernel<<<grid, 256, 0, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(x), static_cast<bf16 *>(y), rows, h,
+                                                                          w, H, W, C);
     return soccdpt::check_launch("upsample_bilinear_kernel");
 }
 

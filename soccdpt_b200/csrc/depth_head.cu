@@ -25,7 +25,7 @@ constexpr int VP = VC + 4;      // smem pitch in floats (400 B): conflict-free f
 //   pass A  V[x][dx*32+c] = sum_{dy: 0 <= Y+dy-1 < H} lerp_y(T[y0|y1][x][(dy*3+dx)*32 + c])      (w x 96 fp32 in smem)
 //   pass B  out[X]        = relu(pb + sum_c pw[c] relu(b2[c] + sum_{dx: 0 <= X+dx-1 < W} lerp_x(V[x0|x1][dx*32+c])))
 // 2.4x fewer FMAs than the direct gather and every T element of the three source row pairs is read once per row.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)   // <= 85 registers: 3 CTAs per SM hide the latency of the T loads (1 CTA at 131 registers did not)
 depth_tail_kernel(const bf16 *__restrict__ T, const float *__restrict__ b2, const float *__restrict__ pw,
                   const float *__restrict__ pb, float *__restrict__ out, int N, int h, int w) {
     extern __shared__ __align__(16) float V[];       // [w][VP]

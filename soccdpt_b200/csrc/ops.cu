@@ -294,6 +294,7 @@ upsample_bilinear_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, unsig
     const bf16 *r0 = x + ((size_t)n * h + y0) * w * C, *r1 = x + ((size_t)n * h + y1) * w * C;
     bf16 *yr = y + (size_t)row * W * C;
     const unsigned items = (unsigned)W * chunks;
+#pragma unroll 4
     for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < items; i += gridDim.x * 256u) {
         const unsigned X = i / chunks, ck = i - X * chunks;
         const float fx = sw * (float)X;
@@ -431,7 +432,8 @@ int soccdpt_upsample_bilinear_fwd(const void *x, void *y, int N, int h, int w, i
     SOCCDPT_REQUIRE(x && y && N >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && C % 8 == 0, "upsample: bad arguments");
     SOCCDPT_REQUIRE((long long)N * H < (1ll << 31) && (long long)W * C < (1ll << 31), "upsample: tensor too large");
     const unsigned per_row = (unsigned)(((long long)W * (C / 8) + 255) / 256), rows = (unsigned)N * (unsigned)H;
-    dim3 grid(per_row < 64u ? per_row : 64u, rows < 65535u ? rows : 65535u);
+    const unsigned gx = (per_row + 3u) / 4u;            // ~4 items per thread: more loads in flight, setup amortised
+    dim3 grid(gx < 64u ? gx : 64u, rows < 65535u ? rows : 65535u);
     upsample_bilinear_kernel<<<grid, 256, 0, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(x), static_cast<bf16 *>(y), rows, h,
                                                                           w, H, W, C);
     return soccdpt::check_launch("upsample_bilinear_kernel");

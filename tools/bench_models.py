@@ -39,6 +39,9 @@ def main():
         torch.cuda.synchronize()
         ms = s.elapsed_time(e) / a.iters
         print(f"{a.model} B={a.batch}: {ms:.3f} ms/step network only -> {a.batch / ms * 1e3:.1f} frames/s")
+        for _ in range(2):
+            net(x)
+        torch.cuda.synchronize()
         s.record()
         for _ in range(a.iters):
             net(x)

@@ -16,6 +16,8 @@
 namespace soccdpt {
 int launch_window_attention_tc(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
                                int C, int heads, int ws, int shift, cudaStream_t st);
+int launch_window_attention_tc24(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
+                                 int C, int heads, int shift, cudaStream_t st);
 }
 
 namespace {
@@ -168,10 +170,14 @@ extern "C" int soccdpt_window_attention_fwd(const void *qkv, const float *bias, 
     SOCCDPT_REQUIRE(ws >= 1 && Hs % ws == 0 && Ws % ws == 0, "window_attention: window %d does not tile %dx%d", ws, Hs, Ws);
     SOCCDPT_REQUIRE(shift >= 0 && shift < ws, "window_attention: bad shift %d", shift);
     const int N = ws * ws;
-    // 16x16 windows (256 tokens) run on the tensor cores (attention_tc.cu); other window sizes (8x8 last stage of
-    // the tiny model, 24x24 / 12x12 of swin2_base_384) use the CUDA-core kernel above.
-    if (N == 256) return soccdpt::launch_window_attention_tc(qkv, bias, scale, out, batch, Hs, Ws, C, heads, ws, shift,
-                                                             soccdpt::as_stream(stream));
+    // 16x16 windows (256 tokens, swin2_tiny_256) and 24x24 windows (576 tokens, swin2_base_384) run on the tensor cores
+    // (attention_tc.cu, attention_tc24.cu); the small last-stage windows (8x8, 12x12) use the CUDA-core kernel above.
+    // SOCCDPT_ATTENTION_REF=1 (tests only) forces the CUDA-core kernel for an on-device cross-check.
+    static const bool force_ref = getenv("SOCCDPT_ATTENTION_REF") != nullptr;
+    if (N == 256 && !force_ref) return soccdpt::launch_window_attention_tc(qkv, bias, scale, out, batch, Hs, Ws, C, heads, ws, shift,
+                                                                           soccdpt::as_stream(stream));
+    if (N == 576 && !force_ref) return soccdpt::launch_window_attention_tc24(qkv, bias, scale, out, batch, Hs, Ws, C, heads, shift,
+                                                                             soccdpt::as_stream(stream));
     SOCCDPT_REQUIRE(N % CH == 0 && N <= 1024, "window_attention: window tokens must be a multiple of %d and <= 1024 (got %d)", CH, N);
     const int threads = N > 256 ? 192 : (N + 31) / 32 * 32;   // larger windows: several query rows per thread
     const size_t smem = (size_t)N * D * 2 * sizeof(float) + (size_t)N * sizeof(int);

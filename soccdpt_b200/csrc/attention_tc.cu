@@ -226,15 +226,35 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        // ---- softmax numerators in ONE pass.  Cosine attention bounds the logits: S = scale * cos(q, k) <= ~1.004 * scale
+        // ---- softmax numerators in ONE pass.  Cosine attention bounds the logits: |S| = scale * |cos(q, k)| <= ~1.004 * scale
         // (bf16-rounded unit vectors), the relative-position bias is 16 * sigmoid(.) in (0, 16) and the shift mask only
-        // subtracts, so m = 1.01 * scale + 16 is an upper bound of every logit of the row; the query's own key (cos = 1, never
-        // masked) is within ~17 of it, so exp(logit - m) cannot underflow where it matters.  Softmax is shift invariant: no
-        // row-max pass, no logits written back to TMEM, one barrier less.
+        // subtracts, so m = 1.01 * scale + 16 is an upper bound of every logit of the row and the largest un-masked logit of a
+        // row is at least -1.004 * scale.  While 2.01 * scale + 16 < 80, exp(logit - m) >= e^-80 cannot underflow where it
+        // matters (every random-init and most trained heads): softmax is shift invariant, so there is no row-max pass, nothing
+        // written back to TMEM and one barrier less.  Heads whose logit scale approaches the clamp of 100 take an exact
+        // row-max pre-pass over the scores (which stay in TMEM) instead -- decided per head from the scale itself.
         // cpb bias[i][j] = table[(qy - ky + 15) * 31 + (qx - kx + 15)]: query part in a register, key part is a
         // per-chunk constant plus a compile-time offset -> one LDS with an immediate offset per logit
         const float *tab_q = s_tab + ((r >> 4) + 15) * 31 + (r & 15) + 15;
-        const float ml = (1.01f * sc + 16.0f) * LOG2E;
+        float ml = (1.01f * sc + 16.0f) * LOG2E;
+        if (!(2.01f * sc + 16.0f < 80.0f)) {       // CTA-uniform
+            float m = -INFINITY;
+#pragma unroll 1
+            for (int c0 = wg * 128; c0 < wg * 128 + 128; c0 += 32) {
+                float v[32];
+                tmem_ld32(t_row + (uint32_t)c0, v);
+                const float *tab = tab_q - (c0 >> 4) * 31;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = v[j] + tab[-((j >> 4) * 31 + (j & 15))];
+                    if (MASK) x += (reg[c0 + j] != my_reg) ? -100.0f : 0.0f;
+                    m = fmaxf(m, x);
+                }
+            }
+            s_max[wg * 128 + row] = m;
+            __syncthreads();
+            ml = fmaxf(m, s_max[(wg ^ 1) * 128 + row]) * LOG2E;
+        }
         float l = 0.f;
 #pragma unroll 1
         for (int kk = 0; kk < 2; ++kk) {

@@ -1,0 +1,415 @@
+// SwinV2 window attention on tcgen05 / TMEM for 576-token windows (24x24: stages 0-2 of
+// swinv2_base_window12to24_192to384, > 99 % of the attention FLOPs of dpt_swin2_base_384).  timm 0.6.12
+// WindowAttention + SwinTransformerBlock._attn (window partition, cyclic shift, reverse) in one kernel.
+//
+//   one CTA (512 threads) per (window, head).  K (L2-normalised) and V^T of the whole window are staged ONCE in shared
+//   memory (72 KB) and serve all five 128-query tiles; per tile, keys are processed in 3 blocks of 192 (= 8 window rows):
+//     S_j[128x192] = Qn * Kn_j^T     tcgen05.mma M128 N192 K32, fp32 accumulators double-buffered in TMEM columns 0..383
+//     softmax                        FOUR threads per query row (TMEM lane), each owns 48 keys (2 window rows) of the block:
+//                                    add the cpb bias (one LDS with a compile-time offset per logit) and the shift mask,
+//                                    exponentiate, write P (bf16) into the 128B-swizzled K-major tile the tensor core reads
+//                                    (double-buffered: the P V MMAs of block j run under the softmax of block j + 1)
+//     O[128x32] += P_j * V_j         tcgen05.mma M128 N32 K192, TMEM columns 384..415
+//     out = O / rowsum               bf16, written straight to the un-shifted token position
+//   Softmax reference point: cosine attention bounds every logit by m = 1.01*scale + 16 (|cos| <= 1 up to bf16 rounding,
+//   bias = 16*sigmoid(.) < 16, the shift mask only subtracts).  When exp(logit - m) cannot underflow for ANY admissible
+//   logit (2.01*scale + 16 < 80: every random-init and most trained heads) the row-max pass is skipped; otherwise
+//   (logit scales towards the clamp of 100) the kernel runs an exact row-max pass first and re-issues the cheap K = 32 score
+//   MMAs -- per head, decided from the scale itself, so the result never depends on a host-side flag.
+#include "common.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+constexpr int D = 32;                      // head dim
+constexpr int WS = 24;                     // window side
+constexpr int NTOK = WS * WS;              // 576 tokens per window
+constexpr int THREADS = 512;
+constexpr int KBLK = 192;                  // keys per block = 8 window rows
+constexpr int NBLK = NTOK / KBLK;          // 3
+constexpr int QT = (NTOK + 127) / 128;     // 5 query tiles (the last one holds 64 rows)
+constexpr int KQ = KBLK / 4;               // 48 keys (2 window rows) per thread and block
+constexpr int TABW = 2 * WS - 1;           // 47
+constexpr int TAB = TABW * TABW;
+constexpr int SM_Q = 0;                                // 128 rows x 64 B, SWIZZLE_64B
+constexpr int SM_K = 8192;                             // 576 rows x 64 B, SWIZZLE_64B
+constexpr int SM_VT = SM_K + NTOK * 64;                // 9 k-blocks x (32 rows x 128 B), SWIZZLE_128B
+constexpr int SM_P = SM_VT + (NTOK / 64) * 4096;       // 2 buffers x 3 k-blocks x (128 rows x 128 B), SWIZZLE_128B
+constexpr int P_BUF = (KBLK / 64) * 16384;
+constexpr int SM_MISC = SM_P + 2 * P_BUF;              // region ids | partial sums / maxima [4][128] | barriers | slot | table
+constexpr int MISC_REG = 640, MISC_RED = 4 * 128 * 4, MISC_BAR = 64;
+constexpr int SMEM_BYTES = SM_MISC + MISC_REG + MISC_RED + MISC_BAR + ((TAB * 4 + 15) & ~15) + 1024;
+constexpr int TM_O = 2 * KBLK;             // TMEM column of O
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(SM_K % 1024 == 0 && SM_VT % 1024 == 0 && SM_P % 1024 == 0 && (KBLK * 64) % 512 == 0, "swizzle atom alignment");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar))); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// shared-memory matrix descriptor, K-major; swizzle_bytes in {64, 128}; 8-row groups are 8*swizzle_bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, int swizzle_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * swizzle_bytes) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(swizzle_bytes == 128 ? 2 : 4) << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t umma_idesc(int n) {   // D=f32, A=B=bf16, K-major, M=128
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
+    uint32_t r[8];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&t);
+}
+__device__ __forceinline__ void load_head(const bf16 *p, float f[D]) {
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+        const uint4 u = *reinterpret_cast<const uint4 *>(p + i * 8);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 t = __bfloat1622float2(h[k]);
+            f[i * 8 + 2 * k] = t.x;
+            f[i * 8 + 2 * k + 1] = t.y;
+        }
+    }
+}
+__device__ __forceinline__ int region_of(int p, int size, int ws, int shift) {
+    // timm: slices (0,-ws), (-ws,-shift), (-shift,None) over the SHIFTED image
+    return p < size - ws ? 0 : (p < size - shift ? 1 : 2);
+}
+__device__ __forceinline__ uint4 pack8_scaled(const float *f, float s) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0] * s, f[1] * s);
+    u.y = pack_bf16x2(f[2] * s, f[3] * s);
+    u.z = pack_bf16x2(f[4] * s, f[5] * s);
+    u.w = pack_bf16x2(f[6] * s, f[7] * s);
+    return u;
+}
+
+// logits of CNT keys starting at key offset J0 (compile time, inside this thread's 48 keys): S + bias (+ mask)
+template <bool MASK, int J0, int CNT>
+__device__ __forceinline__ void add_bias(float *v, const float *tab, const uint8_t *rg, int my_reg) {
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) {
+        const int jl = J0 + i;
+        float x = v[i] + tab[-((jl / WS) * TABW + (jl % WS))];
+        if (MASK) x += (rg[jl] != my_reg) ? -100.0f : 0.0f;
+        v[i] = x;
+    }
+}
+
+template <bool MASK>
+__global__ void __launch_bounds__(THREADS, 1)
+window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ bias_tab, const float *__restrict__ scale,
+                             bf16 *__restrict__ out, int Hs, int Ws, int C, int shift) {
+    extern __shared__ uint8_t tc24_raw[];
+    // 1024-byte alignment as an OFFSET on the __shared__ symbol (a uintptr_t round trip loses the address space)
+    uint8_t *smem = tc24_raw + ((1024u - (smem_u32(tc24_raw) & 1023u)) & 1023u);
+    uint8_t *reg = smem + SM_MISC;                                               // [576] shift-mask region ids
+    float *s_red = reinterpret_cast<float *>(smem + SM_MISC + MISC_REG);          // [4][128]
+    uint64_t *bar_s = reinterpret_cast<uint64_t *>(smem + SM_MISC + MISC_REG + MISC_RED);   // [2]
+    uint64_t *bar_pv = bar_s + 2;                                                // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_pv + 2);
+    float *s_tab = reinterpret_cast<float *>(smem + SM_MISC + MISC_REG + MISC_RED + MISC_BAR);   // [47*47] cpb bias of this head
+
+    const int t = threadIdx.x, warp = t >> 5;
+    const int row = t & 127;            // query row inside the tile == TMEM lane
+    const int quarter = t >> 7;         // which 48 keys of a block (and which 8 output channels) this thread owns
+    const int nwx = Ws / WS, nwy = Hs / WS;
+    const int win = blockIdx.x % (nwx * nwy), b = blockIdx.x / (nwx * nwy);
+    const int head = blockIdx.y;
+
+    for (int i = t; i < TAB; i += THREADS) s_tab[i] = bias_tab[(size_t)head * TAB + i];
+    if (t == 0) {
+        mbar_init(&bar_s[0]); mbar_init(&bar_s[1]); mbar_init(&bar_pv[0]); mbar_init(&bar_pv[1]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+
+    // token index (in the un-shifted image) of window row r, and its shift-mask region
+    auto token_of = [&](int r, int &region) -> long long {
+        const int ty = r / WS, tx = r - ty * WS;
+        const int ys = (win / nwx) * WS + ty, xs = (win % nwx) * WS + tx;
+        const int yo = (ys + shift) % Hs, xo = (xs + shift) % Ws;
+        region = MASK ? region_of(ys, Hs, WS, shift) * 3 + region_of(xs, Ws, WS, shift) : 0;
+        return ((long long)b * Hs + yo) * Ws + xo;
+    };
+
+    // ---- stage K (normalised, SW64) and V^T (SW128) of the whole window: one key row per thread
+    for (int r = t; r < NTOK; r += THREADS) {
+        int region;
+        const long long tok = token_of(r, region);
+        reg[r] = (uint8_t)region;
+        const bf16 *base = qkv + tok * 3 * C + head * D;
+        float k[D], v[D];
+        load_head(base + C, k);
+        load_head(base + 2 * C, v);
+        float kk = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) kk = fmaf(k[d], k[d], kk);
+        const float ks = 1.0f / fmaxf(sqrtf(kk), 1e-12f);     // F.normalize eps
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4)   // 4 x 16-byte chunks of the 64-byte row, Swizzle<2,4,3>
+            *reinterpret_cast<uint4 *>(smem + SM_K + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4)) = pack8_scaled(k + c4 * 8, ks);
+        // V^T: element (d, key r) -> k-block r/64, row d, column r%64 (128-byte rows, Swizzle<3,4,3>)
+        const int kb = r >> 6, col = r & 63;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int off = SM_VT + kb * 4096 + d * 128 + (((col >> 3) ^ (d & 7)) << 4) + (col & 7) * 2;
+            *reinterpret_cast<bf16 *>(smem + off) = __float2bfloat16_rn(v[d]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 TMEM lanes
+    const float sc = scale[head];
+    const float LOG2E = 1.4426950408889634f;
+    const bool one_pass = 2.01f * sc + 16.0f < 80.0f;                    // see the header comment
+    const uint32_t idesc_s = umma_idesc(KBLK), idesc_o = umma_idesc(D);
+    const uint64_t dq = umma_desc(smem_u32(smem + SM_Q), 64);
+    uint32_t ph_s0 = 0, ph_s1 = 0, ph_pv0 = 0;
+
+    auto issue_s = [&](int j) {     // S_j = Qn Kn_j^T into buffer j & 1 (thread 0 only)
+        const uint64_t dk = umma_desc(smem_u32(smem + SM_K + j * (KBLK * 64)), 64);
+        umma_f16(tmem + (uint32_t)((j & 1) * KBLK), dq, dk, idesc_s, 0u);
+        umma_f16(tmem + (uint32_t)((j & 1) * KBLK), dq + 2, dk + 2, idesc_s, 1u);      // second K step: +32 bytes
+        umma_commit(&bar_s[j & 1]);
+    };
+    auto wait_s = [&](int j) {
+        if (j & 1) { mbar_wait(&bar_s[1], ph_s1); ph_s1 ^= 1; } else { mbar_wait(&bar_s[0], ph_s0); ph_s0 ^= 1; }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+
+#pragma unroll 1
+    for (int qt = 0; qt < QT; ++qt) {
+        const int r = min(qt * 128 + row, NTOK - 1);      // my query row inside the window (rows past the end repeat the last)
+        const bool valid = qt * 128 + row < NTOK;
+        const bool active = qt * 128 + (warp & 3) * 32 < NTOK;   // warp-uniform: any valid row in this warp's 32 lanes
+        int my_reg;
+        const long long tok = token_of(r, my_reg);
+        if (quarter == 0) {   // stage normalised, scaled Q of this tile (row `row`)
+            float q[D];
+            load_head(qkv + tok * 3 * C + head * D, q);
+            float qq = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) qq = fmaf(q[d], q[d], qq);
+            const float qs = sc / fmaxf(sqrtf(qq), 1e-12f);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4)
+                *reinterpret_cast<uint4 *>(smem + SM_Q + row * 64 + ((c4 ^ ((row >> 1) & 3)) << 4)) = pack8_scaled(q + c4 * 8, qs);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            issue_s(0);
+            issue_s(1);
+        }
+        // cpb bias[i][j] = table[(qy - ky + 23) * 47 + (qx - kx + 23)]: query part in a register, the key part is a per-block
+        // constant (8 window rows per block, 2 per quarter) plus a compile-time offset
+        const float *tab_q = s_tab + (r / WS + WS - 1) * TABW + (r % WS) + WS - 1 - quarter * 2 * TABW;
+        const uint8_t *reg_q = reg + quarter * KQ;
+        float ml = (1.01f * sc + 16.0f) * LOG2E;
+
+        if (!one_pass) {
+            // ---- exact row maximum first (scores are read, never stored; the score MMAs are re-issued below)
+            float m = -INFINITY;
+#pragma unroll 1
+            for (int j = 0; j < NBLK; ++j) {
+                wait_s(j);
+                if (active) {
+                    const float *tab = tab_q - j * 8 * TABW;
+                    const uint8_t *rg = reg_q + j * KBLK;
+                    const uint32_t col = t_row + (uint32_t)((j & 1) * KBLK + quarter * KQ);
+                    float v[32];
+                    tmem_ld32(col, v);
+                    add_bias<MASK, 0, 32>(v, tab, rg, my_reg);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m = fmaxf(m, v[i]);
+                    tmem_ld16(col + 32, v);
+                    add_bias<MASK, 32, 16>(v, tab, rg, my_reg);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) m = fmaxf(m, v[i]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();                                   // buffer j & 1 has been read by everybody
+                if (t == 0 && j + 2 < NBLK) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    issue_s(j + 2);
+                }
+            }
+            s_red[quarter * 128 + row] = m;
+            __syncthreads();
+            m = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
+            ml = m * LOG2E;
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();                                       // maxima consumed before s_red carries the sums
+            if (t == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue_s(0);
+                issue_s(1);
+            }
+        }
+
+        // ---- P_j = exp(logit - reference), O += P_j V_j
+        float l = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < NBLK; ++j) {
+            wait_s(j);
+            if (j == 2) {                                          // P buffer 0 is free once P_0 V_0 has completed
+                mbar_wait(&bar_pv[0], ph_pv0);
+                ph_pv0 ^= 1;
+            }
+            if (active) {
+                const float *tab = tab_q - j * 8 * TABW;
+                const uint8_t *rg = reg_q + j * KBLK;
+                const uint32_t col = t_row + (uint32_t)((j & 1) * KBLK + quarter * KQ);
+                uint8_t *pbase = smem + SM_P + (j & 1) * P_BUF + (row >> 3) * 1024 + (row & 7) * 128;
+                float v[32];
+                tmem_ld32(col, v);
+                add_bias<MASK, 0, 32>(v, tab, rg, my_reg);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v[i] = fast_exp2(fmaf(v[i], LOG2E, -ml));
+                    l += v[i];
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int kk = quarter * KQ + g * 8;           // key inside the block -> k-block kk/64, 16-byte chunk (kk%64)/8
+                    *reinterpret_cast<uint4 *>(pbase + (kk >> 6) * 16384 + ((((kk & 63) >> 3) ^ (row & 7)) << 4)) =
+                        pack8_scaled(v + g * 8, 1.0f);
+                }
+                tmem_ld16(col + 32, v);
+                add_bias<MASK, 32, 16>(v, tab, rg, my_reg);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = fast_exp2(fmaf(v[i], LOG2E, -ml));
+                    l += v[i];
+                }
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int kk = quarter * KQ + 32 + g * 8;
+                    *reinterpret_cast<uint4 *>(pbase + (kk >> 6) * 16384 + ((((kk & 63) >> 3) ^ (row & 7)) << 4)) =
+                        pack8_scaled(v + g * 8, 1.0f);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();                                       // S_j read, P_j written by everybody
+            if (t == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int kb2 = 0; kb2 < KBLK / 64; ++kb2) {
+                    const uint64_t dp = umma_desc(smem_u32(smem + SM_P + (j & 1) * P_BUF + kb2 * 16384), 128);
+                    const uint64_t dv = umma_desc(smem_u32(smem + SM_VT + (j * (KBLK / 64) + kb2) * 4096), 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem + TM_O, dp + 2 * k, dv + 2 * k, idesc_o, (j | kb2 | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&bar_pv[j & 1]);
+                if (j + 2 < NBLK) issue_s(j + 2);
+            }
+        }
+        s_red[quarter * 128 + row] = l;
+        __syncthreads();
+        l = (s_red[row] + s_red[128 + row]) + (s_red[256 + row] + s_red[384 + row]);
+        mbar_wait(&bar_pv[0], ph_pv0);                             // P_2 V_2 (committed last: everything before it is done too)
+        ph_pv0 ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (active) {   // ---- epilogue: my 8 output channels: O / l -> bf16 -> out[token, head*32 + quarter*8 ...]
+            float o[8];
+            tmem_ld8(t_row + (uint32_t)(TM_O + quarter * 8), o);
+            if (valid) *reinterpret_cast<uint4 *>(out + tok * C + head * D + quarter * 8) = pack8_scaled(o, 1.0f / l);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                       // O / s_red read by everyone before the next tile overwrites TMEM / Q / s_red
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+}  // namespace
+
+namespace soccdpt {
+// qkv bf16 [B, Hs*Ws, 3C]; bias_tab f32 [heads][47*47] relative-position table; window must be 24x24
+int launch_window_attention_tc24(const void *qkv, const float *bias_tab, const float *scale, void *out, int batch, int Hs, int Ws,
+                                 int C, int heads, int shift, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        SOCCDPT_CUDA(cudaFuncSetAttribute(window_attention_tc24_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SOCCDPT_CUDA(cudaFuncSetAttribute(window_attention_tc24_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid((unsigned)(batch * (Hs / WS) * (Ws / WS)), (unsigned)heads);
+    if (shift > 0)
+        window_attention_tc24_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(
+            static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, shift);
+    else
+        window_attention_tc24_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(
+            static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, shift);
+    return check_launch("window_attention_tc24_kernel");
+}
+}  // namespace soccdpt

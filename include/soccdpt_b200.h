@@ -40,6 +40,16 @@ const char *soccdpt_last_error(void);
 long long soccdpt_launch_count(void);
 int soccdpt_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* ------------------------------------------------------------------ input pipeline
+ * The reference's per-frame CPU transform, SOccDPT/model/loader.py:256-270 -> transforms.py:53-251:
+ * cv2.resize(INTER_CUBIC) of a uint8 HWC frame to (dst_w, dst_h), NormalizeImage(0.5, 0.5), PrepareForNet.
+ *   frames u8  [batch, H, W, 3] (what cv2.imread / the dataset loaders produce; NOT divided by 255)
+ *   out    f32 [batch, 3, dst_h, dst_w] = 2 * resized - 1, the tensor the network consumes
+ * Bit-equal to OpenCV's own 8-bit bicubic code (cv2.ipp.setUseIPP(False)); see csrc/preprocess.cu. */
+size_t soccdpt_preprocess_workspace_bytes(int dst_h, int dst_w);
+int soccdpt_preprocess_fwd(const uint8_t *frames, int batch, int H, int W, int channels, float *out, int dst_h,
+                           int dst_w, void *workspace, size_t workspace_bytes, soccdpt_stream_t stream);
+
 /* ------------------------------------------------------------------ post-processing (A8/A9)
  * Geometry constants of the reference base class, SOccDPT/model/SOccDPT.py:134-228.  All
  * values are prepared by the host exactly as the reference prepares them (fp32 casts,

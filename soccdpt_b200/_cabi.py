@@ -51,6 +51,8 @@ SYMBOLS = {
     "soccdpt_last_error": (ctypes.c_char_p, []),
     "soccdpt_launch_count": (_LL, []),
     "soccdpt_device_info": (_I, [ctypes.POINTER(_I)] * 3),
+    "soccdpt_preprocess_workspace_bytes": (_SZ, [_I, _I]),
+    "soccdpt_preprocess_fwd": (_I, [c_void_p, _I, _I, _I, _I, c_void_p, _I, _I, c_void_p, _SZ, c_void_p]),
     "soccdpt_voxel_workspace_bytes": (_SZ, [ctypes.POINTER(Geometry), _I, _I]),
     "soccdpt_voxelize_fwd": (_I, [c_void_p, c_void_p, _I, ctypes.POINTER(Geometry), c_void_p, c_void_p, _I,
                                   c_void_p, _SZ, c_void_p]),

@@ -29,7 +29,9 @@ constexpr int TC_SMEM_VT = 8192 + 16384;  // 4 k-blocks x (32 rows x 128 B), SWI
 constexpr int TC_SMEM_P = TC_SMEM_VT + 16384;    // 4 k-blocks x (128 rows x 128 B), SWIZZLE_128B
 constexpr int TC_SMEM_MISC = TC_SMEM_P + 65536;  // region ids 256 B | row max [2][128] f32 | row sum [2][128] f32 | barrier | slot
 constexpr int TC_TAB = 31 * 31;                    // relative-position bias table of one head: (2*16-1)^2 entries
-constexpr int TC_MISC_BYTES = 256 + 1024 + 1024 + 64 + 4096;
+constexpr int TC_TS = 48;                          // its row stride in shared memory: the 32 query rows of a warp span two window
+                                                   // rows, (TC_TS - 16) % 32 == 0 puts their table reads into 32 different banks
+constexpr int TC_MISC_BYTES = 256 + 1024 + 1024 + 64 + 31 * TC_TS * 4;
 constexpr int TC_SMEM_BYTES = TC_SMEM_MISC + TC_MISC_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -134,7 +136,7 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
     float *s_sum = s_max + 256;                                              // [2][128]
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_sum + 256);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 2);
-    float *s_tab = reinterpret_cast<float *>(bar + 8);                         // [31*31] cpb bias of this head
+    float *s_tab = reinterpret_cast<float *>(bar + 8);                         // [31][TC_TS] cpb bias of this head
 
     const int t = threadIdx.x, warp = t >> 5;
     const int row = t & 127;            // query row inside the half == TMEM lane
@@ -143,7 +145,7 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
     const int win = blockIdx.x % (nwx * nwy), b = blockIdx.x / (nwx * nwy);
     const int head = blockIdx.y;
 
-    for (int i = t; i < TC_TAB; i += TC_THREADS) s_tab[i] = bias_tab[(size_t)blockIdx.y * TC_TAB + i];
+    for (int i = t; i < TC_TAB; i += TC_THREADS) s_tab[(i / 31) * TC_TS + i % 31] = bias_tab[(size_t)blockIdx.y * TC_TAB + i];
     if (t == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -235,7 +237,7 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
         // row-max pre-pass over the scores (which stay in TMEM) instead -- decided per head from the scale itself.
         // cpb bias[i][j] = table[(qy - ky + 15) * 31 + (qx - kx + 15)]: query part in a register, key part is a
         // per-chunk constant plus a compile-time offset -> one LDS with an immediate offset per logit
-        const float *tab_q = s_tab + ((r >> 4) + 15) * 31 + (r & 15) + 15;
+        const float *tab_q = s_tab + ((r >> 4) + 15) * TC_TS + (r & 15) + 15;
         float ml = (1.01f * sc + 16.0f) * LOG2E;
         if (!(2.01f * sc + 16.0f < 80.0f)) {       // CTA-uniform
             float m = -INFINITY;
@@ -243,10 +245,10 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
             for (int c0 = wg * 128; c0 < wg * 128 + 128; c0 += 32) {
                 float v[32];
                 tmem_ld32(t_row + (uint32_t)c0, v);
-                const float *tab = tab_q - (c0 >> 4) * 31;
+                const float *tab = tab_q - (c0 >> 4) * TC_TS;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float x = v[j] + tab[-((j >> 4) * 31 + (j & 15))];
+                    float x = v[j] + tab[-((j >> 4) * TC_TS + (j & 15))];
                     if (MASK) x += (reg[c0 + j] != my_reg) ? -100.0f : 0.0f;
                     m = fmaxf(m, x);
                 }
@@ -265,10 +267,10 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
                 float v[32];
                 const int c0 = kb * 64 + hh * 32;                       // first key of this chunk
                 tmem_ld32(t_row + (uint32_t)c0, v);
-                const float *tab = tab_q - (c0 >> 4) * 31;               // keys of this chunk: rows ky0, ky0 + 1
+                const float *tab = tab_q - (c0 >> 4) * TC_TS;               // keys of this chunk: rows ky0, ky0 + 1
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float x = v[j] + tab[-((j >> 4) * 31 + (j & 15))];
+                    float x = v[j] + tab[-((j >> 4) * TC_TS + (j & 15))];
                     if (MASK) x += (reg[c0 + j] != my_reg) ? -100.0f : 0.0f;
                     v[j] = fast_exp2(fmaf(x, LOG2E, -ml));
                     l += v[j];

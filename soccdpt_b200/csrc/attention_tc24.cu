@@ -31,6 +31,8 @@ constexpr int QT = (NTOK + 127) / 128;     // 5 query tiles (the last one holds 
 constexpr int KQ = KBLK / 4;               // 48 keys (2 window rows) per thread and block
 constexpr int TABW = 2 * WS - 1;           // 47
 constexpr int TAB = TABW * TABW;
+constexpr int TS = 56;                     // table row stride in shared memory: (TS - WS) % 32 == 0 puts the table reads of the
+                                           // 32 query rows of a warp (up to three window rows) into 32 different banks
 constexpr int SM_Q = 0;                                // 128 rows x 64 B, SWIZZLE_64B
 constexpr int SM_K = 8192;                             // 576 rows x 64 B, SWIZZLE_64B
 constexpr int SM_VT = SM_K + NTOK * 64;                // 9 k-blocks x (32 rows x 128 B), SWIZZLE_128B
@@ -38,7 +40,7 @@ constexpr int SM_P = SM_VT + (NTOK / 64) * 4096;       // 2 buffers x 3 k-blocks
 constexpr int P_BUF = (KBLK / 64) * 16384;
 constexpr int SM_MISC = SM_P + 2 * P_BUF;              // region ids | partial sums / maxima [4][128] | barriers | slot | table
 constexpr int MISC_REG = 640, MISC_RED = 4 * 128 * 4, MISC_BAR = 64;
-constexpr int SMEM_BYTES = SM_MISC + MISC_REG + MISC_RED + MISC_BAR + ((TAB * 4 + 15) & ~15) + 1024;
+constexpr int SMEM_BYTES = SM_MISC + MISC_REG + MISC_RED + MISC_BAR + TABW * TS * 4 + 1024;
 constexpr int TM_O = 2 * KBLK;             // TMEM column of O
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(SM_K % 1024 == 0 && SM_VT % 1024 == 0 && SM_P % 1024 == 0 && (KBLK * 64) % 512 == 0, "swizzle atom alignment");
@@ -148,7 +150,7 @@ __device__ __forceinline__ void add_bias(float *v, const float *tab, const uint8
 #pragma unroll
     for (int i = 0; i < CNT; ++i) {
         const int jl = J0 + i;
-        float x = v[i] + tab[-((jl / WS) * TABW + (jl % WS))];
+        float x = v[i] + tab[-((jl / WS) * TS + (jl % WS))];
         if (MASK) x += (rg[jl] != my_reg) ? -100.0f : 0.0f;
         v[i] = x;
     }
@@ -175,7 +177,7 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
     const int win = blockIdx.x % (nwx * nwy), b = blockIdx.x / (nwx * nwy);
     const int head = blockIdx.y;
 
-    for (int i = t; i < TAB; i += THREADS) s_tab[i] = bias_tab[(size_t)head * TAB + i];
+    for (int i = t; i < TAB; i += THREADS) s_tab[(i / TABW) * TS + i % TABW] = bias_tab[(size_t)head * TAB + i];
     if (t == 0) {
         mbar_init(&bar_s[0]); mbar_init(&bar_s[1]); mbar_init(&bar_pv[0]); mbar_init(&bar_pv[1]);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -269,7 +271,7 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
         }
         // cpb bias[i][j] = table[(qy - ky + 23) * 47 + (qx - kx + 23)]: query part in a register, the key part is a per-block
         // constant (8 window rows per block, 2 per quarter) plus a compile-time offset
-        const float *tab_q = s_tab + (r / WS + WS - 1) * TABW + (r % WS) + WS - 1 - quarter * 2 * TABW;
+        const float *tab_q = s_tab + (r / WS + WS - 1) * TS + (r % WS) + WS - 1 - quarter * 2 * TS;
         const uint8_t *reg_q = reg + quarter * KQ;
         float ml = (1.01f * sc + 16.0f) * LOG2E;
 
@@ -280,7 +282,7 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
             for (int j = 0; j < NBLK; ++j) {
                 wait_s(j);
                 if (active) {
-                    const float *tab = tab_q - j * 8 * TABW;
+                    const float *tab = tab_q - j * 8 * TS;
                     const uint8_t *rg = reg_q + j * KBLK;
                     const uint32_t col = t_row + (uint32_t)((j & 1) * KBLK + quarter * KQ);
                     float v[32];
@@ -323,7 +325,7 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                 ph_pv0 ^= 1;
             }
             if (active) {
-                const float *tab = tab_q - j * 8 * TABW;
+                const float *tab = tab_q - j * 8 * TS;
                 const uint8_t *rg = reg_q + j * KBLK;
                 const uint32_t col = t_row + (uint32_t)((j & 1) * KBLK + quarter * KQ);
                 uint8_t *pbase = smem + SM_P + (j & 1) * P_BUF + (row >> 3) * 1024 + (row & 7) * 128;

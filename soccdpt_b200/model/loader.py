@@ -11,8 +11,6 @@ _BACKBONES = {
     "dpt_swin2_tiny_256": "swin2t16_256",
     "dpt_hybrid_384": "vitb_rn50_384",
 }
-# (net_w, net_h) exactly as the reference returns them (loader.py:177-199): 256x256 even for swin2_base_384
-_INPUT_SIZES = {"dpt_swin2_base_384": (256, 256), "dpt_swin2_tiny_256": (256, 256), "dpt_hybrid_384": (384, 384)}
 
 
 def load_model(arch, model_kwargs: dict, device: torch.device, model_path: str, model_type: str = "dpt_large_384",
@@ -31,22 +29,20 @@ def load_model(arch, model_kwargs: dict, device: torch.device, model_path: str, 
 
 def load_transforms(model_type: str = "dpt_large_384", height: int = 0, square: bool = False):
     """Returns (transform, net_w, net_h).  The transform is the reference's CPU pre-processing
-    (cv2 bicubic Resize -> NormalizeImage(0.5,0.5) -> PrepareForNet, transforms.py:53-251) restated on
-    numpy/cv2; it is outside the accelerated path."""
-    if model_type not in _INPUT_SIZES:
-        print(f"model_type '{model_type}' not implemented")
-        assert False
-    net_w, net_h = _INPUT_SIZES[model_type]
-    if height != 0:
-        net_w, net_h = height, height
+    (cv2 bicubic Resize to a multiple of 32 -> NormalizeImage(0.5,0.5) -> PrepareForNet, transforms.py:53-251) restated on
+    numpy/cv2 for callers that hold host frames; `soccdpt_b200.preprocess.load_gpu_transforms` is the same
+    transform as one CUDA kernel on device-resident uint8 frames."""
+    from ..preprocess import get_size, transform_config
+    net_w, net_h, keep_aspect_ratio = transform_config(model_type, height, square)
 
     def transform(sample):
         import cv2
         import numpy as np
-        img = cv2.resize(sample["image"], (net_w, net_h), interpolation=cv2.INTER_CUBIC)
+        w, h = get_size(sample["image"].shape[1], sample["image"].shape[0], net_w, net_h, keep_aspect_ratio)
+        img = cv2.resize(sample["image"], (w, h), interpolation=cv2.INTER_CUBIC)
         img = (img - np.array([0.5, 0.5, 0.5])) / np.array([0.5, 0.5, 0.5])
         out = dict(sample)
-        out["image"] = np.ascontiguousarray(np.transpose(img, (2, 0, 1)).astype(np.float32))
+        out["image"] = np.ascontiguousarray(np.transpose(img, (2, 0, 1))).astype(np.float32)
         return out
 
     return transform, net_w, net_h

@@ -40,6 +40,21 @@ const char *soccdpt_last_error(void);
 long long soccdpt_launch_count(void);
 int soccdpt_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* ------------------------------------------------------------------ sparse occupancy outputs
+ * The reference's occupancy_grid_to_points (SOccDPT/utils/__init__.py:532-568, numpy on the CPU) on the device:
+ * rows (x, y, z, class) as f64 with x = f32(i / G0 * occ_shape[0]) etc. for every cell >= 0.5, ordered by class,
+ * then by (i, j, k).  Input is the bit-packed mask (layout: SOCCDPT_OCC_PACKED above), straight from the voxeliser's
+ * workspace or packed from a dense grid (G0,G1,G2,C) by soccdpt_grid_pack_fwd.
+ * soccdpt_occupancy_points_fwd writes the number of rows to *count (device memory); with points == NULL it only counts
+ * (size the output, then call again); rows beyond `capacity` are dropped. */
+size_t soccdpt_occupancy_mask_bytes(const int grid[3]);
+size_t soccdpt_occupancy_points_workspace_bytes(const int grid[3], int num_classes);
+int soccdpt_grid_pack_fwd(const float *grid_dense, const int grid[3], int num_classes, uint32_t *mask,
+                          soccdpt_stream_t stream);
+int soccdpt_occupancy_points_fwd(const uint32_t *mask, const int grid[3], const float occ_shape[3], int num_classes,
+                                 double *points, long long capacity, long long *count, void *workspace,
+                                 size_t workspace_bytes, soccdpt_stream_t stream);
+
 /* ------------------------------------------------------------------ input pipeline
  * The reference's per-frame CPU transform, SOccDPT/model/loader.py:256-270 -> transforms.py:53-251:
  * cv2.resize(INTER_CUBIC) of a uint8 HWC frame to (dst_w, dst_h), NormalizeImage(0.5, 0.5), PrepareForNet.
@@ -67,6 +82,10 @@ typedef struct {
 
 #define SOCCDPT_OCC_REFERENCE_UNION 0 /* reference semantics: OR over the batch, written to every b */
 #define SOCCDPT_OCC_PER_FRAME 1       /* extension: each frame gets only its own voxels */
+#define SOCCDPT_OCC_PACKED 2          /* flag, OR-ed in: keep the bit-packed voxel mask at the start of the workspace as
+                                         an output (grid may then be NULL): uint32 words, voxel v = (i*G1 + j)*G2 + k lives in
+                                         word v >> 3, class c is bit (v & 7) * 4 + c; one mask per call, or per frame in
+                                         PER_FRAME mode (soccdpt_occupancy_mask_bytes() apart) */
 
 /* bytes of scratch the two calls below need: bit-packed voxel mask (+ per-row / per-column resize tables) */
 size_t soccdpt_voxel_workspace_bytes(const soccdpt_geometry_t *g, int batch, int mode);

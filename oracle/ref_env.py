@@ -58,3 +58,18 @@ def import_reference(repair_hybrid=True):
     import SOccDPT.model.loader as ref_loader  # noqa: E402
     import SOccDPT.model.SOccDPT as ref_model  # noqa: E402
     return ref_loader, ref_model
+
+
+def load_reference_function(rel_path, name, namespace=None):
+    """Compiles ONE top-level function of a reference source file in memory (for modules whose own imports -- matplotlib,
+    wandb -- are missing here).  The text is read from /root/reference at run time and never written into this repo."""
+    import ast
+    path = os.path.join(REFERENCE_ROOT, rel_path)
+    with open(path) as f:
+        src = f.read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            ns = dict(namespace or {})
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+            return ns[name]
+    raise KeyError(f"{name} not found in {path}")

@@ -290,3 +290,18 @@ def occupancy_indices(grid):
     """Sorted (b,i,j,k,c) index list of a dense grid (for index-level comparisons)."""
     g = torch.as_tensor(grid)
     return g.nonzero()
+
+
+def occupancy_grid_to_points(occupancy_grid, grid_size=(256, 256, 32), scale=(2.0, 2.0, 0.666)):
+    """Restatement of SOccDPT/utils/__init__.py:532-568: cells >= 0.5 as float64 rows (x, y, z, class); per class the
+    np.argwhere order, coordinates = float32(index / grid_size * float32(grid_size / scale))."""
+    g = np.asarray(occupancy_grid)
+    assert g.ndim == 4
+    occ = np.array([float(grid_size[i] / scale[i]) for i in range(3)], dtype=np.float32)
+    idx = np.argwhere(g >= 0.5)
+    rows = []
+    for c in range(g.shape[3]):
+        ijk = idx[idx[:, 3] == c][:, :3]
+        xyz = (ijk / np.array(grid_size[:3]) * occ).astype(np.float32)
+        rows.append(np.concatenate([xyz, np.full((xyz.shape[0], 1), c)], axis=1))
+    return np.concatenate(rows, axis=0)

@@ -15,6 +15,7 @@ c_void_p = ctypes.c_void_p
 
 OCC_REFERENCE_UNION = 0
 OCC_PER_FRAME = 1
+OCC_PACKED = 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 
@@ -53,6 +54,11 @@ SYMBOLS = {
     "soccdpt_device_info": (_I, [ctypes.POINTER(_I)] * 3),
     "soccdpt_preprocess_workspace_bytes": (_SZ, [_I, _I]),
     "soccdpt_preprocess_fwd": (_I, [c_void_p, _I, _I, _I, _I, c_void_p, _I, _I, c_void_p, _SZ, c_void_p]),
+    "soccdpt_occupancy_mask_bytes": (_SZ, [ctypes.POINTER(_I)]),
+    "soccdpt_occupancy_points_workspace_bytes": (_SZ, [ctypes.POINTER(_I), _I]),
+    "soccdpt_grid_pack_fwd": (_I, [c_void_p, ctypes.POINTER(_I), _I, c_void_p, c_void_p]),
+    "soccdpt_occupancy_points_fwd": (_I, [c_void_p, ctypes.POINTER(_I), ctypes.POINTER(_F), _I, c_void_p, _LL, c_void_p,
+                                         c_void_p, _SZ, c_void_p]),
     "soccdpt_voxel_workspace_bytes": (_SZ, [ctypes.POINTER(Geometry), _I, _I]),
     "soccdpt_voxelize_fwd": (_I, [c_void_p, c_void_p, _I, ctypes.POINTER(Geometry), c_void_p, c_void_p, _I,
                                   c_void_p, _SZ, c_void_p]),

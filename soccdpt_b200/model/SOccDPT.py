@@ -56,7 +56,7 @@ class SOccDPT(BaseModel):
                  camera_intrinsics_yaml=DEFAULT_CALIB, point_compute_method="torch",
                  grid_size=(256, 256, 32), scale=(2.0, 2.0, 0.666), shift=(0.0, 0.0, 0.0),
                  pc_scale=(10000.0, 50000.0, 800.0), pc_shift=(55.0, -20.0, 15.0), correction_angle=(7.0, 0, 0),
-                 compute_occ=False, occupancy_mode="reference_union", **kwargs):
+                 compute_occ=False, occupancy_mode="reference_union", occupancy_output="dense", **kwargs):
         super(SOccDPT, self).__init__(**kwargs)
         self.compute_occ = compute_occ
         self.grid_size, self.scale, self.shift = grid_size, scale, shift
@@ -70,6 +70,11 @@ class SOccDPT(BaseModel):
         self.point_compute_method = point_compute_method
         assert occupancy_mode in ("reference_union", "per_frame")
         self.occupancy_mode = occupancy_mode
+        # "dense": the reference's (B,G0,G1,G2,C) fp32 grid.  "packed" (extension): the 4th output is the
+        # voxeliser's bit-packed mask instead -- int32 words, (mask_words,) or (B, mask_words) in per_frame mode; see
+        # soccdpt_b200.occupancy.packed_to_points and SOCCDPT_OCC_PACKED in include/soccdpt_b200.h
+        assert occupancy_output in ("dense", "packed")
+        self.occupancy_output = occupancy_output
 
         self.camera_intrinsics_yaml = os.path.expanduser(camera_intrinsics_yaml)
         self.cam_settings = load_calib(self.camera_intrinsics_yaml)
@@ -121,14 +126,19 @@ class SOccDPT(BaseModel):
         seg_up = torch.empty((B, C, H, Wd), dtype=torch.float32, device=dev)
         points = torch.empty((B, H, Wd, 3), dtype=torch.float32, device=dev)
         grid = None
-        if self.compute_occ:
+        packed = self.compute_occ and self.occupancy_output == "packed"
+        if self.compute_occ and not packed:
             G = self.grid_size
             grid = torch.empty((B, G[0], G[1], G[2], C), dtype=torch.float32, device=dev)
+        if packed:
+            mode |= _cabi.OCC_PACKED
         ws, need = self._workspace(geom, B, mode, dev)      # voxel mask + resize tables
         rc = lib.soccdpt_postprocess_fwd(
             _cabi.ptr(inv_depth), _cabi.ptr(segmentation), B, h, w, ctypes_byref(geom), _cabi.ptr(inv_up), _cabi.ptr(seg_up),
             _cabi.ptr(points), _cabi.ptr(grid), mode, _cabi.ptr(ws), need, _cabi.current_stream())
         _cabi.check(rc, "soccdpt_postprocess_fwd")
+        if packed:
+            grid = self._packed_mask(ws, B)
         # the reference's .squeeze() calls (SOccDPT.py:276,282-285)
         seg_out = seg_up.squeeze()
         inv_out = inv_up.squeeze()
@@ -151,14 +161,28 @@ class SOccDPT(BaseModel):
         mode = _cabi.OCC_PER_FRAME if self.occupancy_mode == "per_frame" else _cabi.OCC_REFERENCE_UNION
         points = torch.empty((B, H, Wd, 3), dtype=torch.float32, device=dev)
         grid, ws, need = None, None, 0
+        packed = self.compute_occ and self.occupancy_output == "packed"
+        if packed:
+            mode |= _cabi.OCC_PACKED
         if self.compute_occ:
             G = self.grid_size
-            grid = torch.empty((B, G[0], G[1], G[2], self.num_classes), dtype=torch.float32, device=dev)
+            if not packed:
+                grid = torch.empty((B, G[0], G[1], G[2], self.num_classes), dtype=torch.float32, device=dev)
             ws, need = self._workspace(geom, B, mode, dev)
         rc = lib.soccdpt_voxelize_fwd(_cabi.ptr(inv_depth_up), _cabi.ptr(seg), B, ctypes_byref(geom), _cabi.ptr(points),
                                       _cabi.ptr(grid), mode, _cabi.ptr(ws), need, _cabi.current_stream())
         _cabi.check(rc, "soccdpt_voxelize_fwd")
+        if packed:
+            grid = self._packed_mask(ws, B)
         return points, grid
+
+    def _packed_mask(self, ws, B):
+        """copy of the bit-packed voxel mask the call left at the start of its workspace (int32 words)."""
+        from ..occupancy import mask_words
+        n = mask_words(self.grid_size)
+        if self.occupancy_mode == "per_frame":
+            return ws[: B * n * 4].view(torch.int32).view(B, n).clone()
+        return ws[: n * 4].view(torch.int32).clone()
 
 
 def ctypes_byref(s):

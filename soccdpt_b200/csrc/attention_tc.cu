@@ -27,12 +27,14 @@ constexpr int TC_SMEM_Q = 0;              // 128 rows x 64 B, SWIZZLE_64B
 constexpr int TC_SMEM_K = 8192;           // 256 rows x 64 B, SWIZZLE_64B
 constexpr int TC_SMEM_VT = 8192 + 16384;  // 4 k-blocks x (32 rows x 128 B), SWIZZLE_128B
 constexpr int TC_SMEM_P = TC_SMEM_VT + 16384;    // 4 k-blocks x (128 rows x 128 B), SWIZZLE_128B
-constexpr int TC_SMEM_MISC = TC_SMEM_P + 65536;  // region ids 256 B | row max [2][128] f32 | row sum [2][128] f32 | barrier | slot
+constexpr int TC_SMEM_MISC = TC_SMEM_P + 65536;  // region ids 256 B | barrier | slot | row sums [2][128] f32 | bias table
 constexpr int TC_TAB = 31 * 31;                    // relative-position bias table of one head: (2*16-1)^2 entries
 constexpr int TC_TS = 48;                          // its row stride in shared memory: the 32 query rows of a warp span two window
                                                    // rows, (TC_TS - 16) % 32 == 0 puts their table reads into 32 different banks
-constexpr int TC_MISC_BYTES = 256 + 1024 + 1024 + 64 + 31 * TC_TS * 4;
+constexpr int TC_MISC_BYTES = 256 + 64 + 1024 + 31 * TC_TS * 4;
 constexpr int TC_SMEM_BYTES = TC_SMEM_MISC + TC_MISC_BYTES + 1024;
+// two CTAs per SM is what overlaps one CTA's MMA / staging phases with the other's softmax: 2 x (bytes + 1 KB reserved) <= 228 KB
+static_assert(2 * (TC_SMEM_BYTES + 1024) <= 228 * 1024, "two resident CTAs per SM");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -123,6 +125,16 @@ __device__ __forceinline__ uint4 pack8_scaled(const float *f, float s) {
     return u;
 }
 
+__device__ __forceinline__ void unpack8(const uint4 &u, float *f) {
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 t = __bfloat1622float2(h[k]);
+        f[2 * k] = t.x;
+        f[2 * k + 1] = t.y;
+    }
+}
+
 template <bool MASK>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ bias_tab, const float *__restrict__ scale,
@@ -132,28 +144,21 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
     // makes the compiler lose the address space and emit generic LD/ST for every shared-memory access
     uint8_t *smem = tc_raw + ((1024u - (smem_u32(tc_raw) & 1023u)) & 1023u);
     uint8_t *reg = smem + TC_SMEM_MISC;                                      // [256] region ids
-    float *s_max = reinterpret_cast<float *>(smem + TC_SMEM_MISC + 256);     // [2][128]
-    float *s_sum = s_max + 256;                                              // [2][128]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(s_sum + 256);
+    // row-max exchange of the fallback path [2][128] f32: aliased onto the Q tile, which is dead between the completion of the
+    // S MMA (awaited before the softmax) and the staging of the next half's Q (after the barrier that follows the softmax)
+    float *s_max = reinterpret_cast<float *>(smem + TC_SMEM_Q);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + TC_SMEM_MISC + 256);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 2);
-    float *s_tab = reinterpret_cast<float *>(bar + 8);                         // [31][TC_TS] cpb bias of this head
+    float *s_sum = reinterpret_cast<float *>(bar + 8);                         // [2][128] partial row sums
+    float *s_tab = s_sum + 256;                                                // [31][TC_TS] cpb bias of this head
 
     const int t = threadIdx.x, warp = t >> 5;
     const int row = t & 127;            // query row inside the half == TMEM lane
     const int wg = t >> 7;              // which 128 keys (and which 16 output channels) this thread owns
+    const int qrow = t >> 1, qpart = t & 1;   // Q staging: two threads per query row, 16 channels each
     const int nwx = Ws / ws, nwy = Hs / ws;
     const int win = blockIdx.x % (nwx * nwy), b = blockIdx.x / (nwx * nwy);
     const int head = blockIdx.y;
-
-    for (int i = t; i < TC_TAB; i += TC_THREADS) s_tab[(i / 31) * TC_TS + i % 31] = bias_tab[(size_t)blockIdx.y * TC_TAB + i];
-    if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
 
     // token index (in the un-shifted image) of window row r, and its shift-mask region
     auto token_of = [&](int r, int &region) -> long long {
@@ -163,16 +168,54 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
         region = MASK ? region_of(ys, Hs, ws, shift) * 3 + region_of(xs, Ws, ws, shift) : 0;
         return ((long long)b * Hs + yo) * Ws + xo;
     };
+    // normalised, scaled query row `qrow` of a half from its two 16-byte halves -> SW64 tile
+    auto stage_q = [&](const uint4 &a, const uint4 &c, float sc_) {
+        float q[16];
+        unpack8(a, q);
+        unpack8(c, q + 8);
+        float qq = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) qq = fmaf(q[d], q[d], qq);
+        qq += __shfl_xor_sync(0xffffffffu, qq, 1);
+        const float qs = sc_ / fmaxf(sqrtf(qq), 1e-12f);
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2)
+            *reinterpret_cast<uint4 *>(smem + TC_SMEM_Q + qrow * 64 + (((qpart * 2 + c2) ^ ((qrow >> 1) & 3)) << 4)) =
+                pack8_scaled(q + c2 * 8, qs);
+    };
 
-    {   // ---- stage K (normalised, SW64) and V^T (SW128): one key row per thread
+    // ---- prologue: every global load of the CTA's start-up is issued before anything waits on one of them
+    int region, dummy;
+    const long long tok_k = token_of(t, region);
+    const uint4 *kv = reinterpret_cast<const uint4 *>(qkv + tok_k * 3 * C + head * D);
+    uint4 kraw[4], vraw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) kraw[i] = kv[(C >> 3) + i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vraw[i] = kv[(C >> 2) + i];
+    const uint4 *qp0 = reinterpret_cast<const uint4 *>(qkv + token_of(qrow, dummy) * 3 * C + head * D) + qpart * 2;
+    const uint4 q0a = qp0[0], q0b = qp0[1];
+    float tabv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int e = t + i * TC_THREADS;
+        tabv[i] = e < TC_TAB ? bias_tab[(size_t)head * TC_TAB + e] : 0.f;
+    }
+    const float sc = scale[head];
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // K (normalised, SW64) and V^T (SW128): one key row per thread
         const int r = t;
-        int region;
-        const long long tok = token_of(r, region);
         reg[r] = (uint8_t)region;
-        const bf16 *base = qkv + tok * 3 * C + head * D;
-        float k[D], v[D];
-        load_head(base + C, k);
-        load_head(base + 2 * C, v);
+        float k[D];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) unpack8(kraw[i], k + i * 8);
         float kk = 0.f;
 #pragma unroll
         for (int d = 0; d < D; ++d) kk = fmaf(k[d], k[d], kk);
@@ -183,17 +226,28 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
         // V^T: element (d, key r) -> k-block r/64, row d, column r%64 (128-byte rows, Swizzle<3,4,3>)
         const int kb = r >> 6, col = r & 63;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const int off = TC_SMEM_VT + kb * 4096 + d * 128 + (((col >> 3) ^ (d & 7)) << 4) + (col & 7) * 2;
-            *reinterpret_cast<bf16 *>(smem + off) = __float2bfloat16_rn(v[d]);
+        for (int i = 0; i < 4; ++i) {
+            const bf16 *e = reinterpret_cast<const bf16 *>(&vraw[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int d = i * 8 + j;
+                const int off = TC_SMEM_VT + kb * 4096 + d * 128 + (((col >> 3) ^ (d & 7)) << 4) + (col & 7) * 2;
+                *reinterpret_cast<bf16 *>(smem + off) = e[j];
+            }
         }
     }
+    stage_q(q0a, q0b, sc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int e = t + i * TC_THREADS;
+        if (e < TC_TAB) s_tab[(e / 31) * TC_TS + e % 31] = tabv[i];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 TMEM lanes
-    const float sc = scale[head];
     const float LOG2E = 1.4426950408889634f;
     uint32_t phase = 0;
 
@@ -202,22 +256,7 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
         const int r = half * 128 + row;           // my query row inside the window
         int my_reg;
         const long long tok = token_of(r, my_reg);
-        if (wg == 0) {   // stage normalised, scaled Q of this half (row `row`)
-            float q[D];
-            load_head(qkv + tok * 3 * C + head * D, q);
-            float qq = 0.f;
-#pragma unroll
-            for (int d = 0; d < D; ++d) qq = fmaf(q[d], q[d], qq);
-            const float qs = sc / fmaxf(sqrtf(qq), 1e-12f);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4)
-                *reinterpret_cast<uint4 *>(smem + TC_SMEM_Q + row * 64 + ((c4 ^ ((row >> 1) & 3)) << 4)) = pack8_scaled(q + c4 * 8, qs);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (t == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (t == 0) {                             // Q of this half is staged and visible (barrier above / at the end of the loop)
             const uint64_t da = umma_desc(smem_u32(smem + TC_SMEM_Q), 64), db = umma_desc(smem_u32(smem + TC_SMEM_K), 64);
             const uint32_t idesc = umma_idesc(TC_N);
             umma_f16(tmem, da, db, idesc, 0u);
@@ -283,7 +322,7 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
         s_sum[wg * 128 + row] = l;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                       // all S reads done, all P rows written, partial sums visible
+        __syncthreads();                       // all S reads done, all P rows written, partial sums visible, s_max consumed
         if (t == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t idesc = umma_idesc(D);
@@ -295,6 +334,12 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
                 for (int k = 0; k < 4; ++k) umma_f16(tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(bar);
+        }
+        if (half == 0) {   // stage Q of the second half while the P V MMAs run (the Q tile is dead: S is complete)
+            const uint4 *qp1 = reinterpret_cast<const uint4 *>(qkv + token_of(128 + qrow, dummy) * 3 * C + head * D) + qpart * 2;
+            const uint4 a = qp1[0], c = qp1[1];
+            stage_q(a, c, sc);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         l += s_sum[(wg ^ 1) * 128 + row];
         mbar_wait(bar, phase);
@@ -309,12 +354,10 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
             *reinterpret_cast<uint4 *>(op + 8) = pack8_scaled(o + 8, inv);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                       // O read by everyone before the next half overwrites TMEM / Q / s_max
-    }
-    if (warp == 0) {
+        __syncthreads();                       // O and s_sum read by everyone, Q of the next half visible
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
     }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
 }
 
 }  // namespace

@@ -33,8 +33,8 @@ constexpr int TABW = 2 * WS - 1;           // 47
 constexpr int TAB = TABW * TABW;
 constexpr int TS = 56;                     // table row stride in shared memory: (TS - WS) % 32 == 0 puts the table reads of the
                                            // 32 query rows of a warp (up to three window rows) into 32 different banks
-constexpr int SM_Q = 0;                                // 128 rows x 64 B, SWIZZLE_64B
-constexpr int SM_K = 8192;                             // 576 rows x 64 B, SWIZZLE_64B
+constexpr int SM_Q = 0;                                // 2 buffers x (128 rows x 64 B), SWIZZLE_64B
+constexpr int SM_K = 16384;                            // 576 rows x 64 B, SWIZZLE_64B
 constexpr int SM_VT = SM_K + NTOK * 64;                // 9 k-blocks x (32 rows x 128 B), SWIZZLE_128B
 constexpr int SM_P = SM_VT + (NTOK / 64) * 4096;       // 2 buffers x 3 k-blocks x (128 rows x 128 B), SWIZZLE_128B
 constexpr int P_BUF = (KBLK / 64) * 16384;
@@ -156,6 +156,16 @@ __device__ __forceinline__ void add_bias(float *v, const float *tab, const uint8
     }
 }
 
+__device__ __forceinline__ void unpack8(const uint4 &u, float *f) {
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 t = __bfloat1622float2(h[k]);
+        f[2 * k] = t.x;
+        f[2 * k + 1] = t.y;
+    }
+}
+
 template <bool MASK>
 __global__ void __launch_bounds__(THREADS, 1)
 window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ bias_tab, const float *__restrict__ scale,
@@ -168,24 +178,15 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
     uint64_t *bar_s = reinterpret_cast<uint64_t *>(smem + SM_MISC + MISC_REG + MISC_RED);   // [2]
     uint64_t *bar_pv = bar_s + 2;                                                // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_pv + 2);
-    float *s_tab = reinterpret_cast<float *>(smem + SM_MISC + MISC_REG + MISC_RED + MISC_BAR);   // [47*47] cpb bias of this head
+    float *s_tab = reinterpret_cast<float *>(smem + SM_MISC + MISC_REG + MISC_RED + MISC_BAR);   // [47][TS] cpb bias of this head
 
     const int t = threadIdx.x, warp = t >> 5;
     const int row = t & 127;            // query row inside the tile == TMEM lane
     const int quarter = t >> 7;         // which 48 keys of a block (and which 8 output channels) this thread owns
+    const int qrow = t >> 2, qpart = t & 3;   // Q staging: four threads per query row, 8 channels each
     const int nwx = Ws / WS, nwy = Hs / WS;
     const int win = blockIdx.x % (nwx * nwy), b = blockIdx.x / (nwx * nwy);
     const int head = blockIdx.y;
-
-    for (int i = t; i < TAB; i += THREADS) s_tab[(i / TABW) * TS + i % TABW] = bias_tab[(size_t)head * TAB + i];
-    if (t == 0) {
-        mbar_init(&bar_s[0]); mbar_init(&bar_s[1]); mbar_init(&bar_pv[0]); mbar_init(&bar_pv[1]);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
 
     // token index (in the un-shifted image) of window row r, and its shift-mask region
     auto token_of = [&](int r, int &region) -> long long {
@@ -195,16 +196,29 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
         region = MASK ? region_of(ys, Hs, WS, shift) * 3 + region_of(xs, Ws, WS, shift) : 0;
         return ((long long)b * Hs + yo) * Ws + xo;
     };
-
-    // ---- stage K (normalised, SW64) and V^T (SW128) of the whole window: one key row per thread
-    for (int r = t; r < NTOK; r += THREADS) {
-        int region;
-        const long long tok = token_of(r, region);
+    // the 16 bytes of query row qt*128 + qrow this thread stages (rows past the end of the window repeat the last one)
+    auto q_ptr = [&](int qt) -> const uint4 * {
+        int dummy;
+        return reinterpret_cast<const uint4 *>(qkv + token_of(min(qt * 128 + qrow, NTOK - 1), dummy) * 3 * C + head * D) + qpart;
+    };
+    // normalised, scaled query row -> SW64 tile `buf`
+    auto stage_q = [&](const uint4 &raw, float sc_, int buf) {
+        float q[8];
+        unpack8(raw, q);
+        float qq = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) qq = fmaf(q[d], q[d], qq);
+        qq += __shfl_xor_sync(0xffffffffu, qq, 1);
+        qq += __shfl_xor_sync(0xffffffffu, qq, 2);
+        const float qs = sc_ / fmaxf(sqrtf(qq), 1e-12f);
+        *reinterpret_cast<uint4 *>(smem + SM_Q + buf * 8192 + qrow * 64 + ((qpart ^ ((qrow >> 1) & 3)) << 4)) = pack8_scaled(q, qs);
+    };
+    // K (normalised, SW64) and V^T (SW128) of key row r
+    auto stage_kv = [&](int r, int region, const uint4 (&kraw)[4], const uint4 (&vraw)[4]) {
         reg[r] = (uint8_t)region;
-        const bf16 *base = qkv + tok * 3 * C + head * D;
-        float k[D], v[D];
-        load_head(base + C, k);
-        load_head(base + 2 * C, v);
+        float k[D];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) unpack8(kraw[i], k + i * 8);
         float kk = 0.f;
 #pragma unroll
         for (int d = 0; d < D; ++d) kk = fmaf(k[d], k[d], kk);
@@ -215,24 +229,60 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
         // V^T: element (d, key r) -> k-block r/64, row d, column r%64 (128-byte rows, Swizzle<3,4,3>)
         const int kb = r >> 6, col = r & 63;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const int off = SM_VT + kb * 4096 + d * 128 + (((col >> 3) ^ (d & 7)) << 4) + (col & 7) * 2;
-            *reinterpret_cast<bf16 *>(smem + off) = __float2bfloat16_rn(v[d]);
+        for (int i = 0; i < 4; ++i) {
+            const bf16 *e = reinterpret_cast<const bf16 *>(&vraw[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int d = i * 8 + j;
+                *reinterpret_cast<bf16 *>(smem + SM_VT + kb * 4096 + d * 128 + (((col >> 3) ^ (d & 7)) << 4) + (col & 7) * 2) = e[j];
+            }
         }
+    };
+
+    // ---- prologue: every global load of the CTA's start-up is issued before anything waits on one of them
+    int region_a, region_b = 0;
+    const long long tok_a = token_of(t, region_a);
+    const uint4 *kva = reinterpret_cast<const uint4 *>(qkv + tok_a * 3 * C + head * D);
+    uint4 kra[4], vra[4], krb[4], vrb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) kra[i] = kva[(C >> 3) + i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vra[i] = kva[(C >> 2) + i];
+    const bool second = t < NTOK - THREADS;          // threads 0..63 also stage key rows 512..575
+    if (second) {
+        const uint4 *kvb = reinterpret_cast<const uint4 *>(qkv + token_of(THREADS + t, region_b) * 3 * C + head * D);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) krb[i] = kvb[(C >> 3) + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) vrb[i] = kvb[(C >> 2) + i];
     }
+    uint4 qraw = *q_ptr(0);
+    const float sc = scale[head];
+    for (int i = t; i < TAB; i += THREADS) s_tab[(i / TABW) * TS + i % TABW] = bias_tab[(size_t)head * TAB + i];
+    if (t == 0) {
+        mbar_init(&bar_s[0]); mbar_init(&bar_s[1]); mbar_init(&bar_pv[0]); mbar_init(&bar_pv[1]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    stage_kv(t, region_a, kra, vra);
+    if (second) stage_kv(THREADS + t, region_b, krb, vrb);
+    stage_q(qraw, sc, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 TMEM lanes
-    const float sc = scale[head];
     const float LOG2E = 1.4426950408889634f;
     const bool one_pass = 2.01f * sc + 16.0f < 80.0f;                    // see the header comment
     const uint32_t idesc_s = umma_idesc(KBLK), idesc_o = umma_idesc(D);
-    const uint64_t dq = umma_desc(smem_u32(smem + SM_Q), 64);
     uint32_t ph_s0 = 0, ph_s1 = 0, ph_pv0 = 0;
 
-    auto issue_s = [&](int j) {     // S_j = Qn Kn_j^T into buffer j & 1 (thread 0 only)
+    auto issue_s = [&](int j, int qbuf) {     // S_j = Qn Kn_j^T into buffer j & 1 (thread 0 only)
+        const uint64_t dq = umma_desc(smem_u32(smem + SM_Q + qbuf * 8192), 64);
         const uint64_t dk = umma_desc(smem_u32(smem + SM_K + j * (KBLK * 64)), 64);
         umma_f16(tmem + (uint32_t)((j & 1) * KBLK), dq, dk, idesc_s, 0u);
         umma_f16(tmem + (uint32_t)((j & 1) * KBLK), dq + 2, dk + 2, idesc_s, 1u);      // second K step: +32 bytes
@@ -242,6 +292,10 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
         if (j & 1) { mbar_wait(&bar_s[1], ph_s1); ph_s1 ^= 1; } else { mbar_wait(&bar_s[0], ph_s0); ph_s0 ^= 1; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     };
+    if (t == 0) {
+        issue_s(0, 0);
+        issue_s(1, 0);
+    }
 
 #pragma unroll 1
     for (int qt = 0; qt < QT; ++qt) {
@@ -250,25 +304,9 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
         const bool active = qt * 128 + (warp & 3) * 32 < NTOK;   // warp-uniform: any valid row in this warp's 32 lanes
         int my_reg;
         const long long tok = token_of(r, my_reg);
-        if (quarter == 0) {   // stage normalised, scaled Q of this tile (row `row`)
-            float q[D];
-            load_head(qkv + tok * 3 * C + head * D, q);
-            float qq = 0.f;
-#pragma unroll
-            for (int d = 0; d < D; ++d) qq = fmaf(q[d], q[d], qq);
-            const float qs = sc / fmaxf(sqrtf(qq), 1e-12f);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4)
-                *reinterpret_cast<uint4 *>(smem + SM_Q + row * 64 + ((c4 ^ ((row >> 1) & 3)) << 4)) = pack8_scaled(q + c4 * 8, qs);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (t == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue_s(0);
-            issue_s(1);
-        }
+        // the next tile's query rows: loaded now, staged after the first key block (S_0 / S_1 of this tile were issued at the end
+        // of the previous one, so nothing at a tile boundary waits for global memory)
+        if (qt + 1 < QT) qraw = *q_ptr(qt + 1);
         // cpb bias[i][j] = table[(qy - ky + 23) * 47 + (qx - kx + 23)]: query part in a register, the key part is a per-block
         // constant (8 window rows per block, 2 per quarter) plus a compile-time offset
         const float *tab_q = s_tab + (r / WS + WS - 1) * TS + (r % WS) + WS - 1 - quarter * 2 * TS;
@@ -299,7 +337,7 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                 __syncthreads();                                   // buffer j & 1 has been read by everybody
                 if (t == 0 && j + 2 < NBLK) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    issue_s(j + 2);
+                    issue_s(j + 2, qt & 1);
                 }
             }
             s_red[quarter * 128 + row] = m;
@@ -310,13 +348,13 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
             __syncthreads();                                       // maxima consumed before s_red carries the sums
             if (t == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                issue_s(0);
-                issue_s(1);
+                issue_s(0, qt & 1);
+                issue_s(1, qt & 1);
             }
         }
 
         // ---- P_j = exp(logit - reference), O += P_j V_j
-        float l = 0.f;
+        float l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
         for (int j = 0; j < NBLK; ++j) {
             wait_s(j);
@@ -333,9 +371,11 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                 tmem_ld32(col, v);
                 add_bias<MASK, 0, 32>(v, tab, rg, my_reg);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 32; i += 2) {
                     v[i] = fast_exp2(fmaf(v[i], LOG2E, -ml));
-                    l += v[i];
+                    v[i + 1] = fast_exp2(fmaf(v[i + 1], LOG2E, -ml));
+                    l0 += v[i];
+                    l1 += v[i + 1];
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -346,9 +386,11 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                 tmem_ld16(col + 32, v);
                 add_bias<MASK, 32, 16>(v, tab, rg, my_reg);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 16; i += 2) {
                     v[i] = fast_exp2(fmaf(v[i], LOG2E, -ml));
-                    l += v[i];
+                    v[i + 1] = fast_exp2(fmaf(v[i + 1], LOG2E, -ml));
+                    l0 += v[i];
+                    l1 += v[i + 1];
                 }
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
@@ -357,6 +399,7 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                         pack8_scaled(v + g * 8, 1.0f);
                 }
             }
+            if (j == 0 && qt + 1 < QT) stage_q(qraw, sc, (qt + 1) & 1);   // that buffer's last readers (tile qt - 1) are long done
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();                                       // S_j read, P_j written by everybody
@@ -370,12 +413,17 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                     for (int k = 0; k < 4; ++k) umma_f16(tmem + TM_O, dp + 2 * k, dv + 2 * k, idesc_o, (j | kb2 | k) != 0 ? 1u : 0u);
                 }
                 umma_commit(&bar_pv[j & 1]);
-                if (j + 2 < NBLK) issue_s(j + 2);
+                if (j + 2 < NBLK) {
+                    issue_s(j + 2, qt & 1);
+                } else if (j == NBLK - 1 && qt + 1 < QT) {         // both S buffers are free: start the next tile's scores now
+                    issue_s(0, (qt + 1) & 1);
+                    issue_s(1, (qt + 1) & 1);
+                }
             }
         }
-        s_red[quarter * 128 + row] = l;
+        s_red[quarter * 128 + row] = l0 + l1;
         __syncthreads();
-        l = (s_red[row] + s_red[128 + row]) + (s_red[256 + row] + s_red[384 + row]);
+        const float l = (s_red[row] + s_red[128 + row]) + (s_red[256 + row] + s_red[384 + row]);
         mbar_wait(&bar_pv[0], ph_pv0);                             // P_2 V_2 (committed last: everything before it is done too)
         ph_pv0 ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -384,9 +432,11 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
             tmem_ld8(t_row + (uint32_t)(TM_O + quarter * 8), o);
             if (valid) *reinterpret_cast<uint4 *>(out + tok * C + head * D + quarter * 8) = pack8_scaled(o, 1.0f / l);
         }
+        // no barrier here: O is overwritten by P_0 V_0 of the next tile, issued after that tile's first block barrier, and s_red is
+        // rewritten three (one_pass) barriers later -- every thread has passed this point by then
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                       // O / s_red read by everyone before the next tile overwrites TMEM / Q / s_red
     }
+    __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");

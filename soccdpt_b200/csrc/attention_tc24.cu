@@ -24,7 +24,8 @@ using bf16 = __nv_bfloat16;
 constexpr int D = 32;                      // head dim
 constexpr int WS = 24;                     // window side
 constexpr int NTOK = WS * WS;              // 576 tokens per window
-constexpr int THREADS = 512;
+constexpr int THREADS = 512;                // softmax threads (16 warps); warp 16 only issues the MMAs
+constexpr int CTA_THREADS = THREADS + 32;
 constexpr int KBLK = 192;                  // keys per block = 8 window rows
 constexpr int NBLK = NTOK / KBLK;          // 3
 constexpr int QT = (NTOK + 127) / 128;     // 5 query tiles (the last one holds 64 rows)
@@ -36,14 +37,14 @@ constexpr int TS = 56;                     // table row stride in shared memory:
 constexpr int SM_Q = 0;                                // 2 buffers x (128 rows x 64 B), SWIZZLE_64B
 constexpr int SM_K = 16384;                            // 576 rows x 64 B, SWIZZLE_64B
 constexpr int SM_VT = SM_K + NTOK * 64;                // 9 k-blocks x (32 rows x 128 B), SWIZZLE_128B
-constexpr int SM_P = SM_VT + (NTOK / 64) * 4096;       // 2 buffers x 3 k-blocks x (128 rows x 128 B), SWIZZLE_128B
-constexpr int P_BUF = (KBLK / 64) * 16384;
-constexpr int SM_MISC = SM_P + 2 * P_BUF;              // region ids | partial sums / maxima [4][128] | barriers | slot | table
+constexpr int SM_MISC = SM_VT + (NTOK / 64) * 4096;    // region ids | partial sums / maxima [4][128] | barriers | slot | table
 constexpr int MISC_REG = 640, MISC_RED = 4 * 128 * 4, MISC_BAR = 64;
 constexpr int SMEM_BYTES = SM_MISC + MISC_REG + MISC_RED + MISC_BAR + TABW * TS * 4 + 1024;
-constexpr int TM_O = 2 * KBLK;             // TMEM column of O
+constexpr int TM_O = 2 * KBLK;             // TMEM column of O (32 columns)
+constexpr int TM_P = TM_O + D;             // TMEM columns of P: 128 lanes x KBLK keys as bf16 pairs = KBLK / 2 columns
+static_assert(TM_P + KBLK / 2 <= 512, "TMEM budget");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(SM_K % 1024 == 0 && SM_VT % 1024 == 0 && SM_P % 1024 == 0 && (KBLK * 64) % 512 == 0, "swizzle atom alignment");
+static_assert(SM_K % 1024 == 0 && SM_VT % 1024 == 0 && (KBLK * 64) % 512 == 0, "swizzle atom alignment");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar))); }
@@ -54,6 +55,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
+__device__ __forceinline__ void mbar_init_n(uint64_t *bar, int n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(n)); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void softmax_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 softmax warps only
 // shared-memory matrix descriptor, K-major; swizzle_bytes in {64, 128}; 8-row groups are 8*swizzle_bytes apart
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, int swizzle_bytes) {
     uint64_t d = 0;
@@ -108,6 +114,22 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
         : "r"(taddr) : "memory");
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 columns, each 32-bit column holding two consecutive K elements (bf16)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+                 ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -167,7 +189,7 @@ __device__ __forceinline__ void unpack8(const uint4 &u, float *f) {
 }
 
 template <bool MASK>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(CTA_THREADS, 1)   // 17 warps: one SM sub-partition hosts 5 of them -> 96 registers per thread
 window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ bias_tab, const float *__restrict__ scale,
                              bf16 *__restrict__ out, int Hs, int Ws, int C, int shift) {
     extern __shared__ uint8_t tc24_raw[];
@@ -177,7 +199,8 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
     float *s_red = reinterpret_cast<float *>(smem + SM_MISC + MISC_REG);          // [4][128]
     uint64_t *bar_s = reinterpret_cast<uint64_t *>(smem + SM_MISC + MISC_REG + MISC_RED);   // [2]
     uint64_t *bar_pv = bar_s + 2;                                                // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_pv + 2);
+    uint64_t *bar_p = bar_pv + 2;                                                // [2] softmax warps -> issuer
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_p + 2);
     float *s_tab = reinterpret_cast<float *>(smem + SM_MISC + MISC_REG + MISC_RED + MISC_BAR);   // [47][TS] cpb bias of this head
 
     const int t = threadIdx.x, warp = t >> 5;
@@ -240,37 +263,42 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
     };
 
     // ---- prologue: every global load of the CTA's start-up is issued before anything waits on one of them
-    int region_a, region_b = 0;
-    const long long tok_a = token_of(t, region_a);
-    const uint4 *kva = reinterpret_cast<const uint4 *>(qkv + tok_a * 3 * C + head * D);
-    uint4 kra[4], vra[4], krb[4], vrb[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) kra[i] = kva[(C >> 3) + i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) vra[i] = kva[(C >> 2) + i];
-    const bool second = t < NTOK - THREADS;          // threads 0..63 also stage key rows 512..575
-    if (second) {
-        const uint4 *kvb = reinterpret_cast<const uint4 *>(qkv + token_of(THREADS + t, region_b) * 3 * C + head * D);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) krb[i] = kvb[(C >> 3) + i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) vrb[i] = kvb[(C >> 2) + i];
-    }
-    uint4 qraw = *q_ptr(0);
+    const bool softmax_warp = warp < THREADS / 32;
     const float sc = scale[head];
-    for (int i = t; i < TAB; i += THREADS) s_tab[(i / TABW) * TS + i % TABW] = bias_tab[(size_t)head * TAB + i];
-    if (t == 0) {
-        mbar_init(&bar_s[0]); mbar_init(&bar_s[1]); mbar_init(&bar_pv[0]); mbar_init(&bar_pv[1]);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
+    uint4 qraw = make_uint4(0, 0, 0, 0);
+    if (softmax_warp) {
+        int region_a, region_b = 0;
+        const long long tok_a = token_of(t, region_a);
+        const uint4 *kva = reinterpret_cast<const uint4 *>(qkv + tok_a * 3 * C + head * D);
+        uint4 kra[4], vra[4], krb[4], vrb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) kra[i] = kva[(C >> 3) + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) vra[i] = kva[(C >> 2) + i];
+        const bool second = t < NTOK - THREADS;          // threads 0..63 also stage key rows 512..575
+        if (second) {
+            const uint4 *kvb = reinterpret_cast<const uint4 *>(qkv + token_of(THREADS + t, region_b) * 3 * C + head * D);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) krb[i] = kvb[(C >> 3) + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) vrb[i] = kvb[(C >> 2) + i];
+        }
+        qraw = *q_ptr(0);
+        for (int i = t; i < TAB; i += THREADS) s_tab[(i / TABW) * TS + i % TABW] = bias_tab[(size_t)head * TAB + i];
+        stage_kv(t, region_a, kra, vra);
+        if (second) stage_kv(THREADS + t, region_b, krb, vrb);
+        stage_q(qraw, sc, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core
+    } else {
+        if (t == THREADS) {
+            mbar_init(&bar_s[0]); mbar_init(&bar_s[1]); mbar_init(bar_pv);
+            mbar_init_n(&bar_p[0], THREADS / 32); mbar_init_n(&bar_p[1], THREADS / 32);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    stage_kv(t, region_a, kra, vra);
-    if (second) stage_kv(THREADS + t, region_b, krb, vrb);
-    stage_q(qraw, sc, 0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -279,46 +307,125 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
     const float LOG2E = 1.4426950408889634f;
     const bool one_pass = 2.01f * sc + 16.0f < 80.0f;                    // see the header comment
     const uint32_t idesc_s = umma_idesc(KBLK), idesc_o = umma_idesc(D);
-    uint32_t ph_s0 = 0, ph_s1 = 0, ph_pv0 = 0;
+    // hand-off softmax warps -> issuer: step s (one key block of one pass) completes phase (s >> 1) of bar_p[s & 1]
+    int step = 0;
 
-    auto issue_s = [&](int j, int qbuf) {     // S_j = Qn Kn_j^T into buffer j & 1 (thread 0 only)
-        const uint64_t dq = umma_desc(smem_u32(smem + SM_Q + qbuf * 8192), 64);
-        const uint64_t dk = umma_desc(smem_u32(smem + SM_K + j * (KBLK * 64)), 64);
-        umma_f16(tmem + (uint32_t)((j & 1) * KBLK), dq, dk, idesc_s, 0u);
-        umma_f16(tmem + (uint32_t)((j & 1) * KBLK), dq + 2, dk + 2, idesc_s, 1u);      // second K step: +32 bytes
-        umma_commit(&bar_s[j & 1]);
-    };
-    auto wait_s = [&](int j) {
-        if (j & 1) { mbar_wait(&bar_s[1], ph_s1); ph_s1 ^= 1; } else { mbar_wait(&bar_s[0], ph_s0); ph_s0 ^= 1; }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    };
-    if (t == 0) {
-        issue_s(0, 0);
-        issue_s(1, 0);
-    }
-
+    if (!softmax_warp) {
+        // ================================ MMA issuer: one thread, never touches the data ================================
+        if (t == THREADS) {
+            auto issue_s = [&](int j, int qbuf) {     // S_j = Qn Kn_j^T into buffer j & 1
+                const uint64_t dq = umma_desc(smem_u32(smem + SM_Q + qbuf * 8192), 64);
+                const uint64_t dk = umma_desc(smem_u32(smem + SM_K + j * (KBLK * 64)), 64);
+                umma_f16(tmem + (uint32_t)((j & 1) * KBLK), dq, dk, idesc_s, 0u);
+                umma_f16(tmem + (uint32_t)((j & 1) * KBLK), dq + 2, dk + 2, idesc_s, 1u);      // second K step: +32 bytes
+                umma_commit(&bar_s[j & 1]);
+            };
+            auto wait_step = [&]() {                  // every softmax warp has finished this step's reads of S (and writes of P)
+                mbar_wait(&bar_p[step & 1], (uint32_t)((step >> 1) & 1));
+                ++step;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            };
+            issue_s(0, 0);
+            issue_s(1, 0);
 #pragma unroll 1
-    for (int qt = 0; qt < QT; ++qt) {
-        const int r = min(qt * 128 + row, NTOK - 1);      // my query row inside the window (rows past the end repeat the last)
-        const bool valid = qt * 128 + row < NTOK;
-        const bool active = qt * 128 + (warp & 3) * 32 < NTOK;   // warp-uniform: any valid row in this warp's 32 lanes
-        int my_reg;
-        const long long tok = token_of(r, my_reg);
-        // the next tile's query rows: loaded now, staged after the first key block (S_0 / S_1 of this tile were issued at the end
-        // of the previous one, so nothing at a tile boundary waits for global memory)
-        if (qt + 1 < QT) qraw = *q_ptr(qt + 1);
-        // cpb bias[i][j] = table[(qy - ky + 23) * 47 + (qx - kx + 23)]: query part in a register, the key part is a per-block
-        // constant (8 window rows per block, 2 per quarter) plus a compile-time offset
-        const float *tab_q = s_tab + (r / WS + WS - 1) * TS + (r % WS) + WS - 1 - quarter * 2 * TS;
-        const uint8_t *reg_q = reg + quarter * KQ;
-        float ml = (1.01f * sc + 16.0f) * LOG2E;
+            for (int qt = 0; qt < QT; ++qt) {
+                if (!one_pass) {                      // row-max pass: scores are only read; then they are issued again
+#pragma unroll 1
+                    for (int j = 0; j < NBLK; ++j) {
+                        wait_step();
+                        if (j + 2 < NBLK) issue_s(j + 2, qt & 1);
+                    }
+                    issue_s(0, qt & 1);
+                    issue_s(1, qt & 1);
+                }
+#pragma unroll 1
+                for (int j = 0; j < NBLK; ++j) {
+                    wait_step();
+#pragma unroll
+                    for (int kb2 = 0; kb2 < KBLK / 64; ++kb2) {
+                        const uint64_t dv = umma_desc(smem_u32(smem + SM_VT + (j * (KBLK / 64) + kb2) * 4096), 128);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)       // A = P straight from TMEM: 8 columns per K = 16 step
+                            umma_f16_ts(tmem + TM_O, tmem + (uint32_t)(TM_P + (kb2 * 4 + k) * 8), dv + 2 * k, idesc_o,
+                                        (j | kb2 | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(bar_pv);
+                    if (j + 2 < NBLK) {
+                        issue_s(j + 2, qt & 1);
+                    } else if (j == NBLK - 1 && qt + 1 < QT) {   // both S buffers are free: start the next tile's scores now
+                        issue_s(0, (qt + 1) & 1);
+                        issue_s(1, (qt + 1) & 1);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ softmax warps ================================
+        uint32_t ph_s0 = 0, ph_s1 = 0;
+        int n_pv = 0;                                 // P V products issued so far == completions of bar_pv to expect
+        auto wait_s = [&](int j) {
+            if (j & 1) { mbar_wait(&bar_s[1], ph_s1); ph_s1 ^= 1; } else { mbar_wait(&bar_s[0], ph_s0); ph_s0 ^= 1; }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        };
+        auto step_done = [&]() {                      // my reads of S_j (and writes of P_j / Q) are complete -> issuer
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if ((t & 31) == 0) mbar_arrive(&bar_p[step & 1]);
+            ++step;
+        };
+#pragma unroll 1
+        for (int qt = 0; qt < QT; ++qt) {
+            const int r = min(qt * 128 + row, NTOK - 1);      // my query row inside the window (rows past the end repeat the last)
+            const bool valid = qt * 128 + row < NTOK;
+            const bool active = qt * 128 + (warp & 3) * 32 < NTOK;   // warp-uniform: any valid row in this warp's 32 lanes
+            int my_reg;
+            const long long tok = token_of(r, my_reg);
+            // the next tile's query rows: loaded now, staged after the first key block (S_0 / S_1 of this tile were issued at the
+            // end of the previous one, so nothing at a tile boundary waits for global memory)
+            if (qt + 1 < QT) qraw = *q_ptr(qt + 1);
+            // cpb bias[i][j] = table[(qy - ky + 23) * 47 + (qx - kx + 23)]: query part in a register, the key part is a per-block
+            // constant (8 window rows per block, 2 per quarter) plus a compile-time offset
+            const float *tab_q = s_tab + (r / WS + WS - 1) * TS + (r % WS) + WS - 1 - quarter * 2 * TS;
+            const uint8_t *reg_q = reg + quarter * KQ;
+            float ml = (1.01f * sc + 16.0f) * LOG2E;
 
-        if (!one_pass) {
-            // ---- exact row maximum first (scores are read, never stored; the score MMAs are re-issued below)
-            float m = -INFINITY;
+            if (!one_pass) {
+                // ---- exact row maximum first (scores are read, never stored; the issuer re-issues the score MMAs)
+                float m = -INFINITY;
+#pragma unroll 1
+                for (int j = 0; j < NBLK; ++j) {
+                    wait_s(j);
+                    if (active) {
+                        const float *tab = tab_q - j * 8 * TS;
+                        const uint8_t *rg = reg_q + j * KBLK;
+                        const uint32_t col = t_row + (uint32_t)((j & 1) * KBLK + quarter * KQ);
+                        float v[32];
+                        tmem_ld32(col, v);
+                        add_bias<MASK, 0, 32>(v, tab, rg, my_reg);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) m = fmaxf(m, v[i]);
+                        tmem_ld16(col + 32, v);
+                        add_bias<MASK, 32, 16>(v, tab, rg, my_reg);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) m = fmaxf(m, v[i]);
+                    }
+                    step_done();
+                }
+                s_red[quarter * 128 + row] = m;
+                softmax_sync();
+                m = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
+                ml = m * LOG2E;
+                softmax_sync();                                        // maxima consumed before s_red carries the sums
+            }
+
+            // ---- P_j = exp(logit - reference); the issuer accumulates O += P_j V_j
+            float l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
             for (int j = 0; j < NBLK; ++j) {
                 wait_s(j);
+                uint32_t pk[KQ / 2];                                   // my 48 probabilities as bf16 pairs (key 2c in the low half)
                 if (active) {
                     const float *tab = tab_q - j * 8 * TS;
                     const uint8_t *rg = reg_q + j * KBLK;
@@ -327,117 +434,52 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                     tmem_ld32(col, v);
                     add_bias<MASK, 0, 32>(v, tab, rg, my_reg);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) m = fmaxf(m, v[i]);
+                    for (int i = 0; i < 32; i += 2) {
+                        v[i] = fast_exp2(fmaf(v[i], LOG2E, -ml));
+                        v[i + 1] = fast_exp2(fmaf(v[i + 1], LOG2E, -ml));
+                        l0 += v[i];
+                        l1 += v[i + 1];
+                        pk[i >> 1] = pack_bf16x2(v[i], v[i + 1]);
+                    }
                     tmem_ld16(col + 32, v);
                     add_bias<MASK, 32, 16>(v, tab, rg, my_reg);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) m = fmaxf(m, v[i]);
+                    for (int i = 0; i < 16; i += 2) {
+                        v[i] = fast_exp2(fmaf(v[i], LOG2E, -ml));
+                        v[i + 1] = fast_exp2(fmaf(v[i + 1], LOG2E, -ml));
+                        l0 += v[i];
+                        l1 += v[i + 1];
+                        pk[16 + (i >> 1)] = pack_bf16x2(v[i], v[i + 1]);
+                    }
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncthreads();                                   // buffer j & 1 has been read by everybody
-                if (t == 0 && j + 2 < NBLK) {
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    issue_s(j + 2, qt & 1);
+                if (n_pv > 0) mbar_wait(bar_pv, (uint32_t)((n_pv - 1) & 1));   // the P columns are free once the previous P V is done
+                if (active) {
+                    const uint32_t pcol = t_row + (uint32_t)(TM_P + quarter * (KQ / 2));
+                    tmem_st16(pcol, pk);
+                    tmem_st8(pcol + 16, pk + 16);
+                    tmem_st_wait();
                 }
+                ++n_pv;
+                if (j == 0 && qt + 1 < QT) stage_q(qraw, sc, (qt + 1) & 1);   // that buffer's last readers (tile qt - 1) are long done
+                step_done();
             }
-            s_red[quarter * 128 + row] = m;
-            __syncthreads();
-            m = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
-            ml = m * LOG2E;
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();                                       // maxima consumed before s_red carries the sums
-            if (t == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                issue_s(0, qt & 1);
-                issue_s(1, qt & 1);
+            s_red[quarter * 128 + row] = l0 + l1;
+            softmax_sync();
+            const float l = (s_red[row] + s_red[128 + row]) + (s_red[256 + row] + s_red[384 + row]);
+            mbar_wait(bar_pv, (uint32_t)((n_pv - 1) & 1));             // the tile's last P V (everything before it is done too)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (active) {   // ---- epilogue: my 8 output channels: O / l -> bf16 -> out[token, head*32 + quarter*8 ...]
+                float o[8];
+                tmem_ld8(t_row + (uint32_t)(TM_O + quarter * 8), o);
+                if (valid) *reinterpret_cast<uint4 *>(out + tok * C + head * D + quarter * 8) = pack8_scaled(o, 1.0f / l);
             }
+            // no barrier here: O is overwritten by P_0 V_0 of the next tile, which the issuer starts only after every warp's next
+            // step_done(); s_red is rewritten three hand-offs later, and each hand-off needs every warp to have passed this point
         }
-
-        // ---- P_j = exp(logit - reference), O += P_j V_j
-        float l0 = 0.f, l1 = 0.f;
-#pragma unroll 1
-        for (int j = 0; j < NBLK; ++j) {
-            wait_s(j);
-            if (j == 2) {                                          // P buffer 0 is free once P_0 V_0 has completed
-                mbar_wait(&bar_pv[0], ph_pv0);
-                ph_pv0 ^= 1;
-            }
-            if (active) {
-                const float *tab = tab_q - j * 8 * TS;
-                const uint8_t *rg = reg_q + j * KBLK;
-                const uint32_t col = t_row + (uint32_t)((j & 1) * KBLK + quarter * KQ);
-                uint8_t *pbase = smem + SM_P + (j & 1) * P_BUF + (row >> 3) * 1024 + (row & 7) * 128;
-                float v[32];
-                tmem_ld32(col, v);
-                add_bias<MASK, 0, 32>(v, tab, rg, my_reg);
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    v[i] = fast_exp2(fmaf(v[i], LOG2E, -ml));
-                    v[i + 1] = fast_exp2(fmaf(v[i + 1], LOG2E, -ml));
-                    l0 += v[i];
-                    l1 += v[i + 1];
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int kk = quarter * KQ + g * 8;           // key inside the block -> k-block kk/64, 16-byte chunk (kk%64)/8
-                    *reinterpret_cast<uint4 *>(pbase + (kk >> 6) * 16384 + ((((kk & 63) >> 3) ^ (row & 7)) << 4)) =
-                        pack8_scaled(v + g * 8, 1.0f);
-                }
-                tmem_ld16(col + 32, v);
-                add_bias<MASK, 32, 16>(v, tab, rg, my_reg);
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    v[i] = fast_exp2(fmaf(v[i], LOG2E, -ml));
-                    v[i + 1] = fast_exp2(fmaf(v[i + 1], LOG2E, -ml));
-                    l0 += v[i];
-                    l1 += v[i + 1];
-                }
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int kk = quarter * KQ + 32 + g * 8;
-                    *reinterpret_cast<uint4 *>(pbase + (kk >> 6) * 16384 + ((((kk & 63) >> 3) ^ (row & 7)) << 4)) =
-                        pack8_scaled(v + g * 8, 1.0f);
-                }
-            }
-            if (j == 0 && qt + 1 < QT) stage_q(qraw, sc, (qt + 1) & 1);   // that buffer's last readers (tile qt - 1) are long done
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();                                       // S_j read, P_j written by everybody
-            if (t == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int kb2 = 0; kb2 < KBLK / 64; ++kb2) {
-                    const uint64_t dp = umma_desc(smem_u32(smem + SM_P + (j & 1) * P_BUF + kb2 * 16384), 128);
-                    const uint64_t dv = umma_desc(smem_u32(smem + SM_VT + (j * (KBLK / 64) + kb2) * 4096), 128);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem + TM_O, dp + 2 * k, dv + 2 * k, idesc_o, (j | kb2 | k) != 0 ? 1u : 0u);
-                }
-                umma_commit(&bar_pv[j & 1]);
-                if (j + 2 < NBLK) {
-                    issue_s(j + 2, qt & 1);
-                } else if (j == NBLK - 1 && qt + 1 < QT) {         // both S buffers are free: start the next tile's scores now
-                    issue_s(0, (qt + 1) & 1);
-                    issue_s(1, (qt + 1) & 1);
-                }
-            }
-        }
-        s_red[quarter * 128 + row] = l0 + l1;
-        __syncthreads();
-        const float l = (s_red[row] + s_red[128 + row]) + (s_red[256 + row] + s_red[384 + row]);
-        mbar_wait(&bar_pv[0], ph_pv0);                             // P_2 V_2 (committed last: everything before it is done too)
-        ph_pv0 ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (active) {   // ---- epilogue: my 8 output channels: O / l -> bf16 -> out[token, head*32 + quarter*8 ...]
-            float o[8];
-            tmem_ld8(t_row + (uint32_t)(TM_O + quarter * 8), o);
-            if (valid) *reinterpret_cast<uint4 *>(out + tok * C + head * D + quarter * 8) = pack8_scaled(o, 1.0f / l);
-        }
-        // no barrier here: O is overwritten by P_0 V_0 of the next tile, issued after that tile's first block barrier, and s_red is
-        // rewritten three (one_pass) barriers later -- every thread has passed this point by then
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
+    if (warp == THREADS / 32) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
@@ -457,10 +499,10 @@ int launch_window_attention_tc24(const void *qkv, const float *bias_tab, const f
     }
     dim3 grid((unsigned)(batch * (Hs / WS) * (Ws / WS)), (unsigned)heads);
     if (shift > 0)
-        window_attention_tc24_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(
+        window_attention_tc24_kernel<true><<<grid, CTA_THREADS, SMEM_BYTES, st>>>(
             static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, shift);
     else
-        window_attention_tc24_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(
+        window_attention_tc24_kernel<false><<<grid, CTA_THREADS, SMEM_BYTES, st>>>(
             static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, shift);
     return check_launch("window_attention_tc24_kernel");
 }

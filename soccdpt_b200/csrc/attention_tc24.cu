@@ -2,20 +2,27 @@
 // swinv2_base_window12to24_192to384, > 99 % of the attention FLOPs of dpt_swin2_base_384).  timm 0.6.12
 // WindowAttention + SwinTransformerBlock._attn (window partition, cyclic shift, reverse) in one kernel.
 //
-//   one CTA (512 threads) per (window, head).  K (L2-normalised) and V^T of the whole window are staged ONCE in shared
-//   memory (72 KB) and serve all five 128-query tiles; per tile, keys are processed in 3 blocks of 192 (= 8 window rows):
+//   one CTA per (window, head): 16 softmax warps + 1 warp whose lane 0 only issues MMAs.  K (L2-normalised) and V^T of the whole
+//   window are staged ONCE in shared memory (72 KB) and serve all five 128-query tiles; per tile, keys are processed in 3 blocks
+//   of 192 (= 8 window rows):
 //     S_j[128x192] = Qn * Kn_j^T     tcgen05.mma M128 N192 K32, fp32 accumulators double-buffered in TMEM columns 0..383
 //     softmax                        FOUR threads per query row (TMEM lane), each owns 48 keys (2 window rows) of the block:
-//                                    add the cpb bias (one LDS with a compile-time offset per logit) and the shift mask,
-//                                    exponentiate, write P (bf16) into the 128B-swizzled K-major tile the tensor core reads
-//                                    (double-buffered: the P V MMAs of block j run under the softmax of block j + 1)
-//     O[128x32] += P_j * V_j         tcgen05.mma M128 N32 K192, TMEM columns 384..415
-//     out = O / rowsum               bf16, written straight to the un-shifted token position
+//                                    add the cpb bias (one LDS with a compile-time offset per logit, bank-conflict-free table
+//                                    stride) and the shift mask, exponentiate, pack to bf16 pairs and write P back to TMEM
+//                                    (tcgen05.st, columns 416..511) -- P never touches shared memory
+//     O[128x32] += P_j * V_j         tcgen05.mma with the A operand IN TMEM (M128 N32 K192), TMEM columns 384..415: ~6x faster than
+//                                    the shared-memory-A form, which is bound by the A-operand read for narrow N
+//     out = O / rowsum               bf16, written straight to the un-shifted token position, one key block LATE (inside the
+//                                    next tile's first block) so that nobody waits for the tile's last MMAs
+//   Hand-offs are mbarriers, not CTA barriers: every softmax warp arrives on bar_p when it has consumed S_j and written P_j; the
+//   issuer then issues P_j V_j and S_(j+2) (and, at the end of a tile, the next tile's first two score blocks: query tiles are
+//   double-buffered and staged by all 512 threads during the tile before).  The softmax warps only ever wait for tcgen05.commit
+//   barriers, so they drift apart and their MUFU / LDS / TMEM phases overlap instead of running in lock step.
 //   Softmax reference point: cosine attention bounds every logit by m = 1.01*scale + 16 (|cos| <= 1 up to bf16 rounding,
 //   bias = 16*sigmoid(.) < 16, the shift mask only subtracts).  When exp(logit - m) cannot underflow for ANY admissible
 //   logit (2.01*scale + 16 < 80: every random-init and most trained heads) the row-max pass is skipped; otherwise
-//   (logit scales towards the clamp of 100) the kernel runs an exact row-max pass first and re-issues the cheap K = 32 score
-//   MMAs -- per head, decided from the scale itself, so the result never depends on a host-side flag.
+//   (logit scales towards the clamp of 100) the kernel runs an exact row-max pass first and the issuer re-issues the cheap K = 32
+//   score MMAs -- per head, decided from the scale itself, so the result never depends on a host-side flag.
 #include "common.cuh"
 
 namespace {
@@ -38,7 +45,7 @@ constexpr int SM_Q = 0;                                // 2 buffers x (128 rows 
 constexpr int SM_K = 16384;                            // 576 rows x 64 B, SWIZZLE_64B
 constexpr int SM_VT = SM_K + NTOK * 64;                // 9 k-blocks x (32 rows x 128 B), SWIZZLE_128B
 constexpr int SM_MISC = SM_VT + (NTOK / 64) * 4096;    // region ids | partial sums / maxima [4][128] | barriers | slot | table
-constexpr int MISC_REG = 640, MISC_RED = 4 * 128 * 4, MISC_BAR = 64;
+constexpr int MISC_REG = 640, MISC_RED = 2 * 4 * 128 * 4, MISC_BAR = 64;   // MISC_RED: row sums [4][128] | row maxima [4][128]
 constexpr int SMEM_BYTES = SM_MISC + MISC_REG + MISC_RED + MISC_BAR + TABW * TS * 4 + 1024;
 constexpr int TM_O = 2 * KBLK;             // TMEM column of O (32 columns)
 constexpr int TM_P = TM_O + D;             // TMEM columns of P: 128 lanes x KBLK keys as bf16 pairs = KBLK / 2 columns
@@ -130,6 +137,12 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
                  ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+// 16-byte global load that stays where it is written (volatile): issued early on purpose, consumed much later
+__device__ __forceinline__ uint4 ldg_pinned(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -284,7 +297,18 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
             for (int i = 0; i < 4; ++i) vrb[i] = kvb[(C >> 2) + i];
         }
         qraw = *q_ptr(0);
-        for (int i = t; i < TAB; i += THREADS) s_tab[(i / TABW) * TS + i % TABW] = bias_tab[(size_t)head * TAB + i];
+        constexpr int TAB_PER = (TAB + THREADS - 1) / THREADS;
+        float tabv[TAB_PER];
+#pragma unroll
+        for (int i = 0; i < TAB_PER; ++i) {
+            const int e = t + i * THREADS;
+            tabv[i] = e < TAB ? bias_tab[(size_t)head * TAB + e] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < TAB_PER; ++i) {
+            const int e = t + i * THREADS;
+            if (e < TAB) s_tab[(e / TABW) * TS + e % TABW] = tabv[i];
+        }
         stage_kv(t, region_a, kra, vra);
         if (second) stage_kv(THREADS + t, region_b, krb, vrb);
         stage_q(qraw, sc, 0);
@@ -375,6 +399,21 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
             if ((t & 31) == 0) mbar_arrive(&bar_p[step & 1]);
             ++step;
         };
+        // epilogue of a tile: out = O / rowsum for my 8 output channels.  It runs one key block LATE (inside the first block of
+        // the next tile, right after the wait for the P columns that block needs anyway): the tile's last P V MMAs and the
+        // issuer's wake-up are then hidden behind a block of softmax work instead of stalling all 16 warps at the tile boundary
+        long long prev_tok = 0;
+        bool prev_valid = false, prev_active = false;
+        auto epilogue = [&]() {
+            softmax_sync();                                            // every quarter's partial row sum is in s_red
+            const float l = (s_red[row] + s_red[128 + row]) + (s_red[256 + row] + s_red[384 + row]);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (prev_active) {
+                float o[8];
+                tmem_ld8(t_row + (uint32_t)(TM_O + quarter * 8), o);
+                if (prev_valid) *reinterpret_cast<uint4 *>(out + prev_tok * C + head * D + quarter * 8) = pack8_scaled(o, 1.0f / l);
+            }
+        };
 #pragma unroll 1
         for (int qt = 0; qt < QT; ++qt) {
             const int r = min(qt * 128 + row, NTOK - 1);      // my query row inside the window (rows past the end repeat the last)
@@ -384,7 +423,7 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
             const long long tok = token_of(r, my_reg);
             // the next tile's query rows: loaded now, staged after the first key block (S_0 / S_1 of this tile were issued at the
             // end of the previous one, so nothing at a tile boundary waits for global memory)
-            if (qt + 1 < QT) qraw = *q_ptr(qt + 1);
+            if (qt + 1 < QT) qraw = ldg_pinned(q_ptr(qt + 1));
             // cpb bias[i][j] = table[(qy - ky + 23) * 47 + (qx - kx + 23)]: query part in a register, the key part is a per-block
             // constant (8 window rows per block, 2 per quarter) plus a compile-time offset
             const float *tab_q = s_tab + (r / WS + WS - 1) * TS + (r % WS) + WS - 1 - quarter * 2 * TS;
@@ -413,11 +452,12 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                     }
                     step_done();
                 }
-                s_red[quarter * 128 + row] = m;
+                float *s_mx = s_red + 512;
+                s_mx[quarter * 128 + row] = m;
                 softmax_sync();
-                m = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
+                m = fmaxf(fmaxf(s_mx[row], s_mx[128 + row]), fmaxf(s_mx[256 + row], s_mx[384 + row]));
                 ml = m * LOG2E;
-                softmax_sync();                                        // maxima consumed before s_red carries the sums
+                // (the next write to s_mx is a whole tile -- at least three hand-offs -- away)
             }
 
             // ---- P_j = exp(logit - reference); the issuer accumulates O += P_j V_j
@@ -453,6 +493,7 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                     }
                 }
                 if (n_pv > 0) mbar_wait(bar_pv, (uint32_t)((n_pv - 1) & 1));   // the P columns are free once the previous P V is done
+                if (j == 0 && qt > 0) epilogue();                      // ... and O of the previous tile is complete
                 if (active) {
                     const uint32_t pcol = t_row + (uint32_t)(TM_P + quarter * (KQ / 2));
                     tmem_st16(pcol, pk);
@@ -463,19 +504,12 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                 if (j == 0 && qt + 1 < QT) stage_q(qraw, sc, (qt + 1) & 1);   // that buffer's last readers (tile qt - 1) are long done
                 step_done();
             }
+            // s_red was last read inside this tile's first block (epilogue of the previous tile): two hand-offs ago for everyone
             s_red[quarter * 128 + row] = l0 + l1;
-            softmax_sync();
-            const float l = (s_red[row] + s_red[128 + row]) + (s_red[256 + row] + s_red[384 + row]);
-            mbar_wait(bar_pv, (uint32_t)((n_pv - 1) & 1));             // the tile's last P V (everything before it is done too)
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (active) {   // ---- epilogue: my 8 output channels: O / l -> bf16 -> out[token, head*32 + quarter*8 ...]
-                float o[8];
-                tmem_ld8(t_row + (uint32_t)(TM_O + quarter * 8), o);
-                if (valid) *reinterpret_cast<uint4 *>(out + tok * C + head * D + quarter * 8) = pack8_scaled(o, 1.0f / l);
-            }
-            // no barrier here: O is overwritten by P_0 V_0 of the next tile, which the issuer starts only after every warp's next
-            // step_done(); s_red is rewritten three hand-offs later, and each hand-off needs every warp to have passed this point
+            prev_tok = tok; prev_valid = valid; prev_active = active;
         }
+        mbar_wait(bar_pv, (uint32_t)((n_pv - 1) & 1));                 // the last tile's last P V (everything before it is done too)
+        epilogue();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -2,16 +2,20 @@
 // swinv2_tiny_window16_256, > 95 % of the attention FLOPs).  timm 0.6.12 WindowAttention +
 // SwinTransformerBlock._attn (window partition, cyclic shift, reverse) in one kernel:
 //
-//   one CTA (256 threads) per (window, head), two CTAs per SM (105 KB smem, 256 TMEM columns each)
-//   per 128-query half:
+//   one CTA (256 threads) per (window, head), two CTAs per SM (49 KB smem, 256 TMEM columns each): one CTA's MMA / staging
+//   phases run under the other's softmax.  Every global load of the CTA's start-up (K, V, the first query half, the bias
+//   table) is issued before anything waits on one of them.  Per 128-query half:
 //     S[128x256] = Qn * Kn^T         tcgen05.mma M128 N256 K32, fp32 accumulator in TMEM columns 0..255
 //     softmax                        two threads per query row (TMEM lane), each owns 128 keys; ONE pass: add cpb bias
 //                                    (+ shift mask), exponentiate against the analytic bound 1.01*scale + 16 of the
-//                                    cosine-attention logits (no row-max pass, nothing written back to TMEM) and write
-//                                    P (bf16) into shared memory in the 128B-swizzled K-major layout the tensor core reads
-//     O[128x32]  = P * V             tcgen05.mma M128 N32 K256 (A = P in smem, B = V^T staged through a
-//                                    register transpose), accumulated over TMEM columns 0..31
+//                                    cosine-attention logits (exact row-max pre-pass only for heads with huge logit scales),
+//                                    pack to bf16 pairs and write P back to TMEM OVER the score columns the thread has already
+//                                    consumed (tcgen05.st; keys 0..127 -> columns 0..63, keys 128..255 -> columns 128..191)
+//     O[128x32]  = P * V             tcgen05.mma with the A operand in TMEM (M128 N32 K256; B = V^T staged through a register
+//                                    transpose), TMEM columns 64..95.  P never touches shared memory: no 64 KB P tile, no proxy
+//                                    fence, and the narrow-N MMA is no longer bound by its A-operand read from shared memory
 //     out        = O / rowsum        bf16, written straight to the un-shifted token position
+//     the second half's query rows are staged by all 256 threads while the P V MMAs of the first half run
 //   q and k are L2-normalised in fp32 while being staged (q also carries the clamped logit scale).
 // The cyclic shift lives in the token index arithmetic; the {0,-100} mask is regenerated from region ids
 // exactly like timm's attn_mask buffer and compiled out for un-shifted blocks.
@@ -26,8 +30,9 @@ constexpr int TC_THREADS = 256;
 constexpr int TC_SMEM_Q = 0;              // 128 rows x 64 B, SWIZZLE_64B
 constexpr int TC_SMEM_K = 8192;           // 256 rows x 64 B, SWIZZLE_64B
 constexpr int TC_SMEM_VT = 8192 + 16384;  // 4 k-blocks x (32 rows x 128 B), SWIZZLE_128B
-constexpr int TC_SMEM_P = TC_SMEM_VT + 16384;    // 4 k-blocks x (128 rows x 128 B), SWIZZLE_128B
-constexpr int TC_SMEM_MISC = TC_SMEM_P + 65536;  // region ids 256 B | barrier | slot | row sums [2][128] f32 | bias table
+constexpr int TC_SMEM_MISC = TC_SMEM_VT + 16384;  // region ids 256 B | barrier | slot | row sums [2][128] f32 | bias table
+constexpr int TC_TM_O = 64;                       // TMEM columns: S = 0..255; P (bf16 pairs) overwrites the consumed score columns
+                                                  // 0..63 (keys 0..127) and 128..191 (keys 128..255); O = 64..95
 constexpr int TC_TAB = 31 * 31;                    // relative-position bias table of one head: (2*16-1)^2 entries
 constexpr int TC_TS = 48;                          // its row stride in shared memory: the 32 query rows of a warp span two window
                                                    // rows, (TC_TS - 16) % 32 == 0 puts their table reads into 32 different banks
@@ -88,6 +93,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
         : "r"(taddr) : "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 columns, each 32-bit column holding two consecutive K elements (bf16)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+                 ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -298,40 +315,45 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
         }
         float l = 0.f;
 #pragma unroll 1
-        for (int kk = 0; kk < 2; ++kk) {
-            const int kb = wg * 2 + kk;
-            uint8_t *prow = smem + TC_SMEM_P + kb * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
+        for (int ch = 0; ch < 4; ++ch) {
+            float v[32];
+            const int c0 = wg * 128 + ch * 32;                          // first key of this chunk
+            tmem_ld32(t_row + (uint32_t)c0, v);
+            const float *tab = tab_q - (c0 >> 4) * TC_TS;               // keys of this chunk: rows ky0, ky0 + 1
+            uint32_t pk[16];
+            float l2 = 0.f;
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                float v[32];
-                const int c0 = kb * 64 + hh * 32;                       // first key of this chunk
-                tmem_ld32(t_row + (uint32_t)c0, v);
-                const float *tab = tab_q - (c0 >> 4) * TC_TS;               // keys of this chunk: rows ky0, ky0 + 1
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = v[j] + tab[-((j >> 4) * TC_TS + (j & 15))];
-                    if (MASK) x += (reg[c0 + j] != my_reg) ? -100.0f : 0.0f;
-                    v[j] = fast_exp2(fmaf(x, LOG2E, -ml));
-                    l += v[j];
+            for (int j = 0; j < 32; j += 2) {
+                float x0 = v[j] + tab[-((j >> 4) * TC_TS + (j & 15))];
+                float x1 = v[j + 1] + tab[-(((j + 1) >> 4) * TC_TS + ((j + 1) & 15))];
+                if (MASK) {
+                    x0 += (reg[c0 + j] != my_reg) ? -100.0f : 0.0f;
+                    x1 += (reg[c0 + j + 1] != my_reg) ? -100.0f : 0.0f;
                 }
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4)
-                    *reinterpret_cast<uint4 *>(prow + (((hh * 4 + c4) ^ (row & 7)) << 4)) = pack8_scaled(v + c4 * 8, 1.0f);
+                x0 = fast_exp2(fmaf(x0, LOG2E, -ml));
+                x1 = fast_exp2(fmaf(x1, LOG2E, -ml));
+                l += x0;
+                l2 += x1;
+                pk[j >> 1] = pack_bf16x2(x0, x1);
             }
+            l += l2;
+            // P (bf16 pairs, key 2c in the low half) over score columns this thread has already consumed: chunk ch of my 128
+            // score columns was just read, its 16 P columns land at wg*128 + ch*16 <= the columns read so far
+            tmem_st16(t_row + (uint32_t)(wg * 128 + ch * 16), pk);
         }
+        tmem_st_wait();
         s_sum[wg * 128 + row] = l;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();                       // all S reads done, all P rows written, partial sums visible, s_max consumed
         if (t == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t idesc = umma_idesc(D);
 #pragma unroll 1
-            for (int kb = 0; kb < 4; ++kb) {
-                const uint64_t da = umma_desc(smem_u32(smem + TC_SMEM_P + kb * 16384), 128);
+            for (int kb = 0; kb < 4; ++kb) {     // 64 keys = 32 P columns per k-block; keys 128.. live at column 128..
+                const uint32_t pa = tmem + (uint32_t)((kb >> 1) * 128 + (kb & 1) * 32);
                 const uint64_t db = umma_desc(smem_u32(smem + TC_SMEM_VT + kb * 4096), 128);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) umma_f16_ts(tmem + TC_TM_O, pa + 8 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(bar);
         }
@@ -347,7 +369,7 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {   // ---- epilogue: my 16 output channels: O / l -> bf16 -> out[token, head*32 + wg*16 ...]
             float o[16];
-            tmem_ld16(t_row + (uint32_t)(wg * 16), o);
+            tmem_ld16(t_row + (uint32_t)(TC_TM_O + wg * 16), o);
             const float inv = 1.0f / l;
             bf16 *op = out + tok * C + head * D + wg * 16;
             *reinterpret_cast<uint4 *>(op) = pack8_scaled(o, inv);

@@ -16,6 +16,8 @@ ViT-hybrid encoder (dpt_hybrid_384) instead of the Swin part:
 import ctypes
 import math
 
+import os
+
 import torch
 
 from . import _cabi
@@ -55,6 +57,15 @@ class NetworkEngine:
         self._weights = None
         self._plans = {}
         self.lib = _cabi.load()
+        self.use_graphs = os.environ.get("SOCCDPT_CUDA_GRAPH", "0") == "1"
+
+    def enable_graphs(self, on=True):
+        """Replay each batch size's launch list as a CUDA graph (opt-in; SOCCDPT_CUDA_GRAPH=1 sets it at construction)."""
+        self.use_graphs = bool(on)
+        if not on:
+            for p in self._plans.values():
+                p.pop("graph", None)
+        return self
 
     def invalidate(self):
         self._weights = None
@@ -434,6 +445,23 @@ class NetworkEngine:
         if tuple(x.shape[1:]) != (3, plan["img"], plan["img"]):
             raise AssertionError("Input image size doesn't match model")
         plan["x_in"].copy_(x, non_blocking=True)
+        if self.use_graphs:
+            # CUDA-graph replay of the plan's launch list (all buffers are static, every entry point only enqueues on the
+            # current stream): the first call of a plan runs eagerly (sets the kernels' attributes), the second is captured.
+            # What it buys is the host side: ~130 ctypes launches per forward cost more than the kernels at small batches.
+            g = plan.get("graph")
+            if g is None and plan.get("warm", False):
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize(x.device)
+                with torch.cuda.graph(g):
+                    stream = _cabi.current_stream()
+                    for op in plan["ops"]:
+                        op(stream)
+                plan["graph"] = g
+            if g is not None:
+                g.replay()
+                return plan["depth"], plan["seg"]
+            plan["warm"] = True
         stream = _cabi.current_stream()
         for op in plan["ops"]:
             op(stream)

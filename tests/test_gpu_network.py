@@ -114,3 +114,24 @@ def test_batch_invariance(setup):
         d3, s3 = (t.clone() for t in net.network(x))
         d1, s1 = (t.clone() for t in net.network(x[1:2]))
     assert torch.allclose(d3[1:2], d1, rtol=1e-3, atol=1e-4) and torch.allclose(s3[1:2], s1, rtol=1e-3, atol=1e-4)
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager(setup):
+    """engine.enable_graphs(): the captured launch list replays to the same bytes as the eager launches (B = 1 and 3)."""
+    net, _ = setup
+    eng = net.engine("tcgen05")
+    for B in (1, 3):
+        x = synthetic_frames(B, 256, 5).cuda()
+        with torch.no_grad():
+            eng.enable_graphs(False)
+            d0, s0 = [t.clone() for t in net.network(x)]
+            eng.enable_graphs(True)
+            for _ in range(3):                      # warm call, capture call, replay
+                d1, s1 = net.network(x)
+            assert eng.plan_for(B, x.device).get("graph") is not None
+            assert torch.equal(d0, d1) and torch.equal(s0, s1)
+            x2 = synthetic_frames(B, 256, 6).cuda()
+            d2, s2 = [t.clone() for t in net.network(x2)]          # replay with new input
+            eng.enable_graphs(False)
+            d3, s3 = net.network(x2)
+            assert torch.equal(d2, d3) and torch.equal(s2, s3)

@@ -162,7 +162,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def _tiny_state_dict():
@@ -228,6 +228,9 @@ def instrumented_pass(net, x, reps):
             for k, v in samples.items()}
 
 
+_emit = None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -242,6 +245,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # stdout carries exactly ONE line (the JSON): everything libraries print while the run is set up (NCCL's version banner,
+    # model-loading messages) goes to stderr -- at the file-descriptor level, so native code is covered too
+    global _emit
+    sys.stdout.flush()
+    _stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def _emit(line):
+        sys.stdout.flush()
+        os.dup2(_stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -378,7 +394,7 @@ def main():
         "kernels_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -363,7 +363,7 @@ def main():
     pp_gbs = pp_bytes / (pp["ms"] * 1e-3) / 1e9
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # timed on rank 0 at N = 1 only (torchrun pins every rank to one thread)
         fps, times = cpu_reference_fps(sd, frames=2, reps=3)
         cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "3 x 2 frames of the same workload, fp32 oracle port (torch CPU + C voxeliser), median"}

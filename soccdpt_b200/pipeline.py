@@ -38,7 +38,11 @@ def gather_masks(grid, group=None):
 
 
 class FrameStream:
-    def __init__(self, net, batch, device=None):
+    """`camera_frames=(H, W)`: the batches are pinned uint8 (B, H, W, 3) camera frames instead of network-resolution fp32
+    tensors; they are uploaded as they are and resized / normalised on the device by the input-pipeline kernel
+    (soccdpt_b200.preprocess.GpuTransform, the reference's load_transforms)."""
+
+    def __init__(self, net, batch, device=None, camera_frames=None):
         self.net = net
         self.batch = batch
         self.device = torch.device(device) if device is not None else next(net.parameters()).device
@@ -48,13 +52,19 @@ class FrameStream:
         C, G = net.num_classes, net.grid_size
         self.up, self.comp, self.down = (torch.cuda.Stream(self.device) for _ in range(3))
         self.x_dev = [torch.empty((batch, 3, img, img), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.transform, self.u8_dev = None, None
+        if camera_frames is not None:
+            from .preprocess import GpuTransform
+            fh, fw = camera_frames
+            self.transform = GpuTransform(img, img, keep_aspect_ratio=False)
+            self.u8_dev = [torch.empty((batch, fh, fw, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
         self.d_dev = [torch.empty((batch, img, img), dtype=torch.float32, device=self.device) for _ in range(2)]
         self.s_dev = [torch.empty((batch, C, img, img), dtype=torch.float32, device=self.device) for _ in range(2)]
         self.g_dev = [torch.empty((G[0], G[1], G[2], C), dtype=torch.float32, device=self.device) for _ in range(2)]
         self.d_host = [torch.empty((batch, img, img), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.s_host = [torch.empty((batch, C, img, img), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.g_host = [torch.empty((G[0], G[1], G[2], C), dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.h2d_bytes = self.x_dev[0].numel() * 4
+        self.h2d_bytes = self.u8_dev[0].numel() if self.u8_dev is not None else self.x_dev[0].numel() * 4
         self.d2h_bytes = (self.d_host[0].numel() + self.s_host[0].numel() + self.g_host[0].numel()) * 4
 
     @torch.no_grad()
@@ -68,16 +78,20 @@ class FrameStream:
         i = -1
         for i, xh in enumerate(host_batches):
             slot = i & 1
-            assert tuple(xh.shape) == tuple(self.x_dev[0].shape), "every batch must have the FrameStream's shape"
+            stage_in = self.u8_dev if self.u8_dev is not None else self.x_dev
+            assert tuple(xh.shape) == tuple(stage_in[0].shape) and xh.dtype == stage_in[0].dtype, \
+                "every batch must have the FrameStream's shape and dtype"
             with torch.cuda.stream(self.up):
                 if ev_free_x[slot] is not None:
                     self.up.wait_event(ev_free_x[slot])
-                self.x_dev[slot].copy_(xh, non_blocking=True)
+                stage_in[slot].copy_(xh, non_blocking=True)
                 ev_up[slot].record(self.up)
             with torch.cuda.stream(self.comp):
                 self.comp.wait_event(ev_up[slot])
                 if i >= 2:
                     self.comp.wait_event(ev_down[slot])      # download of batch i-2 has drained this slot
+                if self.transform is not None:
+                    self.transform(self.u8_dev[slot], out=self.x_dev[slot])
                 out = self.net(self.x_dev[slot])
                 depth, seg = self.net.engine().plan_for(self.batch, self.device)["depth"], \
                     self.net.engine().plan_for(self.batch, self.device)["seg"]

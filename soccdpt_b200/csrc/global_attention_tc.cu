@@ -4,8 +4,9 @@
 //   one CTA (256 threads) per (image, head, 128-query tile); keys are processed in blocks of 128:
 //     S_j[128x128] = Q K_j^T          tcgen05.mma M128 N128 K64, fp32 accumulators double-buffered in TMEM columns 0..255
 //     pass 1: row max over all key blocks (scores are only read, never stored)
-//     pass 2: S_j recomputed (4 MMAs, far cheaper than a rescale of O), P_j = exp2((S_j - max) * scale * log2e) -> bf16 into
-//             shared memory in the 128B-swizzled K-major layout, O[128x64] += P_j V_j (M128 N64 K128, TMEM columns 256..319)
+//     pass 2: S_j recomputed (4 MMAs, far cheaper than a rescale of O), P_j = exp2((S_j - max) * scale * log2e) -> bf16 pairs
+//             written back to TMEM (tcgen05.st, columns 320..383), O[128x64] += P_j V_j with the A operand in TMEM
+//             (M128 N64 K128, TMEM columns 256..319): P never touches shared memory
 //     out = O / rowsum, bf16
 //   Q, K are copied as they are (16-byte chunks) into swizzled rows; V is transposed while staged (the B operand of P V is
 //   V^T, K-major).  Two threads per query row (TMEM lane), each owns 64 of the 128 keys of a block and 32 output channels.
@@ -18,12 +19,12 @@ using bf16 = __nv_bfloat16;
 constexpr int GD = 64;                  // head dim
 constexpr int GT = 256;                 // threads
 constexpr int KB = 128;                 // keys per block
-constexpr int MAX_BLOCKS = 5;           // 640 keys: what fits next to Q and P in 227 KB
+constexpr int MAX_BLOCKS = 6;           // 768 keys: K and V^T (32 KB per 128 keys) next to Q in 227 KB
 constexpr int SM_Q = 0;                 // 128 rows x 128 B, SWIZZLE_128B
-constexpr int SM_P = 16384;             // 2 k-blocks x (128 rows x 128 B), SWIZZLE_128B
-constexpr int SM_MISC = SM_P + 32768;   // row max [2][128] | row sum [2][128] | barriers | tmem slot
+constexpr int SM_MISC = 16384;          // row max [2][128] | row sum [2][128] | barriers | tmem slot
 constexpr int SM_K = SM_MISC + 4096;    // nb x (128 rows x 128 B);  then V^T: 2*nb x (64 rows x 128 B)
-constexpr int TM_O = 256;               // TMEM column of O
+constexpr int TM_O = 256;               // TMEM column of O (64 columns)
+constexpr int TM_P = 320;               // TMEM columns of P: 128 keys as bf16 pairs = 64 columns (A operand of the P V MMAs)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -65,6 +66,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         : "r"(taddr) : "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n"
+        "tcgen05.wait::st.sync.aligned;"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+          "r"(r[30]), "r"(r[31]) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 columns, each 32-bit column holding two consecutive K elements (bf16)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+                 ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -199,13 +215,13 @@ global_attention_tc_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out,
         if (nb > 1) issue_s(1);
     }
     float l = 0.f;
-    uint8_t *prow = smem + SM_P + wg * 16384 + row * 128;      // my 64 keys = k-block `wg` of the P tile
 #pragma unroll 1
     for (int j = 0; j < nb; ++j) {
         mbar_wait(&bar_s[j & 1], ph_s[j & 1]);
         ph_s[j & 1] ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int key0 = j * KB + wg * 64;
+        uint32_t pk[32];                                       // my 64 probabilities as bf16 pairs (key 2c in the low half)
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             float v[32];
@@ -218,25 +234,24 @@ global_attention_tc_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out,
                 v[i] = p;
                 l += p;
             }
-            if (hh == 0 && j > 0) {                            // P V of the previous block must have consumed P
-                mbar_wait(bar_pv, ph_pv);
-                ph_pv ^= 1;
-            }
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4)
-                *reinterpret_cast<uint4 *>(prow + (((hh * 4 + c4) ^ (row & 7)) << 4)) = pack8(v + c4 * 8);
+            for (int i = 0; i < 16; ++i) pk[hh * 16 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (j > 0) {                                           // P V of the previous block must have consumed the P columns
+            mbar_wait(bar_pv, ph_pv);
+            ph_pv ^= 1;
+        }
+        tmem_st32(t_row + (uint32_t)(TM_P + wg * 32), pk);     // P never touches shared memory: it is the TMEM A operand of P V
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();                                       // S_j read, P_j written by everybody
         if (t == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int kb2 = 0; kb2 < 2; ++kb2) {
-                const uint64_t dp = umma_desc128(smem_u32(smem + SM_P + kb2 * 16384));
                 const uint64_t dv = umma_desc128(smem_u32(sVT + (j * 2 + kb2) * 8192));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(tmem + TM_O, dp + 2 * k, dv + 2 * k, idesc_o, (j | kb2 | k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                    umma_f16_ts(tmem + TM_O, tmem + (uint32_t)(TM_P + (kb2 * 4 + k) * 8), dv + 2 * k, idesc_o, (j | kb2 | k) ? 1u : 0u);
             }
             umma_commit(bar_pv);
             if (j + 2 < nb) issue_s(j + 2);

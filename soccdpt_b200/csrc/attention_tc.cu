@@ -19,6 +19,8 @@
 //   q and k are L2-normalised in fp32 while being staged (q also carries the clamped logit scale).
 // The cyclic shift lives in the token index arithmetic; the {0,-100} mask is regenerated from region ids
 // exactly like timm's attn_mask buffer and compiled out for un-shifted blocks.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -219,6 +221,9 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
         tabv[i] = e < TC_TAB ? bias_tab[(size_t)head * TC_TAB + e] : 0.f;
     }
     const float sc = scale[head];
+    const float LOG2E = 1.4426950408889634f;
+    const bool one_pass = 2.01f * sc + 16.0f < 80.0f;                       // CTA-uniform, see the softmax comment below
+    const float tab_shift = one_pass ? (1.01f * sc + 16.0f) * LOG2E : 0.0f;
     if (t == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -257,7 +262,9 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int e = t + i * TC_THREADS;
-        if (e < TC_TAB) s_tab[(e / 31) * TC_TS + e % 31] = tabv[i];
+        // stored in the log2 domain, and (one-pass heads) already shifted by the analytic logit bound: the softmax loop is then
+        // one FMA per logit (score * log2e + table entry) straight into ex2
+        if (e < TC_TAB) s_tab[(e / 31) * TC_TS + e % 31] = fmaf(tabv[i], LOG2E, -tab_shift);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -265,7 +272,6 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 TMEM lanes
-    const float LOG2E = 1.4426950408889634f;
     uint32_t phase = 0;
 
 #pragma unroll 1
@@ -294,8 +300,9 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
         // cpb bias[i][j] = table[(qy - ky + 15) * 31 + (qx - kx + 15)]: query part in a register, key part is a
         // per-chunk constant plus a compile-time offset -> one LDS with an immediate offset per logit
         const float *tab_q = s_tab + ((r >> 4) + 15) * TC_TS + (r & 15) + 15;
-        float ml = (1.01f * sc + 16.0f) * LOG2E;
-        if (!(2.01f * sc + 16.0f < 80.0f)) {       // CTA-uniform
+        const float MASKED = -100.0f * LOG2E;
+        float ml = 0.0f;
+        if (!one_pass) {
             float m = -INFINITY;
 #pragma unroll 1
             for (int c0 = wg * 128; c0 < wg * 128 + 128; c0 += 32) {
@@ -304,43 +311,48 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
                 const float *tab = tab_q - (c0 >> 4) * TC_TS;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float x = v[j] + tab[-((j >> 4) * TC_TS + (j & 15))];
-                    if (MASK) x += (reg[c0 + j] != my_reg) ? -100.0f : 0.0f;
+                    float x = fmaf(v[j], LOG2E, tab[-((j >> 4) * TC_TS + (j & 15))]);
+                    if (MASK) x += (reg[c0 + j] != my_reg) ? MASKED : 0.0f;
                     m = fmaxf(m, x);
                 }
             }
             s_max[wg * 128 + row] = m;
             __syncthreads();
-            ml = fmaxf(m, s_max[(wg ^ 1) * 128 + row]) * LOG2E;
+            ml = fmaxf(m, s_max[(wg ^ 1) * 128 + row]);
         }
         float l = 0.f;
+        auto softmax_chunks = [&](auto one_pass_c) {
+            constexpr bool ONE = decltype(one_pass_c)::value;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-            float v[32];
-            const int c0 = wg * 128 + ch * 32;                          // first key of this chunk
-            tmem_ld32(t_row + (uint32_t)c0, v);
-            const float *tab = tab_q - (c0 >> 4) * TC_TS;               // keys of this chunk: rows ky0, ky0 + 1
-            uint32_t pk[16];
-            float l2 = 0.f;
+            for (int ch = 0; ch < 4; ++ch) {
+                float v[32];
+                const int c0 = wg * 128 + ch * 32;                          // first key of this chunk
+                tmem_ld32(t_row + (uint32_t)c0, v);
+                const float *tab = tab_q - (c0 >> 4) * TC_TS;               // keys of this chunk: rows ky0, ky0 + 1
+                uint32_t pk[16];
+                float l2 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                float x0 = v[j] + tab[-((j >> 4) * TC_TS + (j & 15))];
-                float x1 = v[j + 1] + tab[-(((j + 1) >> 4) * TC_TS + ((j + 1) & 15))];
-                if (MASK) {
-                    x0 += (reg[c0 + j] != my_reg) ? -100.0f : 0.0f;
-                    x1 += (reg[c0 + j + 1] != my_reg) ? -100.0f : 0.0f;
+                for (int j = 0; j < 32; j += 2) {
+                    float x0 = fmaf(v[j], LOG2E, tab[-((j >> 4) * TC_TS + (j & 15))]);
+                    float x1 = fmaf(v[j + 1], LOG2E, tab[-(((j + 1) >> 4) * TC_TS + ((j + 1) & 15))]);
+                    if (MASK) {
+                        x0 += (reg[c0 + j] != my_reg) ? MASKED : 0.0f;
+                        x1 += (reg[c0 + j + 1] != my_reg) ? MASKED : 0.0f;
+                    }
+                    x0 = fast_exp2(ONE ? x0 : x0 - ml);
+                    x1 = fast_exp2(ONE ? x1 : x1 - ml);
+                    l += x0;
+                    l2 += x1;
+                    pk[j >> 1] = pack_bf16x2(x0, x1);
                 }
-                x0 = fast_exp2(fmaf(x0, LOG2E, -ml));
-                x1 = fast_exp2(fmaf(x1, LOG2E, -ml));
-                l += x0;
-                l2 += x1;
-                pk[j >> 1] = pack_bf16x2(x0, x1);
+                l += l2;
+                // P (bf16 pairs, key 2c in the low half) over score columns this thread has already consumed: chunk ch of my
+                // 128 score columns was just read, its 16 P columns land at wg*128 + ch*16 <= the columns read so far
+                tmem_st16(t_row + (uint32_t)(wg * 128 + ch * 16), pk);
             }
-            l += l2;
-            // P (bf16 pairs, key 2c in the low half) over score columns this thread has already consumed: chunk ch of my 128
-            // score columns was just read, its 16 P columns land at wg*128 + ch*16 <= the columns read so far
-            tmem_st16(t_row + (uint32_t)(wg * 128 + ch * 16), pk);
-        }
+        };
+        if (one_pass) softmax_chunks(std::true_type{});
+        else softmax_chunks(std::false_type{});
         tmem_st_wait();
         s_sum[wg * 128 + row] = l;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

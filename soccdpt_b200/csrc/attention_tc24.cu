@@ -23,6 +23,8 @@
 //   logit (2.01*scale + 16 < 80: every random-init and most trained heads) the row-max pass is skipped; otherwise
 //   (logit scales towards the clamp of 100) the kernel runs an exact row-max pass first and the issuer re-issues the cheap K = 32
 //   score MMAs -- per head, decided from the scale itself, so the result never depends on a host-side flag.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -179,14 +181,17 @@ __device__ __forceinline__ uint4 pack8_scaled(const float *f, float s) {
     return u;
 }
 
-// logits of CNT keys starting at key offset J0 (compile time, inside this thread's 48 keys): S + bias (+ mask)
+// logits of CNT keys starting at key offset J0 (compile time, inside this thread's 48 keys), in the log2 domain:
+// S * log2e + table entry (+ mask).  The table holds bias * log2e, for one-pass heads already minus the analytic logit bound,
+// so this is ONE FMA per logit and its result goes straight into ex2.
 template <bool MASK, int J0, int CNT>
 __device__ __forceinline__ void add_bias(float *v, const float *tab, const uint8_t *rg, int my_reg) {
+    const float LOG2E = 1.4426950408889634f;
 #pragma unroll
     for (int i = 0; i < CNT; ++i) {
         const int jl = J0 + i;
-        float x = v[i] + tab[-((jl / WS) * TS + (jl % WS))];
-        if (MASK) x += (rg[jl] != my_reg) ? -100.0f : 0.0f;
+        float x = fmaf(v[i], LOG2E, tab[-((jl / WS) * TS + (jl % WS))]);
+        if (MASK) x += (rg[jl] != my_reg) ? -100.0f * LOG2E : 0.0f;
         v[i] = x;
     }
 }
@@ -278,6 +283,9 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
     // ---- prologue: every global load of the CTA's start-up is issued before anything waits on one of them
     const bool softmax_warp = warp < THREADS / 32;
     const float sc = scale[head];
+    const float LOG2E = 1.4426950408889634f;
+    const bool one_pass = 2.01f * sc + 16.0f < 80.0f;                    // see the header comment
+    const float tab_shift = one_pass ? (1.01f * sc + 16.0f) * LOG2E : 0.0f;
     uint4 qraw = make_uint4(0, 0, 0, 0);
     if (softmax_warp) {
         int region_a, region_b = 0;
@@ -307,7 +315,7 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
 #pragma unroll
         for (int i = 0; i < TAB_PER; ++i) {
             const int e = t + i * THREADS;
-            if (e < TAB) s_tab[(e / TABW) * TS + e % TABW] = tabv[i];
+            if (e < TAB) s_tab[(e / TABW) * TS + e % TABW] = fmaf(tabv[i], LOG2E, -tab_shift);
         }
         stage_kv(t, region_a, kra, vra);
         if (second) stage_kv(THREADS + t, region_b, krb, vrb);
@@ -328,8 +336,6 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 TMEM lanes
-    const float LOG2E = 1.4426950408889634f;
-    const bool one_pass = 2.01f * sc + 16.0f < 80.0f;                    // see the header comment
     const uint32_t idesc_s = umma_idesc(KBLK), idesc_o = umma_idesc(D);
     // hand-off softmax warps -> issuer: step s (one key block of one pass) completes phase (s >> 1) of bar_p[s & 1]
     int step = 0;
@@ -428,7 +434,7 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
             // constant (8 window rows per block, 2 per quarter) plus a compile-time offset
             const float *tab_q = s_tab + (r / WS + WS - 1) * TS + (r % WS) + WS - 1 - quarter * 2 * TS;
             const uint8_t *reg_q = reg + quarter * KQ;
-            float ml = (1.01f * sc + 16.0f) * LOG2E;
+            float ml = 0.0f;                                           // fallback only: exact row maximum (log2 domain)
 
             if (!one_pass) {
                 // ---- exact row maximum first (scores are read, never stored; the issuer re-issues the score MMAs)
@@ -456,7 +462,7 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                 s_mx[quarter * 128 + row] = m;
                 softmax_sync();
                 m = fmaxf(fmaxf(s_mx[row], s_mx[128 + row]), fmaxf(s_mx[256 + row], s_mx[384 + row]));
-                ml = m * LOG2E;
+                ml = m;
                 // (the next write to s_mx is a whole tile -- at least three hand-offs -- away)
             }
 
@@ -466,7 +472,8 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
             for (int j = 0; j < NBLK; ++j) {
                 wait_s(j);
                 uint32_t pk[KQ / 2];                                   // my 48 probabilities as bf16 pairs (key 2c in the low half)
-                if (active) {
+                auto exps = [&](auto one_pass_c) {
+                    constexpr bool ONE = decltype(one_pass_c)::value;
                     const float *tab = tab_q - j * 8 * TS;
                     const uint8_t *rg = reg_q + j * KBLK;
                     const uint32_t col = t_row + (uint32_t)((j & 1) * KBLK + quarter * KQ);
@@ -475,8 +482,8 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                     add_bias<MASK, 0, 32>(v, tab, rg, my_reg);
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        v[i] = fast_exp2(fmaf(v[i], LOG2E, -ml));
-                        v[i + 1] = fast_exp2(fmaf(v[i + 1], LOG2E, -ml));
+                        v[i] = fast_exp2(ONE ? v[i] : v[i] - ml);
+                        v[i + 1] = fast_exp2(ONE ? v[i + 1] : v[i + 1] - ml);
                         l0 += v[i];
                         l1 += v[i + 1];
                         pk[i >> 1] = pack_bf16x2(v[i], v[i + 1]);
@@ -485,12 +492,16 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
                     add_bias<MASK, 32, 16>(v, tab, rg, my_reg);
 #pragma unroll
                     for (int i = 0; i < 16; i += 2) {
-                        v[i] = fast_exp2(fmaf(v[i], LOG2E, -ml));
-                        v[i + 1] = fast_exp2(fmaf(v[i + 1], LOG2E, -ml));
+                        v[i] = fast_exp2(ONE ? v[i] : v[i] - ml);
+                        v[i + 1] = fast_exp2(ONE ? v[i + 1] : v[i + 1] - ml);
                         l0 += v[i];
                         l1 += v[i + 1];
                         pk[16 + (i >> 1)] = pack_bf16x2(v[i], v[i + 1]);
                     }
+                };
+                if (active) {
+                    if (one_pass) exps(std::true_type{});
+                    else exps(std::false_type{});
                 }
                 if (n_pv > 0) mbar_wait(bar_pv, (uint32_t)((n_pv - 1) & 1));   // the P columns are free once the previous P V is done
                 if (j == 0 && qt > 0) epilogue();                      // ... and O of the previous tile is complete

@@ -98,12 +98,12 @@ __global__ void __launch_bounds__(256)
 patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
                    const float *__restrict__ g, const float *__restrict__ be, bf16 *__restrict__ out,
                    float *__restrict__ out_f32, int B, int H, int W, int E) {
-    extern __shared__ float pe_smem[];
-    float *wT = pe_smem;                       // [48][E]
+    extern __shared__ __align__(16) float pe_smem[];
+    float4 *wT4 = reinterpret_cast<float4 *>(pe_smem);   // [12][E]: taps 4*k4 .. 4*k4+3 of channel e (one LDS.128 feeds 4 FMAs per token)
     float *stage = pe_smem + 48 * E;           // [8 warps][PE_TOK][48]
     for (int i = threadIdx.x; i < 48 * E; i += 256) {
         const int e = i / 48, k = i - e * 48;
-        wT[k * E + e] = w[i];
+        pe_smem[((k >> 2) * E + e) * 4 + (k & 3)] = w[i];
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -130,16 +130,18 @@ patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w, con
         for (int t = 0; t < PE_TOK; ++t)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[t][j] = (j < nch && lane + 32 * j < E) ? b[lane + 32 * j] : 0.0f;
-#pragma unroll 4
-        for (int k = 0; k < 48; ++k) {
-            float wv[4];
+#pragma unroll 2
+        for (int k4 = 0; k4 < 12; ++k4) {
+            float4 wv[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) wv[j] = (j < nch && lane + 32 * j < E) ? wT[k * E + lane + 32 * j] : 0.0f;
+            for (int j = 0; j < 4; ++j)
+                wv[j] = (j < nch && lane + 32 * j < E) ? wT4[k4 * E + lane + 32 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int t = 0; t < PE_TOK; ++t) {
-                const float xv = in[t * 48 + k];
+                const float4 xv = *reinterpret_cast<const float4 *>(in + t * 48 + k4 * 4);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[t][j] = fmaf(xv, wv[j], acc[t][j]);
+                for (int j = 0; j < 4; ++j)     // ascending tap order, like the scalar loop it replaces
+                    acc[t][j] = fmaf(xv.w, wv[j].w, fmaf(xv.z, wv[j].z, fmaf(xv.y, wv[j].y, fmaf(xv.x, wv[j].x, acc[t][j]))));
             }
         }
         __syncwarp();
@@ -368,24 +370,49 @@ upsample2x_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, unsigned N, 
 
 // ------------------------------------------------------------------ seg head tail
 // logits f32 [N,h,w,P] -> bilinear x2 (align_corners=True) -> sigmoid | 0.5*tanh+0.5 -> f32 NCHW
+// One thread per 4 consecutive output pixels of a row (W = 2w is a multiple of 4 whenever w is even; odd w falls back to the
+// scalar tail): their bilinear taps fall into at most 4 consecutive source columns, which are loaded once per source row and
+// channel, and every class plane gets one float4 store.
 __global__ void __launch_bounds__(256)
 seg_finish_kernel(const float *__restrict__ lg, float *__restrict__ seg, int N, int h, int w, int P, int act) {
     const int H = 2 * h, W = 2 * w;
-    const long long total = (long long)N * H * W;
+    const int W4 = W / 4;
+    const long long total = (long long)N * H * W4;
     const float sh = (float)(h - 1) / (float)(H - 1), sw = (float)(w - 1) / (float)(W - 1);
     for (long long o = (long long)blockIdx.x * 256 + threadIdx.x; o < total; o += (long long)gridDim.x * 256) {
-        const int X = (int)(o % W), Y = (int)((o / W) % H), n = (int)(o / ((long long)W * H));
-        const float fy = sh * (float)Y, fx = sw * (float)X;
-        const int y0 = (int)fy, x0 = (int)fx;
-        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-        const float ly = fy - (float)y0, lx = fx - (float)x0;
-        const float *base = lg + (long long)n * h * w * P;
+        const int X4 = (int)(o % W4) * 4, Y = (int)((o / W4) % H), n = (int)(o / ((long long)W4 * H));
+        const float fy = sh * (float)Y;
+        const int y0 = (int)fy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
+        const float ly = fy - (float)y0;
+        int xo[4];
+        float lx[4];
+        const int xb = (int)(sw * (float)X4);                       // first source column of the group
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float fx = sw * (float)(X4 + i);
+            const int x0 = (int)fx;
+            xo[i] = x0 - xb;                                        // 0..2 (x2 up-scaling: 4 outputs span < 2 source columns)
+            lx[i] = fx - (float)x0;
+        }
+        const float *r0 = lg + (((long long)n * h + y0) * w) * P, *r1 = lg + (((long long)n * h + y1) * w) * P;
         for (int p = 0; p < P; ++p) {
-            const float a = base[((long long)y0 * w + x0) * P + p], b = base[((long long)y0 * w + x1) * P + p];
-            const float c = base[((long long)y1 * w + x0) * P + p], d = base[((long long)y1 * w + x1) * P + p];
-            const float v = (1.0f - ly) * ((1.0f - lx) * a + lx * b) + ly * ((1.0f - lx) * c + lx * d);
-            const float r = act == 0 ? 1.0f / (1.0f + expf(-v)) : 0.5f * tanhf(v) + 0.5f;
-            seg[(((long long)n * P + p) * H + Y) * W + X] = r;
+            float t[4];                                             // vertical lerp of source columns xb .. xb+3 (clamped)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int xs = min(xb + j, w - 1);
+                const float a = __ldg(r0 + (long long)xs * P + p), c = __ldg(r1 + (long long)xs * P + p);
+                t[j] = (1.0f - ly) * a + ly * c;
+            }
+            float r[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float a = xo[i] == 0 ? t[0] : (xo[i] == 1 ? t[1] : t[2]);
+                const float b = xo[i] == 0 ? t[1] : (xo[i] == 1 ? t[2] : t[3]);
+                // same association as (1-ly)*((1-lx)*a + lx*b) + ly*((1-lx)*c + lx*d) up to fp32 rounding
+                const float v = (1.0f - lx[i]) * a + lx[i] * b;
+                r[i] = act == 0 ? 1.0f / (1.0f + expf(-v)) : 0.5f * tanhf(v) + 0.5f;
+            }
+            *reinterpret_cast<float4 *>(seg + (((long long)n * P + p) * H + Y) * W + X4) = make_float4(r[0], r[1], r[2], r[3]);
         }
     }
 }
@@ -502,7 +529,8 @@ int soccdpt_seg_finish_fwd(const float *logits, float *seg, int N, int h, int w,
                            soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(logits && seg && N >= 1 && h >= 2 && w >= 2 && P >= 1 && P <= 4 && (act == 0 || act == 1),
                     "seg_finish: bad arguments");
-    seg_finish_kernel<<<grid_for((long long)N * 4 * h * w), 256, 0, soccdpt::as_stream(stream)>>>(logits, seg, N, h, w, P, act);
+    SOCCDPT_REQUIRE(w % 2 == 0 && (reinterpret_cast<uintptr_t>(seg) & 15) == 0, "seg_finish: w must be even and seg 16-byte aligned");
+    seg_finish_kernel<<<grid_for((long long)N * h * w), 256, 0, soccdpt::as_stream(stream)>>>(logits, seg, N, h, w, P, act);
     return soccdpt::check_launch("seg_finish_kernel");
 }
 

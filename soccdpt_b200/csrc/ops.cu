@@ -443,7 +443,8 @@ int validate_conv(const soccdpt_conv_t *c) {
     SOCCDPT_REQUIRE(c->N >= 1 && c->H >= 1 && c->W >= 1, "conv: bad image dims %dx%dx%d", c->N, c->H, c->W);
     SOCCDPT_REQUIRE(c->Cin >= 8 && c->Cin % 8 == 0, "conv: Cin must be a multiple of 8 (got %d)", c->Cin);
     SOCCDPT_REQUIRE(c->Cout >= 8 && c->Cout % 8 == 0, "conv: Cout must be a multiple of 8 (got %d)", c->Cout);
-    SOCCDPT_REQUIRE((c->KH == 1 || c->KH == 3) && c->KW == c->KH, "conv: kernel must be 1x1 or 3x3");
+    SOCCDPT_REQUIRE((c->KH == 1 || c->KH == 3 || (c->KH == 2 && c->stride == 2 && c->pad_trim == 1)) && c->KW == c->KH,
+                    "conv: kernel must be 1x1, 3x3, or 2x2 with stride 2 and no padding (patch merging)");
     SOCCDPT_REQUIRE(c->act >= 0 && c->act <= 2, "conv: bad activation %d", c->act);
     SOCCDPT_REQUIRE(c->stride >= 0 && c->stride <= 2, "conv: stride must be 1 or 2 (got %d)", c->stride);
     SOCCDPT_REQUIRE(c->pad_trim >= 0 && c->pad_trim <= c->KH / 2, "conv: pad_trim must be in [0, KH/2] (got %d)", c->pad_trim);

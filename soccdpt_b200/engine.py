@@ -153,7 +153,13 @@ class NetworkEngine:
                     n2=(_f32(blk.norm2.weight, dev), _f32(blk.norm2.bias, dev))))
             ds = None
             if not isinstance(layer.downsample, torch.nn.Identity):
-                ds = dict(w=_bf16(layer.downsample.reduction.weight, dev),
+                # PatchMerging = cat(x[0::2,0::2], x[1::2,0::2], x[0::2,1::2], x[1::2,1::2]) -> Linear(4C, 2C): a 2x2 stride-2 conv
+                # whose tap (kh, kw) takes the weight columns of the slice with row parity kh and column parity kw
+                rw = layer.downsample.reduction.weight                       # (2C, 4C)
+                Cd = rw.shape[1] // 4
+                order = (0, 2, 1, 3)                                         # taps (0,0) (0,1) (1,0) (1,1) <- x0 x2 x1 x3
+                rw_taps = torch.stack([rw[:, q * Cd:(q + 1) * Cd] for q in order], dim=1).contiguous()   # (2C, 4, C)
+                ds = dict(w=_bf16(layer.downsample.reduction.weight, dev), w_taps=_bf16(rw_taps, dev),
                           n=(_f32(layer.downsample.norm.weight, dev), _f32(layer.downsample.norm.bias, dev)))
             W["stages"].append(dict(dim=layer.dim, res=layer.input_resolution, blocks=blocks, down=ds))
 
@@ -218,7 +224,6 @@ class NetworkEngine:
         att = buf(B * maxLC)
         tmp = buf(B * maxLC)
         hid = buf(B * maxLC * 4)
-        gat = buf(B * maxLC)           # patch-merge gather: (L/4) * 4C = L*C elements
         cur = buf(B * g0 * g0, E)                               # bf16 copy of the residual stream (GEMM operand)
         master = buf(B * g0 * g0, E, dtype=torch.float32)       # fp32 residual stream
         ops.append(_Launch("patch_embed", lib.soccdpt_patch_embed_fwd, x_in.data_ptr(), *(t.data_ptr() for t in Wt["pe"]),
@@ -241,9 +246,9 @@ class NetworkEngine:
                                    b["n2"][0].data_ptr(), b["n2"][1].data_ptr(), cur.data_ptr(), M, C, ctypes.c_float(1e-5)))
             taps.append((cur, Hs, Ws, C))   # hooks sit on the last block of every stage (dpt.py:61-72)
             if st["down"] is not None:
-                ops.append(_Launch("merge_gather", lib.soccdpt_patch_merge_gather_fwd, cur.data_ptr(), gat.data_ptr(), B, Hs, Ws, C))
                 M2 = B * L // 4
-                self._conv(plan, gat, st["down"]["w"], 1, 1, M2, 4 * C, 2 * C, 1, y=tmp)
+                # the 2x2 gather lives in the TMA box of the implicit GEMM (element strides 2, tap offsets (kh, kw))
+                self._conv(plan, cur, st["down"]["w_taps"], B, Hs, Ws, C, 2 * C, 2, y=tmp, stride=2, pad_trim=1)
                 nxt = buf(M2, 2 * C)
                 master = buf(M2, 2 * C, dtype=torch.float32)
                 ops.append(_Launch("ln", lib.soccdpt_layernorm_master_fwd, tmp.data_ptr(), master.data_ptr(), 0,

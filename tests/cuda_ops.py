@@ -16,7 +16,7 @@ def conv(x, w, bias=None, act=0, res1=None, res2=None, want_y=True, want_relu=Fa
     lib = _cabi.load()
     N, H, W, Cin = x.shape
     Cout, taps, _ = w.shape
-    K = 3 if taps == 9 else 1
+    K = {9: 3, 4: 2, 1: 1}[taps]
     c = _cabi.Conv()
     c.x, c.wgt = x.data_ptr(), w.data_ptr()
     c.bias = bias.data_ptr() if bias is not None else None

@@ -76,3 +76,21 @@ def test_tcgen05_conv_is_deterministic_and_reentrant():
     a = K.conv(x, w)[0]
     for _ in range(3):
         assert torch.equal(K.conv(x, w)[0], a)
+
+
+@pytest.mark.parametrize("B,Hs,Ws,C", [(2, 64, 64, 96), (3, 16, 16, 384), (1, 96, 96, 128), (2, 24, 24, 512)])
+def test_patch_merging_as_2x2_stride2_conv(B, Hs, Ws, C):
+    """timm PatchMerging (cat of the four parity slices -> Linear(4C, 2C, bias=False)) evaluated as a 2x2 stride-2 implicit GEMM:
+    the gather lives in the TMA box (element strides 2) -- against the torch restatement and the CUDA-core kernel."""
+    g = torch.Generator().manual_seed(B * 100 + C)
+    x = torch.randn(B, Hs, Ws, C, generator=g).bfloat16()
+    rw = (torch.randn(2 * C, 4 * C, generator=g) / math.sqrt(4 * C)).bfloat16()
+    xf = x.float()
+    cat = torch.cat([xf[:, 0::2, 0::2], xf[:, 1::2, 0::2], xf[:, 0::2, 1::2], xf[:, 1::2, 1::2]], -1)      # timm order
+    ref = cat @ rw.float().t()
+    w_taps = torch.stack([rw[:, q * C:(q + 1) * C] for q in (0, 2, 1, 3)], dim=1).contiguous().cuda()      # (2C, 4, C)
+    y, _, _ = K.conv(x.cuda(), w_taps, impl="tcgen05", stride=2, pad_trim=1)
+    y2, _, _ = K.conv(x.cuda(), w_taps, impl="ref", stride=2, pad_trim=1)
+    assert y.shape == (B, Hs // 2, Ws // 2, 2 * C)
+    assert torch.allclose(y.float().cpu(), ref, rtol=2e-2, atol=2e-2), (y.float().cpu() - ref).abs().max()
+    assert torch.allclose(y.float(), y2.float(), rtol=1e-2, atol=1e-2)

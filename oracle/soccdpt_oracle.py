@@ -143,10 +143,19 @@ def _conv(sd, name, x, padding):
     return F.conv2d(x, sd[name + ".weight"], sd.get(name + ".bias"), stride=1, padding=padding)
 
 
+def _bn(sd, name, x):
+    return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"], sd[name + ".bias"],
+                        False, 0.1, 1e-5)
+
+
 def _rcu(sd, p, x):
-    """ResidualConvUnit_custom, bn=False (blocks.py:391-414)."""
+    """ResidualConvUnit_custom (blocks.py:391-414); bn1 / bn2 exist with use_bn (DPTSegmentationModel, dpt.py:240)."""
     out = _conv(sd, p + ".conv1", F.relu(x), 1)
+    if p + ".bn1.weight" in sd:
+        out = _bn(sd, p + ".bn1", out)
     out = _conv(sd, p + ".conv2", F.relu(out), 1)
+    if p + ".bn2.weight" in sd:
+        out = _bn(sd, p + ".bn2", out)
     return out + x
 
 
@@ -164,6 +173,8 @@ def _fusion(sd, p, xs, size):
 class OracleV3:
     """SOccDPT_V3 (SOccDPT.py:626-685) evaluated functionally from a reference-keyed state_dict."""
 
+    PREFIX = "depth_net."       # the DPT whose encoder / decoder this instance evaluates
+
     def __init__(self, state_dict, model_type="dpt_swin2_tiny_256", sigmoid=True, geom=None,
                  compute_occ=True):
         import sys
@@ -174,7 +185,7 @@ class OracleV3:
         name, self.hooks, self.chans = ENCODERS[model_type]
         self.sd = {k: v.detach().to(torch.float32).cpu() for k, v in state_dict.items()}
         self.encoder = timm.create_model(name, pretrained=False).eval()
-        pfx = "depth_net.pretrained.model."
+        pfx = self.PREFIX + "pretrained.model."
         enc_sd = {k[len(pfx):]: v for k, v in self.sd.items() if k.startswith(pfx)}
         missing, unexpected = self.encoder.load_state_dict(enc_sd, strict=False)
         assert not unexpected and not missing, (missing, unexpected)
@@ -187,7 +198,7 @@ class OracleV3:
     def _hybrid_taps(self, x):
         """forward_vit -> forward_adapted_unflatten(pretrained, x, "forward_flex") (vit.py:19-85, utils.py:84-133)
         with the post-processing of _make_vit_b_rn50_backbone (vit.py:179-219, readout = "project")."""
-        m, sd, pp = self.encoder, self.sd, "depth_net.pretrained.act_postprocess"
+        m, sd, pp = self.encoder, self.sd, self.PREFIX + "pretrained.act_postprocess"
         b, c, h, w = x.shape
         gh, gw = h // 16, w // 16
         # _resize_pos_embed (vit.py:23-41)
@@ -236,7 +247,7 @@ class OracleV3:
 
     @torch.no_grad()
     def decoder(self, taps):
-        sd, s = self.sd, "depth_net.scratch."
+        sd, s = self.sd, self.PREFIX + "scratch."
         l1, l2, l3, l4 = [_conv(sd, f"{s}layer{i + 1}_rn", taps[i], 1) for i in range(4)]
         p4 = _fusion(sd, s + "refinenet4", [l4], l3.shape[2:])
         p3 = _fusion(sd, s + "refinenet3", [p4, l3], l2.shape[2:])
@@ -244,19 +255,26 @@ class OracleV3:
         return _fusion(sd, s + "refinenet1", [p2, l1], None)
 
     @torch.no_grad()
-    def heads(self, path_1):
-        sd, h = self.sd, "depth_net.scratch.output_conv."
+    def depth_head(self, path_1):
+        """DPTDepthModel head (dpt.py:199-219) + squeeze (dpt.py:226-232)."""
+        sd, h = self.sd, self.PREFIX + "scratch.output_conv."
         d = _conv(sd, h + "0", path_1, 1)
         d = F.interpolate(d, scale_factor=2, mode="bilinear", align_corners=True)
         d = F.relu(_conv(sd, h + "2", d, 1))
-        d = F.relu(_conv(sd, h + "4", d, 0)).squeeze(1)
-        g = _conv(sd, "seg_head.0", path_1, 1)
-        g = F.batch_norm(g, sd["seg_head.1.running_mean"], sd["seg_head.1.running_var"],
-                         sd["seg_head.1.weight"], sd["seg_head.1.bias"], False, 0.1, 1e-5)
-        g = _conv(sd, "seg_head.4", F.relu(g), 0)
+        return F.relu(_conv(sd, h + "4", d, 0)).squeeze(1)
+
+    @torch.no_grad()
+    def seg_head(self, path_1, h="seg_head."):
+        """conv3x3 (no bias) -> BN -> ReLU -> conv1x1 -> x2 bilinear -> sigmoid | scaled tanh (SOccDPT.py:660-674, dpt.py:242-252)."""
+        sd = self.sd
+        g = _bn(sd, h + "1", _conv(sd, h + "0", path_1, 1))
+        g = _conv(sd, h + "4", F.relu(g), 0)
         g = F.interpolate(g, scale_factor=2, mode="bilinear", align_corners=True)
-        g = torch.sigmoid(g) if self.sigmoid else 0.5 * torch.tanh(g) + 0.5
-        return d, g
+        return torch.sigmoid(g) if self.sigmoid else 0.5 * torch.tanh(g) + 0.5
+
+    @torch.no_grad()
+    def heads(self, path_1):
+        return self.depth_head(path_1), self.seg_head(path_1)
 
     @torch.no_grad()
     def network(self, x):
@@ -265,6 +283,32 @@ class OracleV3:
         path_1 = self.decoder(taps)
         d, g = self.heads(path_1)
         return d, g, path_1, taps
+
+    @torch.no_grad()
+    def __call__(self, x, threads=0):
+        d, g, _, _ = self.network(x)
+        return get_semantic_occupancy(d, g, self.geom, self.compute_occ, threads=threads)
+
+
+class _OracleSegDPT(OracleV3):
+    """the DPTSegmentationModel half of SOccDPT_V1: keys under ``seg_net.``, head = its own scratch.output_conv."""
+    PREFIX = "seg_net."
+
+
+class OracleV1:
+    """SOccDPT_V1 (SOccDPT.py:470-523): depth_net(x) and seg_net(x) are two complete DPTs, then get_semantic_occupancy."""
+
+    def __init__(self, state_dict, model_type="dpt_swin2_tiny_256", geom=None, compute_occ=True):
+        self.depth = OracleV3(state_dict, model_type, True, geom, compute_occ)
+        self.seg = _OracleSegDPT(state_dict, model_type, True, geom, compute_occ)
+        self.geom, self.compute_occ = self.depth.geom, compute_occ
+
+    @torch.no_grad()
+    def network(self, x):
+        """image -> (inv_depth (B,h,w), seg (B,C,h,w), depth path_1, seg path_1)"""
+        p_d = self.depth.decoder(self.depth.encoder_taps(x))
+        p_s = self.seg.decoder(self.seg.encoder_taps(x))
+        return self.depth.depth_head(p_d), self.seg.seg_head(p_s, "seg_net.scratch.output_conv."), p_d, p_s
 
     @torch.no_grad()
     def __call__(self, x, threads=0):

@@ -51,8 +51,16 @@ def _pack_conv(w, dev):
 
 
 class NetworkEngine:
-    def __init__(self, net, conv_impl="tcgen05"):
+    def __init__(self, net, conv_impl="tcgen05", dpt=None, seg_head=None, heads=("depth", "seg")):
+        """``dpt``: the DPT parameter container to run (default ``net.depth_net``); ``seg_head``: the segmentation head
+        Sequential (default ``net.seg_head``; SOccDPT_V1's segmentation network passes its own ``scratch.output_conv``);
+        ``heads``: which outputs the plan produces -- ("depth", "seg") for SOccDPT_V3's shared trunk, ("depth",) / ("seg",)
+        for the two networks of SOccDPT_V1 (SOccDPT.py:470-523)."""
         self.net = net
+        self.dpt = dpt if dpt is not None else net.depth_net
+        self.heads = tuple(heads)
+        assert self.heads and set(self.heads) <= {"depth", "seg"}
+        self.seg_head = seg_head if seg_head is not None else (getattr(net, "seg_head", None) if "seg" in self.heads else None)
         self.conv_impl = conv_impl        # "tcgen05" (product) | "ref" (CUDA-core cross-check, tests only)
         self._weights = None
         self._plans = {}
@@ -74,7 +82,7 @@ class NetworkEngine:
     # ------------------------------------------------------------------ weight packing
     def _pack(self, dev):
         net = self.net
-        enc = net.depth_net.pretrained.model
+        enc = self.dpt.pretrained.model
         W = {"stages": []}
         self.hybrid = not isinstance(enc, SwinV2Params)
         if self.hybrid:
@@ -94,7 +102,7 @@ class NetworkEngine:
         return ((flat - mean) * torch.rsqrt(var + conv.eps)).reshape_as(w)
 
     def _pack_hybrid(self, dev):
-        pre = self.net.depth_net.pretrained
+        pre = self.dpt.pretrained
         enc = pre.model
         bb = enc.patch_embed.backbone
         gn = lambda n: (_f32(n.weight, dev), _f32(n.bias, dev))
@@ -163,36 +171,49 @@ class NetworkEngine:
                           n=(_f32(layer.downsample.norm.weight, dev), _f32(layer.downsample.norm.bias, dev)))
             W["stages"].append(dict(dim=layer.dim, res=layer.input_resolution, blocks=blocks, down=ds))
 
+    @staticmethod
+    def _fold_bn(w, b, bn):
+        """eval-mode BatchNorm2d after a conv -> (scaled weight, bias): bn(conv(x) + b) = conv(x) * g + (b - mean) * g + beta."""
+        g = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+        b0 = b.detach().float() if b is not None else torch.zeros_like(g)
+        return w.detach().float() * g.view(-1, 1, 1, 1), (b0 - bn.running_mean.detach().float()) * g + bn.bias.detach().float()
+
+    def _pack_rcu(self, rcu, dev):
+        """ResidualConvUnit_custom (blocks.py:348-414); with ``use_bn`` (DPTSegmentationModel, dpt.py:240) each conv is followed
+        by a BatchNorm2d, folded into the conv here."""
+        out = []
+        for conv, bn in ((rcu.conv1, getattr(rcu, "bn1", None)), (rcu.conv2, getattr(rcu, "bn2", None))):
+            w, b = conv.weight, conv.bias
+            if bn is not None:
+                w, b = self._fold_bn(w, b, bn)
+            out += [_pack_conv(w, dev), _f32(b, dev)]
+        return tuple(out)
+
     def _pack_decoder(self, W, dev):
-        net = self.net
-        sc = net.depth_net.scratch
+        sc = self.dpt.scratch
         W["rn"] = [_pack_conv(getattr(sc, f"layer{i}_rn").weight, dev) for i in (1, 2, 3, 4)]
         W["fusion"] = {}
         for i in (1, 2, 3, 4):
             f = getattr(sc, f"refinenet{i}")
             W["fusion"][i] = dict(
                 out_w=_pack_conv(f.out_conv.weight, dev), out_b=_f32(f.out_conv.bias, dev),
-                rcu1=(_pack_conv(f.resConfUnit1.conv1.weight, dev), _f32(f.resConfUnit1.conv1.bias, dev),
-                      _pack_conv(f.resConfUnit1.conv2.weight, dev), _f32(f.resConfUnit1.conv2.bias, dev)),
-                rcu2=(_pack_conv(f.resConfUnit2.conv1.weight, dev), _f32(f.resConfUnit2.conv1.bias, dev),
-                      _pack_conv(f.resConfUnit2.conv2.weight, dev), _f32(f.resConfUnit2.conv2.bias, dev)))
-        oc = sc.output_conv
-        # conv 2 of the head acts on a bilinear upsample: apply its nine tap matrices at low resolution instead
-        # (rows = tap*32 + c), the gather kernel interpolates and sums them (csrc/depth_head.cu)
-        w2 = oc[2].weight.detach().float()                       # (32, 128, 3, 3)
-        w2t = w2.permute(2, 3, 0, 1).reshape(9 * w2.shape[0], w2.shape[1], 1, 1)
-        W["dh"] = dict(w0=_pack_conv(oc[0].weight, dev), b0=_f32(oc[0].bias, dev),
-                       w2t=_pack_conv(w2t, dev), b2=_f32(oc[2].bias, dev),
-                       pw=_f32(oc[4].weight.reshape(1, -1), dev), pb=_f32(oc[4].bias, dev))
-        sh = net.seg_head
-        bn = sh[1]
-        inv_std = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
-        g = bn.weight.detach().float() * inv_std
-        W["sh"] = dict(w0=_pack_conv(sh[0].weight.detach().float() * g.view(-1, 1, 1, 1), dev),
-                       b0=_f32(bn.bias.detach().float() - bn.running_mean.detach().float() * g, dev),
-                       pw=_f32(sh[4].weight.reshape(sh[4].weight.shape[0], -1), dev), pb=_f32(sh[4].bias, dev))
-        W["num_classes"] = sh[4].weight.shape[0]
-        W["seg_act"] = 0 if isinstance(sh[6], torch.nn.Sigmoid) else 1
+                rcu1=self._pack_rcu(f.resConfUnit1, dev), rcu2=self._pack_rcu(f.resConfUnit2, dev))
+        if "depth" in self.heads:
+            oc = sc.output_conv
+            # conv 2 of the head acts on a bilinear upsample: apply its nine tap matrices at low resolution instead
+            # (rows = tap*32 + c), the gather kernel interpolates and sums them (csrc/depth_head.cu)
+            w2 = oc[2].weight.detach().float()                       # (32, 128, 3, 3)
+            w2t = w2.permute(2, 3, 0, 1).reshape(9 * w2.shape[0], w2.shape[1], 1, 1)
+            W["dh"] = dict(w0=_pack_conv(oc[0].weight, dev), b0=_f32(oc[0].bias, dev),
+                           w2t=_pack_conv(w2t, dev), b2=_f32(oc[2].bias, dev),
+                           pw=_f32(oc[4].weight.reshape(1, -1), dev), pb=_f32(oc[4].bias, dev))
+        if "seg" in self.heads:
+            sh = self.seg_head
+            w0, b0 = self._fold_bn(sh[0].weight, sh[0].bias, sh[1])
+            W["sh"] = dict(w0=_pack_conv(w0, dev), b0=_f32(b0, dev),
+                           pw=_f32(sh[4].weight.reshape(sh[4].weight.shape[0], -1), dev), pb=_f32(sh[4].bias, dev))
+            W["num_classes"] = sh[4].weight.shape[0]
+            W["seg_act"] = 0 if isinstance(sh[6], torch.nn.Sigmoid) else 1
 
     # ------------------------------------------------------------------ plan construction
     def _conv(self, plan, x, w, N, H, Wd, Cin, Cout, K, bias=None, act=_cabi.ACT_NONE, res1=None, res2=None, y=None,
@@ -371,7 +392,7 @@ class NetworkEngine:
             plan["keep"].append(t)
             return t
 
-        enc = self.net.depth_net.pretrained.model
+        enc = self.dpt.pretrained.model
         img = enc.img_size
         plan["img"] = img
         x_in = buf(B, 3, img, img, dtype=torch.float32)
@@ -380,7 +401,7 @@ class NetworkEngine:
         plan["taps"] = taps
 
         # ---------------- decoder (dpt.py:152-172)
-        F = self.net.depth_net.features
+        F = self.dpt.features
         lv = []
         for i, (t, Hs, Ws, C) in enumerate(taps):
             y, yr = buf(B, Hs, Ws, F), buf(B, Hs, Ws, F)
@@ -413,22 +434,27 @@ class NetworkEngine:
         plan["path_1"] = path
 
         # ---------------- heads
-        dh, sh = Wt["dh"], Wt["sh"]
-        d0 = buf(B, PH, PW, F // 2)
-        self._conv(plan, path, dh["w0"], B, PH, PW, F, F // 2, 3, bias=dh["b0"], y=d0)
-        assert dh["w2t"].shape[0] == 9 * 32, "depth head: head_features_2 must be 32"
-        taps = buf(B, PH, PW, 9 * 32)
-        self._conv(plan, d0, dh["w2t"], B, PH, PW, F // 2, 9 * 32, 1, y=taps)
-        depth = buf(B, 2 * PH, 2 * PW, dtype=torch.float32)
-        ops.append(_Launch("depth_tail", lib.soccdpt_depth_tail_fwd, taps.data_ptr(), dh["b2"].data_ptr(), dh["pw"].data_ptr(),
-                           dh["pb"].data_ptr(), depth.data_ptr(), B, PH, PW))
-        P = Wt["num_classes"]
-        logits = buf(B, PH, PW, P, dtype=torch.float32)
-        self._conv(plan, path, sh["w0"], B, PH, PW, F, F, 3, bias=sh["b0"], act=_cabi.ACT_RELU,
-                   proj=(sh["pw"], sh["pb"], logits, False))
-        seg = buf(B, P, 2 * PH, 2 * PW, dtype=torch.float32)
-        ops.append(_Launch("seg_finish", lib.soccdpt_seg_finish_fwd, logits.data_ptr(), seg.data_ptr(), B, PH, PW, P, Wt["seg_act"]))
-        plan["depth"], plan["seg"] = depth, seg
+        plan["depth"] = plan["seg"] = None
+        if "depth" in self.heads:
+            dh = Wt["dh"]
+            d0 = buf(B, PH, PW, F // 2)
+            self._conv(plan, path, dh["w0"], B, PH, PW, F, F // 2, 3, bias=dh["b0"], y=d0)
+            assert dh["w2t"].shape[0] == 9 * 32, "depth head: head_features_2 must be 32"
+            taps = buf(B, PH, PW, 9 * 32)
+            self._conv(plan, d0, dh["w2t"], B, PH, PW, F // 2, 9 * 32, 1, y=taps)
+            depth = buf(B, 2 * PH, 2 * PW, dtype=torch.float32)
+            ops.append(_Launch("depth_tail", lib.soccdpt_depth_tail_fwd, taps.data_ptr(), dh["b2"].data_ptr(), dh["pw"].data_ptr(),
+                               dh["pb"].data_ptr(), depth.data_ptr(), B, PH, PW))
+            plan["depth"] = depth
+        if "seg" in self.heads:
+            sh = Wt["sh"]
+            P = Wt["num_classes"]
+            logits = buf(B, PH, PW, P, dtype=torch.float32)
+            self._conv(plan, path, sh["w0"], B, PH, PW, F, F, 3, bias=sh["b0"], act=_cabi.ACT_RELU,
+                       proj=(sh["pw"], sh["pb"], logits, False))
+            seg = buf(B, P, 2 * PH, 2 * PW, dtype=torch.float32)
+            ops.append(_Launch("seg_finish", lib.soccdpt_seg_finish_fwd, logits.data_ptr(), seg.data_ptr(), B, PH, PW, P, Wt["seg_act"]))
+            plan["seg"] = seg
         return plan
 
     # ------------------------------------------------------------------ run

@@ -2,6 +2,7 @@
 keywords, output tuple, attribute names and state_dict keys -- with the arithmetic on B200 kernels.
 
     SOccDPT        base class: geometry constants + get_semantic_occupancy      (SOccDPT.py:133-463)
+    SOccDPT_V1     two complete DPT networks (depth, segmentation) on one voxeliser  (SOccDPT.py:470-523)
     SOccDPT_V3     DPT depth net with return_features + segmentation head        (SOccDPT.py:626-685)
     DepthNet/SegNet adaptors picking tuple element 0 / 1                         (SOccDPT.py:697-724)
 
@@ -22,7 +23,7 @@ from .. import _cabi
 from ..engine import NetworkEngine
 from ..geometry import load_calib, make_geometry
 from .base_model import BaseModel
-from .dpt import DPTDepthModel
+from .dpt import DPTDepthModel, DPTSegmentationModel, Interpolate
 
 cpu_device = torch.device("cpu")
 
@@ -36,19 +37,15 @@ default_depth_models = {
 }
 model_types = default_depth_models.keys()
 
-DEPTH_l39icv3q = "checkpoints_pretrained/depth_dpt_hybrid/l39icv3q/checkpoint_epoch15.pth"  # reference default
+# SOccDPT.py:43-55: no segmentation checkpoints are published for any model type
+default_seg_models = {k: None for k in default_depth_models}
+
+DEPTH_l39icv3q = "checkpoints_pretrained/depth_dpt_hybrid/l39icv3q/checkpoint_epoch15.pth"  # reference defaults
+SEG_wrlnq5jb = "checkpoints_pretrained/seg_dpt_hybrid/wrlnq5jb/checkpoint_epoch15.pth"
 
 
 class ScaledTanh(nn.Module):
     """0.5*tanh(x)+0.5 (reference scaled_tanh.py:8-10); marker module, evaluated in seg_finish_kernel."""
-
-
-class Interpolate(nn.Module):
-    """Marker for the x2 bilinear (align_corners=True) stage of the heads (reference blocks.py:239-273)."""
-
-    def __init__(self, scale_factor, mode, align_corners=False):
-        super().__init__()
-        self.scale_factor, self.mode, self.align_corners = scale_factor, mode, align_corners
 
 
 class SOccDPT(BaseModel):
@@ -190,7 +187,95 @@ def ctypes_byref(s):
     return ctypes.byref(s)
 
 
-class SOccDPT_V3(SOccDPT):
+class _EngineOwner:
+    """Weights changed (load_state_dict / .to()) -> the engines repack on the next forward."""
+
+    def _engines(self):
+        return [e for e in (getattr(self, "_engine", None), getattr(self, "_seg_engine", None)) if e is not None]
+
+    def _invalidate(self):
+        for e in self._engines():
+            e.invalidate()
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._invalidate()
+        return out
+
+    def _conv_impl(self, conv_impl):
+        return conv_impl or os.environ.get("SOCCDPT_CONV_IMPL", "tcgen05")
+
+
+class SOccDPT_V1(_EngineOwner, SOccDPT):
+    """Two independent DPT networks -- ``depth_net`` (DPTDepthModel) and ``seg_net`` (DPTSegmentationModel, BatchNorm in its
+    residual conv units) -- feeding the shared resize + unproject + voxelise stage (SOccDPT.py:470-523).  Each network is its
+    own launch plan over the same kernels as SOccDPT_V3; the segmentation plan runs on a second CUDA stream so the two
+    encoders / decoders overlap on the GPU."""
+
+    def __init__(self, load_depth: str = DEPTH_l39icv3q, load_seg: str = SEG_wrlnq5jb, **kwargs):
+        super(SOccDPT_V1, self).__init__(**kwargs)
+        from .loader import load_model
+
+        depth_model_weights = load_depth
+        if depth_model_weights is None:
+            depth_model_weights = default_depth_models[self.model_type]
+        self.depth_net = load_model(DPTDepthModel, dict(non_negative=True, return_features=False), cpu_device,
+                                    depth_model_weights, self.model_type)
+        self.pretrained = self.depth_net.pretrained     # alias, as in the reference (SOccDPT.py:496)
+
+        seg_model_weights = load_seg
+        if seg_model_weights is None:
+            seg_model_weights = default_seg_models[self.model_type]
+        self.seg_net = load_model(DPTSegmentationModel, dict(num_classes=self.num_classes), cpu_device,
+                                  seg_model_weights, self.model_type)
+        self._engine = None
+        self._seg_engine = None
+        self._side_streams = {}
+        self.load_net(self.path)
+
+    def engine(self, conv_impl=None):
+        """the depth network's engine (``seg_engine()`` is the other one)."""
+        impl = self._conv_impl(conv_impl)
+        if self._engine is None or (conv_impl is not None and self._engine.conv_impl != impl):
+            self._engine = NetworkEngine(self, impl, dpt=self.depth_net, heads=("depth",))
+        return self._engine
+
+    def seg_engine(self, conv_impl=None):
+        impl = self._conv_impl(conv_impl)
+        if self._seg_engine is None or (conv_impl is not None and self._seg_engine.conv_impl != impl):
+            self._seg_engine = NetworkEngine(self, impl, dpt=self.seg_net, seg_head=self.seg_net.scratch.output_conv,
+                                             heads=("seg",))
+        return self._seg_engine
+
+    def network(self, x, conv_impl=None):
+        """image -> (depth_net(x) (B,h,w) f32, seg_net(x) (B,C,h,w) f32), SOccDPT.py:519-520.  Static engine buffers."""
+        if self.training:
+            raise _cabi.SoccdptError("soccdpt_b200 implements the inference path only: call net.eval() first")
+        if not x.is_cuda:
+            raise _cabi.SoccdptError("soccdpt_b200 runs on CUDA devices only (no CPU fallback)")
+        main = torch.cuda.current_stream(x.device)
+        side = self._side_streams.get(x.device)
+        if side is None:
+            side = self._side_streams[x.device] = torch.cuda.Stream(device=x.device)
+        side.wait_stream(main)                          # x is ready on the caller's stream
+        with torch.cuda.stream(side):
+            _, segmentation = self.seg_engine(conv_impl).run(x)
+        x.record_stream(side)
+        inv_depth, _ = self.engine(conv_impl).run(x)
+        main.wait_stream(side)
+        return inv_depth, segmentation
+
+    def forward(self, x: torch.Tensor):
+        inv_depth, segmentation = self.network(x)
+        return self.get_semantic_occupancy(inv_depth, segmentation)
+
+
+class SOccDPT_V3(_EngineOwner, SOccDPT):
     def __init__(self, sigmoid=True, load_depth: str = DEPTH_l39icv3q, **kwargs):
         super(SOccDPT_V3, self).__init__(**kwargs)
         from .loader import load_model
@@ -217,24 +302,9 @@ class SOccDPT_V3(SOccDPT):
         self._engine = None
         self.load_net(self.path)
 
-    # weights changed -> repack on the next forward
-    def _invalidate(self):
-        if getattr(self, "_engine", None) is not None:
-            self._engine.invalidate()
-
-    def load_state_dict(self, *args, **kwargs):
-        out = super().load_state_dict(*args, **kwargs)
-        self._invalidate()
-        return out
-
-    def _apply(self, fn, *args, **kwargs):
-        out = super()._apply(fn, *args, **kwargs)
-        self._invalidate()
-        return out
-
     def engine(self, conv_impl=None):
         if self._engine is None or (conv_impl is not None and self._engine.conv_impl != conv_impl):
-            self._engine = NetworkEngine(self, conv_impl or os.environ.get("SOCCDPT_CONV_IMPL", "tcgen05"))
+            self._engine = NetworkEngine(self, self._conv_impl(conv_impl))
         return self._engine
 
     def network(self, x):
@@ -249,7 +319,8 @@ class SOccDPT_V3(SOccDPT):
         return self.get_semantic_occupancy(inv_depth, segmentation)
 
 
-SOccDPT_versions = {3: SOccDPT_V3}
+# SOccDPT_V2 is not constructible in the reference either (``seg_ead`` / ``seg_head`` typo, SOccDPT.py:580-621)
+SOccDPT_versions = {1: SOccDPT_V1, 3: SOccDPT_V3}
 
 
 class DepthNet:

@@ -51,7 +51,9 @@ def seeded_state_dict(state_dict, seed=0, residual_gain=1.0):
         if k.endswith("attn_mask") or k.endswith("num_batches_tracked"):
             out[k] = v.detach().clone().cpu()
             continue
-        is_norm = (".norm" in k) or k.startswith("seg_head.1.")
+        # BatchNorms: SOccDPT_V3's seg head; SOccDPT_V1's segmentation DPT (residual conv units, head, auxlayer)
+        is_norm = (".norm" in k) or k.startswith("seg_head.1.") or (
+            k.startswith("seg_net.") and (".bn1." in k or ".bn2." in k or ".output_conv.1." in k or ".auxlayer.1." in k))
         if k.endswith("running_mean"):
             t = torch.randn(shape, generator=g) * 0.1
         elif k.endswith("running_var"):
@@ -75,9 +77,9 @@ def seeded_state_dict(state_dict, seed=0, residual_gain=1.0):
         # land inside the 128 m x 128 m x 48 m occupancy volume instead of the never-filled k=0 plane
         if residual_gain != 1.0 and (k.endswith(".norm3.weight") or k.endswith(".norm3.bias")):
             t = t * residual_gain
-        if k.endswith("scratch.output_conv.4.weight"):
+        if k.endswith("scratch.output_conv.4.weight") and not k.startswith("seg_net."):
             t = t * 0.03
-        if k.endswith("scratch.output_conv.4.bias"):
+        if k.endswith("scratch.output_conv.4.bias") and not k.startswith("seg_net."):
             t = t * 0.1 + 0.05
         out[k] = t.to(torch.float32)
     for k in state_dict.keys():

@@ -35,10 +35,10 @@ def occupied_list(grid):
     return np.argwhere(g != 0).astype(np.int16)
 
 
-def tiny_state_dict(seed=0):
+def tiny_state_dict(seed=0, keys_file="state_keys_tiny.txt", encoder_prefixes=("depth_net.pretrained.model.", "pretrained.model.")):
     """The seeded weights of golden/net_tiny_b2.npz, rebuilt from the recorded key/shape list."""
     shapes = {}
-    with open(os.path.join(GOLD, "state_keys_tiny.txt")) as f:
+    with open(os.path.join(GOLD, keys_file)) as f:
         for line in f:
             k, shp = line.rstrip("\n").split(" ", 1)
             shapes[k] = ast.literal_eval(shp)
@@ -58,7 +58,13 @@ def tiny_state_dict(seed=0):
     m = timm.create_model("swinv2_tiny_window16_256")
     for k, v in m.state_dict().items():
         if k.endswith("attn_mask"):
-            sd["depth_net.pretrained.model." + k] = v.clone()
-            sd["pretrained.model." + k] = v.clone()
+            for pfx in encoder_prefixes:
+                sd[pfx + k] = v.clone()
     del enc
     return seeded_state_dict(sd, seed)
+
+
+def v1_tiny_state_dict(seed=0):
+    """The seeded SOccDPT_V1 weights of golden/net_v1_tiny_b2.npz (two DPTs: depth_net.* (+ pretrained.* alias), seg_net.*)."""
+    return tiny_state_dict(seed, "state_keys_v1_tiny.txt",
+                           ("depth_net.pretrained.model.", "pretrained.model.", "seg_net.pretrained.model."))

@@ -17,11 +17,12 @@ def main():
     ap.add_argument("--model", default="dpt_hybrid_384")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--version", type=int, default=3, choices=(1, 3), help="SOccDPT_V1 (two DPTs, two streams) or SOccDPT_V3")
     a = ap.parse_args()
     yml = write_calib_yaml("/tmp/bench_models_calib.yaml")
-    net = load_model(arch=SOccDPT_versions[3],
-                     model_kwargs=dict(load_depth=False, num_classes=3, sigmoid=True, compute_occ=True,
-                                       camera_intrinsics_yaml=yml, model_type=a.model),
+    kw = dict(load_depth=False, num_classes=3, compute_occ=True, camera_intrinsics_yaml=yml, model_type=a.model)
+    kw.update(dict(sigmoid=True) if a.version == 3 else dict(load_seg=False))
+    net = load_model(arch=SOccDPT_versions[a.version], model_kwargs=kw,
                      device=torch.device("cpu"), model_path=None, model_type=a.model)
     net.load_state_dict(seeded_state_dict(net.state_dict(), 0, residual_gain=0.1), strict=True)
     net.to("cuda").eval()
@@ -38,7 +39,7 @@ def main():
         e.record()
         torch.cuda.synchronize()
         ms = s.elapsed_time(e) / a.iters
-        print(f"{a.model} B={a.batch}: {ms:.3f} ms/step network only -> {a.batch / ms * 1e3:.1f} frames/s")
+        print(f"V{a.version} {a.model} B={a.batch}: {ms:.3f} ms/step network only -> {a.batch / ms * 1e3:.1f} frames/s")
         for _ in range(2):
             net(x)
         torch.cuda.synchronize()
@@ -48,7 +49,15 @@ def main():
         e.record()
         torch.cuda.synchronize()
         ms2 = s.elapsed_time(e) / a.iters
-        print(f"{a.model} B={a.batch}: {ms2:.3f} ms/step image -> occupancy -> {a.batch / ms2 * 1e3:.1f} frames/s")
+        print(f"V{a.version} {a.model} B={a.batch}: {ms2:.3f} ms/step image -> occupancy -> {a.batch / ms2 * 1e3:.1f} frames/s")
+        if a.version == 1:
+            for name, eng in (("depth DPT", net.engine()), ("segmentation DPT", net.seg_engine())):
+                s.record()
+                for _ in range(a.iters):
+                    eng.run(x)
+                e.record()
+                torch.cuda.synchronize()
+                print(f"  {name} alone on one stream: {s.elapsed_time(e) / a.iters:.3f} ms/step")
         # per-family breakdown: every op bracketed by events (serialising, so the sum exceeds the step time a little)
         from soccdpt_b200 import _cabi
         plan = net.engine().plan_for(a.batch, x.device)

@@ -39,6 +39,13 @@ const char *soccdpt_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long soccdpt_launch_count(void);
 int soccdpt_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* programmatic dependent launch between the kernels of a launch plan (csrc/common.cuh), per kernel family:
+ * mask bits 1 = implicit-GEMM conv / linear, 2 = attention, 4 = normalisation / element-wise, 8 = post-processing;
+ * 0 = plain stream order everywhere, negative = back to the default (SOCCDPT_PDL in the environment, else
+ * SOCCDPT_PDL_DEFAULT).  Returns the previous mask.  No reference counterpart: the reference's eager PyTorch ops are
+ * stream-ordered (every kernel boundary a full drain). */
+#define SOCCDPT_PDL_DEFAULT 15
+int soccdpt_set_pdl(int mask);
 
 /* ------------------------------------------------------------------ sparse occupancy outputs
  * The reference's occupancy_grid_to_points (SOccDPT/utils/__init__.py:532-568, numpy on the CPU) on the device:

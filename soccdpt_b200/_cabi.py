@@ -51,6 +51,7 @@ SYMBOLS = {
     "soccdpt_abi_version": (_I, []),
     "soccdpt_last_error": (ctypes.c_char_p, []),
     "soccdpt_launch_count": (_LL, []),
+    "soccdpt_set_pdl": (_I, [_I]),
     "soccdpt_device_info": (_I, [ctypes.POINTER(_I)] * 3),
     "soccdpt_preprocess_workspace_bytes": (_SZ, [_I, _I]),
     "soccdpt_preprocess_fwd": (_I, [c_void_p, _I, _I, _I, _I, c_void_p, _I, _I, c_void_p, _SZ, c_void_p]),

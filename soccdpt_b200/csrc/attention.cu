@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(256)
 window_attention_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ bias_tab, const float *__restrict__ scale,
                         bf16 *__restrict__ out, int Hs, int Ws, int C, int ws, int shift) {
     extern __shared__ float smem[];
+    soccdpt::pdl_wait();
     const int N = ws * ws;
     float *Ks = smem;                 // [N][32]
     float *Vs = smem + (size_t)N * D; // [N][32]
@@ -188,7 +189,7 @@ extern "C" int soccdpt_window_attention_fwd(const void *qkv, const float *bias, 
         configured = smem;
     }
     dim3 grid((unsigned)(batch * (Hs / ws) * (Ws / ws)), (unsigned)heads);
-    window_attention_kernel<<<grid, threads, smem, soccdpt::as_stream(stream)>>>(
-        static_cast<const bf16 *>(qkv), bias, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift);
+    SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ATTENTION, window_attention_kernel, grid, dim3(threads), smem, soccdpt::as_stream(stream),
+                                     static_cast<const bf16 *>(qkv), bias, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift));
     return soccdpt::check_launch("window_attention_kernel");
 }

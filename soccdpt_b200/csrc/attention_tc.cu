@@ -203,6 +203,7 @@ window_attention_tc_kernel(const bf16 *__restrict__ qkv, const float *__restrict
                 pack8_scaled(q + c2 * 8, qs);
     };
 
+    soccdpt::pdl_wait();        // qkv is the previous kernel's output
     // ---- prologue: every global load of the CTA's start-up is issued before anything waits on one of them
     int region, dummy;
     const long long tok_k = token_of(t, region);
@@ -408,11 +409,11 @@ int launch_window_attention_tc(const void *qkv, const float *bias_tab, const flo
     }
     dim3 grid((unsigned)(batch * (Hs / ws) * (Ws / ws)), (unsigned)heads);
     if (shift > 0)
-        window_attention_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(
-            static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift);
+        SOCCDPT_CUDA(launch_pdl(PDL_ATTENTION, window_attention_tc_kernel<true>, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st,
+                                static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift));
     else
-        window_attention_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(
-            static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift);
+        SOCCDPT_CUDA(launch_pdl(PDL_ATTENTION, window_attention_tc_kernel<false>, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st,
+                                static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, ws, shift));
     return check_launch("window_attention_tc_kernel");
 }
 }  // namespace soccdpt

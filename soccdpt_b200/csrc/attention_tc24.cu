@@ -280,6 +280,7 @@ window_attention_tc24_kernel(const bf16 *__restrict__ qkv, const float *__restri
         }
     };
 
+    soccdpt::pdl_wait();        // qkv is the previous kernel's output
     // ---- prologue: every global load of the CTA's start-up is issued before anything waits on one of them
     const bool softmax_warp = warp < THREADS / 32;
     const float sc = scale[head];
@@ -544,11 +545,11 @@ int launch_window_attention_tc24(const void *qkv, const float *bias_tab, const f
     }
     dim3 grid((unsigned)(batch * (Hs / WS) * (Ws / WS)), (unsigned)heads);
     if (shift > 0)
-        window_attention_tc24_kernel<true><<<grid, CTA_THREADS, SMEM_BYTES, st>>>(
-            static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, shift);
+        SOCCDPT_CUDA(launch_pdl(PDL_ATTENTION, window_attention_tc24_kernel<true>, grid, dim3(CTA_THREADS), SMEM_BYTES, st,
+                                static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, shift));
     else
-        window_attention_tc24_kernel<false><<<grid, CTA_THREADS, SMEM_BYTES, st>>>(
-            static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, shift);
+        SOCCDPT_CUDA(launch_pdl(PDL_ATTENTION, window_attention_tc24_kernel<false>, grid, dim3(CTA_THREADS), SMEM_BYTES, st,
+                                static_cast<const bf16 *>(qkv), bias_tab, scale, static_cast<bf16 *>(out), Hs, Ws, C, shift));
     return check_launch("window_attention_tc24_kernel");
 }
 }  // namespace soccdpt

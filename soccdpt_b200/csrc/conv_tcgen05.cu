@@ -304,6 +304,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barriers, TMEM, tensor-map fetch) overlapped the previous kernel's tail; its outputs from here on
+    soccdpt::pdl_wait();
 
     const int taps = c.KH * c.KW;
     const int k_blocks = taps * p.k_blocks_per_tap;
@@ -479,6 +481,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
             const int cout0 = nb * p.block_n;
+            if (tile + (int)gridDim.x >= p.total_tiles) soccdpt::pdl_trigger();   // this CTA's last tile: let the next kernel in
             if (nb != cached_nb) {
                 // per-channel constants of this N block -> smem (visible to the 256 epilogue threads only)
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -770,7 +773,8 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
                                               SMEM_BYTES));                                                             \
             configured = true;                                                                                          \
         }                                                                                                               \
-        conv_tcgen05_kernel<A, M, HL><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, map_y, map_yr, p);                           \
+        SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_CONV, conv_tcgen05_kernel<A, M, HL>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, map_a, map_b, \
+                                         map_y, map_yr, p));                                                            \
     } while (0)
 #define SOCC_MODES(A)                                                    \
     do {                                                                 \

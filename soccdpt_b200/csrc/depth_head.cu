@@ -34,6 +34,7 @@ depth_tail_kernel(const bf16 *__restrict__ T, const float *__restrict__ b2, cons
         s_b2[threadIdx.x] = b2[threadIdx.x];
         s_pw[threadIdx.x] = pw[threadIdx.x];
     }
+    soccdpt::pdl_wait();        // constants above; T below is the previous kernel's output
     const int H = 2 * h, W = 2 * w;
     const int Y = blockIdx.x % H, n = blockIdx.x / H;
     const float sh = (float)(h - 1) / (float)(H - 1), sw = (float)(w - 1) / (float)(W - 1);   // align_corners=True
@@ -119,7 +120,7 @@ extern "C" int soccdpt_depth_tail_fwd(const void *T, const float *b2, const floa
         SOCCDPT_CUDA(cudaFuncSetAttribute(depth_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    depth_tail_kernel<<<(unsigned)(N * 2 * h), 256, smem, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(T), b2, pw, pb,
-                                                                                       depth, N, h, w);
+    SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, depth_tail_kernel, dim3((unsigned)(N * 2 * h)), dim3(256), smem, soccdpt::as_stream(stream),
+                                     static_cast<const bf16 *>(T), b2, pw, pb, depth, N, h, w));
     return soccdpt::check_launch("depth_tail_kernel");
 }

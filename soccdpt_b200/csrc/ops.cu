@@ -105,6 +105,7 @@ patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w, con
         const int e = i / 48, k = i - e * 48;
         pe_smem[((k >> 2) * E + e) * 4 + (k & 3)] = w[i];
     }
+    soccdpt::pdl_wait();        // the weights above are constants; the frames below may come from the previous kernel
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ph = H / 4, pw = W / 4;
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const bf16 *__restrict__ t, const bf16 *__restrict__ res, float *__restrict__ master, int accumulate,
                  const float *__restrict__ gamma, const float *__restrict__ beta, bf16 *__restrict__ y, long long rows,
                  int C, float eps) {
+    soccdpt::pdl_wait();
     const int gl = threadIdx.x % G;                              // lane inside the group
     const long long row = (long long)blockIdx.x * (256 / G) + threadIdx.x / G;
     const bool live = row < rows;                                // keep dead groups in the shuffles
@@ -249,8 +251,8 @@ layernorm_kernel(const bf16 *__restrict__ t, const bf16 *__restrict__ res, float
 int launch_layernorm(const bf16 *t, const bf16 *res, float *master, int accumulate, const float *gamma, const float *beta,
                      bf16 *y, long long rows, int C, float eps, cudaStream_t st) {
 #define SOCC_LN(G, IT)                                                                                              \
-    layernorm_kernel<G, IT><<<(unsigned)((rows + (256 / G) - 1) / (256 / G)), 256, 0, st>>>(t, res, master, accumulate, \
-                                                                                            gamma, beta, y, rows, C, eps)
+    SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, layernorm_kernel<G, IT>, dim3((unsigned)((rows + (256 / G) - 1) / (256 / G))), dim3(256), 0, \
+                                     st, t, res, master, accumulate, gamma, beta, y, rows, C, eps))
     if (C <= 128) SOCC_LN(16, 1);
     else if (C <= 256) SOCC_LN(32, 1);
     else if (C <= 512) SOCC_LN(32, 2);
@@ -285,6 +287,7 @@ patch_merge_gather_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, int 
 // pixel.  32-bit index math only (the first version spent five emulated 64-bit divisions per 16 output bytes).
 __global__ void __launch_bounds__(256)
 upsample_bilinear_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, unsigned rows, int h, int w, int H, int W, int C) {
+    soccdpt::pdl_wait();
     const unsigned chunks = (unsigned)C / 8u;
     for (unsigned row = blockIdx.y; row < rows; row += gridDim.y) {
     const unsigned n = row / (unsigned)H, Y = row - n * (unsigned)H;
@@ -322,6 +325,7 @@ upsample_bilinear_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, unsig
 // by its L1 traffic).  Row / column groups: {0}, {1,2}, ..., {2h-3, 2h-2}, {2h-1}: h + 1 of them.
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, unsigned N, int h, int w, int C) {
+    soccdpt::pdl_wait();
     const int H = 2 * h, W = 2 * w;
     const unsigned chunks = (unsigned)C / 8u, gw = (unsigned)w + 1u, gh = (unsigned)h + 1u;
     const float sh = (float)(h - 1) / (float)(H - 1), sw = (float)(w - 1) / (float)(W - 1);
@@ -375,6 +379,7 @@ upsample2x_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, unsigned N, 
 // channel, and every class plane gets one float4 store.
 __global__ void __launch_bounds__(256)
 seg_finish_kernel(const float *__restrict__ lg, float *__restrict__ seg, int N, int h, int w, int P, int act) {
+    soccdpt::pdl_wait();
     const int H = 2 * h, W = 2 * w;
     const int W4 = W / 4;
     const long long total = (long long)N * H * W4;
@@ -478,8 +483,8 @@ int soccdpt_patch_embed_fwd(const float *x, const float *w, const float *b, cons
     const long long cap = (long long)soccdpt::sm_count() * 8;
     if (blocks > cap) blocks = cap;
     const size_t smem = (size_t)(48 * E + 8 * PE_TOK * 48) * sizeof(float);
-    patch_embed_kernel<<<(unsigned)blocks, 256, smem, soccdpt::as_stream(stream)>>>(
-        x, w, b, ln_w, ln_b, static_cast<bf16 *>(tokens), tokens_f32, batch, H, W, E);
+    SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, patch_embed_kernel, dim3((unsigned)blocks), dim3(256), smem, soccdpt::as_stream(stream), x, w, b,
+                                     ln_w, ln_b, static_cast<bf16 *>(tokens), tokens_f32, batch, H, W, E));
     return soccdpt::check_launch("patch_embed_kernel");
 }
 
@@ -515,14 +520,15 @@ int soccdpt_upsample_bilinear_fwd(const void *x, void *y, int N, int h, int w, i
         const unsigned groups = (unsigned)N * (unsigned)(h + 1);
         const unsigned per_group = (unsigned)(((long long)(w + 1) * (C / 8) + 255) / 256);
         dim3 grid(per_group < 64u ? per_group : 64u, groups < 65535u ? groups : 65535u);
-        upsample2x_kernel<<<grid, 256, 0, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(x), static_cast<bf16 *>(y), (unsigned)N, h, w, C);
+        SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, upsample2x_kernel, grid, dim3(256), 0, soccdpt::as_stream(stream), static_cast<const bf16 *>(x),
+                                         static_cast<bf16 *>(y), (unsigned)N, h, w, C));
         return soccdpt::check_launch("upsample2x_kernel");
     }
     const unsigned per_row = (unsigned)(((long long)W * (C / 8) + 255) / 256), rows = (unsigned)N * (unsigned)H;
     const unsigned gx = (per_row + 3u) / 4u;            // ~4 items per thread: more loads in flight, setup amortised
     dim3 grid(gx < 64u ? gx : 64u, rows < 65535u ? rows : 65535u);
-    upsample_bilinear_kernel<<<grid, 256, 0, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(x), static_cast<bf16 *>(y), rows, h,
-                                                                          w, H, W, C);
+    SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, upsample_bilinear_kernel, grid, dim3(256), 0, soccdpt::as_stream(stream),
+                                     static_cast<const bf16 *>(x), static_cast<bf16 *>(y), rows, h, w, H, W, C));
     return soccdpt::check_launch("upsample_bilinear_kernel");
 }
 
@@ -531,7 +537,8 @@ int soccdpt_seg_finish_fwd(const float *logits, float *seg, int N, int h, int w,
     SOCCDPT_REQUIRE(logits && seg && N >= 1 && h >= 2 && w >= 2 && P >= 1 && P <= 4 && (act == 0 || act == 1),
                     "seg_finish: bad arguments");
     SOCCDPT_REQUIRE(w % 2 == 0 && (reinterpret_cast<uintptr_t>(seg) & 15) == 0, "seg_finish: w must be even and seg 16-byte aligned");
-    seg_finish_kernel<<<grid_for((long long)N * h * w), 256, 0, soccdpt::as_stream(stream)>>>(logits, seg, N, h, w, P, act);
+    SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, seg_finish_kernel, dim3(grid_for((long long)N * h * w)), dim3(256), 0, soccdpt::as_stream(stream),
+                                     logits, seg, N, h, w, P, act));
     return soccdpt::check_launch("seg_finish_kernel");
 }
 

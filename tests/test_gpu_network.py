@@ -135,3 +135,31 @@ def test_cuda_graph_replay_is_bit_identical_to_eager(setup):
             eng.enable_graphs(False)
             d3, s3 = net.network(x2)
             assert torch.equal(d2, d3) and torch.equal(s2, s3)
+
+
+def test_programmatic_dependent_launch_equals_plain_stream_order(setup):
+    """PDL (csrc/common.cuh: kernels become resident and run their prologue under the previous kernel, then block in
+    griddepcontrol.wait) must give the bits plain stream order gives -- alternating inputs, so that a kernel that read a
+    buffer before its producer had finished (stale data of the previous call) shows up."""
+    from soccdpt_b200 import _cabi
+    net, sd = setup
+    net.engine("tcgen05")
+    lib = _cabi.load()
+    xs = [synthetic_frames(B, 256, s).cuda() for s, B in ((0, 2), (1, 2), (2, 1), (3, 2))]
+
+    def bits(t):
+        return t.contiguous().view(torch.int32).clone()
+
+    lib.soccdpt_set_pdl(0)
+    try:
+        with torch.no_grad():
+            ref = [[bits(o) for o in net(x)] for x in xs]
+            torch.cuda.synchronize()
+            assert lib.soccdpt_set_pdl(15) == 0          # every kernel family
+            for rep in range(4):
+                for x, r in zip(xs, ref):
+                    out = net(x)
+                    for a, b in zip(out, r):
+                        assert torch.equal(bits(a), b)
+    finally:
+        lib.soccdpt_set_pdl(-1)

@@ -130,6 +130,7 @@ global_attention_tc_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out,
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    soccdpt::pdl_wait();        // qkv is the previous kernel's output
     // ---- stage Q (this tile), K (all keys), V^T (all keys); rows past N are zero
     for (int i = t; i < 128 * 8; i += GT) {
         const int r = i >> 3, c = i & 7;
@@ -298,8 +299,8 @@ int launch_global_attention_tc(const void *qkv, void *out, int batch, int N, int
         configured = smem;
     }
     dim3 grid((unsigned)(batch * heads), (unsigned)((N + 127) / 128));
-    global_attention_tc_kernel<<<grid, GT, smem, st>>>(static_cast<const bf16 *>(qkv), static_cast<bf16 *>(out), N, heads,
-                                                       1.4426950408889634f / sqrtf((float)GD));
+    SOCCDPT_CUDA(launch_pdl(PDL_ATTENTION, global_attention_tc_kernel, grid, dim3(GT), smem, st, static_cast<const bf16 *>(qkv),
+                            static_cast<bf16 *>(out), N, heads, 1.4426950408889634f / sqrtf((float)GD)));
     return check_launch("global_attention_tc_kernel");
 }
 }  // namespace soccdpt

@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256)
 groupnorm_stats_kernel(const bf16 *__restrict__ x, double *__restrict__ stats, int HW, int C, int slabs) {
     __shared__ float s_sum[32], s_sq[32];
     if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+    soccdpt::pdl_wait();
     __syncthreads();
     const int n = blockIdx.x / slabs, slab = blockIdx.x % slabs;
     const int chunks = C / 8, cpg = C / 32;               // channels per group (>= 2)
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(const bf16 *__restrict__ x, const double *__restrict__ stats, const float *__restrict__ gamma,
                        const float *__restrict__ beta, const bf16 *__restrict__ shortcut, bf16 *__restrict__ y, long long total_chunks,
                        int HW, int C, float eps, int relu) {
+    soccdpt::pdl_wait();
     const int chunks = C / 8, cpg = C / 32;
     const double inv_cnt = 1.0 / ((double)HW * cpg);
     for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < (unsigned)total_chunks; i += gridDim.x * 256u) {   // 32-bit index math
@@ -196,6 +198,7 @@ groupnorm_apply_kernel(const bf16 *__restrict__ x, const double *__restrict__ st
 // ------------------------------------------------------------------ MaxPool2dSame 3x3 s2, NHWC bf16 (pad value -inf)
 __global__ void __launch_bounds__(256)
 maxpool3_s2_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, int B, int H, int W, int C) {
+    soccdpt::pdl_wait();
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, chunks = C / 8;
     const int pad_h = max((Ho - 1) * 2 + 3 - H, 0) / 2, pad_w = max((Wo - 1) * 2 + 3 - W, 0) / 2;
     const long long total = (long long)B * Ho * Wo * chunks;
@@ -227,6 +230,7 @@ maxpool3_s2_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, int B, int 
 __global__ void __launch_bounds__(256)
 vit_tokens_kernel(const bf16 *__restrict__ patches, const float *__restrict__ cls, const float *__restrict__ pos,
                   bf16 *__restrict__ tokens, float *__restrict__ tokens_f32, int B, int L, int D) {
+    soccdpt::pdl_wait();
     const long long total = (long long)B * (L + 1) * D;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int d = (int)(i % D);
@@ -243,6 +247,7 @@ vit_tokens_kernel(const bf16 *__restrict__ patches, const float *__restrict__ cl
 // tokens bf16 [B,1+L,D] -> feats bf16 [B,L,2D]
 __global__ void __launch_bounds__(256)
 readout_concat_kernel(const bf16 *__restrict__ tokens, bf16 *__restrict__ feats, int B, int L, int D) {
+    soccdpt::pdl_wait();
     const int chunks = D / 8;
     const long long total = (long long)B * L * 2 * chunks;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -346,6 +351,7 @@ template <int ITERS>
 __global__ void __launch_bounds__(256)
 prenorm_kernel(const bf16 *__restrict__ t, float *__restrict__ master, const float *__restrict__ gamma,
                const float *__restrict__ beta, bf16 *__restrict__ y, bf16 *__restrict__ stream_bf16, long long rows, int C, float eps) {
+    soccdpt::pdl_wait();        // before the early return: every thread of a PDL-launched grid waits
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;                                    // whole warps leave together
@@ -438,10 +444,12 @@ int soccdpt_groupnorm_fwd(const void *x, const float *gamma, const float *beta, 
     const unsigned g1 = (unsigned)(batch * slabs), g2 = (unsigned)grid_for(total);
 #define SOCC_GN(SUB)                                                                                          \
     do {                                                                                                      \
-        groupnorm_stats_kernel<SUB><<<g1, 256, 0, st>>>(xp, stats, HW, C, slabs);                             \
+        SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, groupnorm_stats_kernel<SUB>, dim3(g1), dim3(256), 0, st, xp, stats, \
+                                         HW, C, slabs));                                                      \
         int rc = soccdpt::check_launch("groupnorm_stats_kernel");                                             \
         if (rc) return rc;                                                                                    \
-        groupnorm_apply_kernel<SUB><<<g2, 256, 0, st>>>(xp, stats, gamma, beta, sp, yp, total, HW, C, eps, relu); \
+        SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, groupnorm_apply_kernel<SUB>, dim3(g2), dim3(256), 0, st, xp, stats, \
+                                         gamma, beta, sp, yp, total, HW, C, eps, relu));                      \
     } while (0)
     if (C == 64) SOCC_GN(2);
     else if (C == 128) SOCC_GN(4);
@@ -453,23 +461,25 @@ int soccdpt_groupnorm_fwd(const void *x, const float *gamma, const float *beta, 
 int soccdpt_maxpool3s2_fwd(const void *x, void *y, int batch, int H, int W, int C, soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(x && y && batch >= 1 && H >= 2 && W >= 2 && C % 8 == 0, "maxpool: bad arguments");
     const long long items = (long long)batch * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-    maxpool3_s2_kernel<<<grid_for(items), 256, 0, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(x), static_cast<bf16 *>(y),
-                                                                              batch, H, W, C);
+    SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, maxpool3_s2_kernel, dim3(grid_for(items)), dim3(256), 0,
+                                     soccdpt::as_stream(stream), static_cast<const bf16 *>(x), static_cast<bf16 *>(y), batch, H, W, C));
     return soccdpt::check_launch("maxpool3_s2_kernel");
 }
 
 int soccdpt_vit_tokens_fwd(const void *patches, const float *cls, const float *pos, void *tokens, float *tokens_f32, int batch,
                            int L, int D, soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(patches && cls && pos && tokens && batch >= 1 && L >= 1 && D >= 8, "vit_tokens: bad arguments");
-    vit_tokens_kernel<<<grid_for((long long)batch * (L + 1) * D), 256, 0, soccdpt::as_stream(stream)>>>(
-        static_cast<const bf16 *>(patches), cls, pos, static_cast<bf16 *>(tokens), tokens_f32, batch, L, D);
+    SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, vit_tokens_kernel, dim3(grid_for((long long)batch * (L + 1) * D)), dim3(256),
+                                     0, soccdpt::as_stream(stream), static_cast<const bf16 *>(patches), cls, pos,
+                                     static_cast<bf16 *>(tokens), tokens_f32, batch, L, D));
     return soccdpt::check_launch("vit_tokens_kernel");
 }
 
 int soccdpt_readout_concat_fwd(const void *tokens, void *feats, int batch, int L, int D, soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(tokens && feats && batch >= 1 && L >= 1 && D % 8 == 0, "readout_concat: bad arguments");
-    readout_concat_kernel<<<grid_for((long long)batch * L * 2 * (D / 8)), 256, 0, soccdpt::as_stream(stream)>>>(
-        static_cast<const bf16 *>(tokens), static_cast<bf16 *>(feats), batch, L, D);
+    SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, readout_concat_kernel, dim3(grid_for((long long)batch * L * 2 * (D / 8))),
+                                     dim3(256), 0, soccdpt::as_stream(stream), static_cast<const bf16 *>(tokens),
+                                     static_cast<bf16 *>(feats), batch, L, D));
     return soccdpt::check_launch("readout_concat_kernel");
 }
 
@@ -502,10 +512,10 @@ int soccdpt_prenorm_fwd(const void *t, float *master, const float *gamma, const 
     const unsigned blocks = (unsigned)((rows + 7) / 8);
     const bf16 *tp = static_cast<const bf16 *>(t);
     bf16 *yp = static_cast<bf16 *>(y), *sp = static_cast<bf16 *>(stream_bf16);
-    if (C <= 256) prenorm_kernel<1><<<blocks, 256, 0, st>>>(tp, master, gamma, beta, yp, sp, rows, C, eps);
-    else if (C <= 512) prenorm_kernel<2><<<blocks, 256, 0, st>>>(tp, master, gamma, beta, yp, sp, rows, C, eps);
-    else if (C <= 768) prenorm_kernel<3><<<blocks, 256, 0, st>>>(tp, master, gamma, beta, yp, sp, rows, C, eps);
-    else prenorm_kernel<4><<<blocks, 256, 0, st>>>(tp, master, gamma, beta, yp, sp, rows, C, eps);
+    if (C <= 256) SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, prenorm_kernel<1>, dim3(blocks), dim3(256), 0, st, tp, master, gamma, beta, yp, sp, rows, C, eps));
+    else if (C <= 512) SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, prenorm_kernel<2>, dim3(blocks), dim3(256), 0, st, tp, master, gamma, beta, yp, sp, rows, C, eps));
+    else if (C <= 768) SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, prenorm_kernel<3>, dim3(blocks), dim3(256), 0, st, tp, master, gamma, beta, yp, sp, rows, C, eps));
+    else SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, prenorm_kernel<4>, dim3(blocks), dim3(256), 0, st, tp, master, gamma, beta, yp, sp, rows, C, eps));
     return soccdpt::check_launch("prenorm_kernel");
 }
 }

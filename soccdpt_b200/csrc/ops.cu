@@ -1,5 +1,7 @@
 // Bandwidth-bound glue kernels of the network path + the CUDA-core reference convolution.
 // Layout everywhere: NHWC / token-major bf16 activations, fp32 math inside the kernels.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(256) conv_ref_kernel(const soccdpt_conv_t c) {
 // every warp handles 4 horizontally adjacent tokens per iteration so each weight read feeds 4 FMAs.
 // Lane l owns channels l, l+32, ... (E <= 128).  Two-pass LayerNorm (eps 1e-5) in fp32 on the warp.
 constexpr int PE_TOK = 4;
+template <int NCH>      // 32-channel slices per lane: 3 for E = 96 (a fourth, all-zero slice cost a quarter of the FMAs), 4 for E = 128
 __global__ void __launch_bounds__(256)
 patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
                    const float *__restrict__ g, const float *__restrict__ be, bf16 *__restrict__ out,
@@ -110,63 +113,77 @@ patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w, con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ph = H / 4, pw = W / 4;
     const int groups_per_row = pw / PE_TOK;
-    const long long groups = (long long)B * ph * groups_per_row;
+    const unsigned groups = (unsigned)B * (unsigned)ph * (unsigned)groups_per_row;      // < 2^31 (checked on the host)
     float *in = stage + warp * PE_TOK * 48;
-    const int nch = (E + 31) / 32;
-    for (long long gi = (long long)blockIdx.x * 8 + warp; gi < groups; gi += (long long)gridDim.x * 8) {
-        const int gx = (int)(gi % groups_per_row), ty = (int)((gi / groups_per_row) % ph);
-        const int n = (int)(gi / ((long long)groups_per_row * ph));
+    // per-lane constants of the channels this lane owns (loop invariant: they were re-read from L1 for every token)
+    float bias_r[NCH], gam_r[NCH], bet_r[NCH];
+    bool own[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        own[j] = lane + 32 * j < E;
+        bias_r[j] = own[j] ? b[lane + 32 * j] : 0.0f;
+        gam_r[j] = own[j] ? g[lane + 32 * j] : 0.0f;
+        bet_r[j] = own[j] ? be[lane + 32 * j] : 0.0f;
+    }
+    // staging slots of this lane's (up to two) input float4s: f = lane, lane + 32 -> r = f >> 2 (= ci*4 + i), q = f & 3
+    const int q_tok = lane & 3, r0 = lane >> 2, r1 = (lane + 32) >> 2;
+    const size_t plane = (size_t)H * W;
+    const size_t off0 = (size_t)(r0 >> 2) * plane + (size_t)(r0 & 3) * W + q_tok * 4;
+    const size_t off1 = (size_t)(r1 >> 2) * plane + (size_t)(r1 & 3) * W + q_tok * 4;
+    float *d0 = in + q_tok * 48 + r0 * 4, *d1 = in + q_tok * 48 + r1 * 4;      // ci*16 + i*4 == r*4
+    for (unsigned gi = blockIdx.x * 8u + warp; gi < groups; gi += gridDim.x * 8u) {
+        const unsigned gx = gi % (unsigned)groups_per_row, rowi = gi / (unsigned)groups_per_row;
+        const unsigned ty = rowi % (unsigned)ph, n = rowi / (unsigned)ph;
         // 12 image rows (3 channels x 4 rows) x 16 consecutive floats = 48 float4, coalesced 64 B segments
-        for (int f = lane; f < 48; f += 32) {
-            const int r = f >> 2, q = f & 3;             // r = ci*4 + i ; q = token within the group
-            const int ci = r >> 2, i = r & 3;
-            const float4 v = *reinterpret_cast<const float4 *>(
-                x + (((long long)n * 3 + ci) * H + ty * 4 + i) * W + (gx * PE_TOK + q) * 4);
-            float *d = in + q * 48 + ci * 16 + i * 4;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
+        const float *xg = x + ((size_t)n * 3 * H + (size_t)ty * 4) * W + (size_t)gx * (PE_TOK * 4);
+        const float4 v0 = *reinterpret_cast<const float4 *>(xg + off0);
+        float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < 16) v1 = *reinterpret_cast<const float4 *>(xg + off1);
+        *reinterpret_cast<float4 *>(d0) = v0;
+        if (lane < 16) *reinterpret_cast<float4 *>(d1) = v1;
         __syncwarp();
-        float acc[PE_TOK][4];
+        float acc[PE_TOK][NCH];
 #pragma unroll
         for (int t = 0; t < PE_TOK; ++t)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[t][j] = (j < nch && lane + 32 * j < E) ? b[lane + 32 * j] : 0.0f;
+            for (int j = 0; j < NCH; ++j) acc[t][j] = bias_r[j];
 #pragma unroll 2
         for (int k4 = 0; k4 < 12; ++k4) {
-            float4 wv[4];
+            float4 wv[NCH];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                wv[j] = (j < nch && lane + 32 * j < E) ? wT4[k4 * E + lane + 32 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < NCH; ++j)
+                wv[j] = own[j] ? wT4[k4 * E + lane + 32 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int t = 0; t < PE_TOK; ++t) {
                 const float4 xv = *reinterpret_cast<const float4 *>(in + t * 48 + k4 * 4);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)     // ascending tap order, like the scalar loop it replaces
+                for (int j = 0; j < NCH; ++j)     // ascending tap order, like the scalar loop it replaces
                     acc[t][j] = fmaf(xv.w, wv[j].w, fmaf(xv.z, wv[j].z, fmaf(xv.y, wv[j].y, fmaf(xv.x, wv[j].x, acc[t][j]))));
             }
         }
         __syncwarp();
+        const size_t tok0 = ((size_t)n * ph + ty) * pw + (size_t)gx * PE_TOK;
+        bf16 *o16 = out + tok0 * E + lane;
+        float *o32 = out_f32 ? out_f32 + tok0 * E + lane : nullptr;
 #pragma unroll
         for (int t = 0; t < PE_TOK; ++t) {
             float s = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) s += (lane + 32 * j < E && j < nch) ? acc[t][j] : 0.0f;
+            for (int j = 0; j < NCH; ++j) s += own[j] ? acc[t][j] : 0.0f;
             const float mean = warp_sum(s) / (float)E;
             float q = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NCH; ++j) {
                 const float d = acc[t][j] - mean;
-                q += (lane + 32 * j < E && j < nch) ? d * d : 0.0f;
+                q += own[j] ? d * d : 0.0f;
             }
             const float rstd = rsqrtf(warp_sum(q) / (float)E + 1e-5f);
-            const long long tok = ((long long)n * ph + ty) * pw + gx * PE_TOK + t;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int e = lane + 32 * j;
-                if (j < nch && e < E) {
-                    const float v = (acc[t][j] - mean) * rstd * g[e] + be[e];
-                    out[tok * E + e] = __float2bfloat16_rn(v);
-                    if (out_f32) out_f32[tok * E + e] = v;
+            for (int j = 0; j < NCH; ++j) {
+                if (own[j]) {
+                    const float v = (acc[t][j] - mean) * rstd * gam_r[j] + bet_r[j];
+                    o16[t * E + 32 * j] = __float2bfloat16_rn(v);
+                    if (o32) o32[t * E + 32 * j] = v;
                 }
             }
         }
@@ -189,14 +206,30 @@ layernorm_kernel(const bf16 *__restrict__ t, const bf16 *__restrict__ res, float
     const long long row = (long long)blockIdx.x * (256 / G) + threadIdx.x / G;
     const bool live = row < rows;                                // keep dead groups in the shuffles
     const int chunks = C / 8;
-    const uint4 *tp = reinterpret_cast<const uint4 *>(t + (live ? row : 0) * C);
-    float f[ITERS][8];
-    float s = 0.0f;
+    const long long base = (live ? row : 0) * C;
+    const uint4 *tp = reinterpret_cast<const uint4 *>(t + base);
+    const uint4 *rp = res ? reinterpret_cast<const uint4 *>(res + base) : nullptr;
+    float4 *mp = master ? reinterpret_cast<float4 *>(master + base) : nullptr;
+    const bool add_master = mp && accumulate;
+    // every load of the row -- branch output AND residual -- is issued before the first reduction: one memory round trip
+    // per thread instead of two (the kernel is a pure HBM stream; bytes in flight per SM are what sets its speed)
+    uint4 traw[ITERS], rraw[ITERS];
+    float4 ma[ITERS], mb[ITERS];
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
         const int k = gl + it * G;
         if (k < chunks) {
-            unpack8(tp[k], f[it]);
+            traw[it] = tp[k];
+            if (rp) rraw[it] = rp[k];
+            if (add_master) { ma[it] = mp[2 * k]; mb[it] = mp[2 * k + 1]; }
+        }
+    }
+    float f[ITERS][8];
+    float s = 0.0f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        if (gl + it * G < chunks) {
+            unpack8(traw[it], f[it]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) s += f[it][i];
         }
@@ -216,18 +249,16 @@ layernorm_kernel(const bf16 *__restrict__ t, const bf16 *__restrict__ res, float
     for (int o = G / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q / (float)C + eps);
     if (!live) return;
-    const uint4 *rp = res ? reinterpret_cast<const uint4 *>(res + row * C) : nullptr;
-    float4 *mp = master ? reinterpret_cast<float4 *>(master + row * C) : nullptr;
-    uint4 *yp = reinterpret_cast<uint4 *>(y + row * C);
-    const bool add = rp || (mp && accumulate);
+    uint4 *yp = reinterpret_cast<uint4 *>(y + base);
+    const bool add = rp || add_master;
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
         const int k = gl + it * G;
         if (k < chunks) {
             float r[8], o8[8];
-            if (rp) unpack8(rp[k], r);
-            if (mp && accumulate) {
-                const float4 a = mp[2 * k], b2 = mp[2 * k + 1];
+            if (rp) unpack8(rraw[it], r);
+            if (add_master) {
+                const float4 a = ma[it], b2 = mb[it];
                 r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b2.x; r[5] = b2.y; r[6] = b2.z; r[7] = b2.w;
             }
             const float4 g0 = *reinterpret_cast<const float4 *>(gamma + k * 8), g1 = *reinterpret_cast<const float4 *>(gamma + k * 8 + 4);
@@ -253,6 +284,8 @@ int launch_layernorm(const bf16 *t, const bf16 *res, float *master, int accumula
 #define SOCC_LN(G, IT)                                                                                              \
     SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, layernorm_kernel<G, IT>, dim3((unsigned)((rows + (256 / G) - 1) / (256 / G))), dim3(256), 0, \
                                      st, t, res, master, accumulate, gamma, beta, y, rows, C, eps))
+    // (C = 3 * 2^k as C / 24 lanes x 3 chunks -- every lane busy, three chunks of loads in flight per thread -- was measured
+    // 3 % SLOWER than a quarter of the lanes idle: 104 registers halve the resident warps; profiles/r1_progress.md step 15)
     if (C <= 128) SOCC_LN(16, 1);
     else if (C <= 256) SOCC_LN(32, 1);
     else if (C <= 512) SOCC_LN(32, 2);
@@ -479,12 +512,20 @@ int soccdpt_patch_embed_fwd(const float *x, const float *w, const float *b, cons
     SOCCDPT_REQUIRE(x && w && b && ln_w && ln_b && tokens, "patch_embed: NULL pointer");
     SOCCDPT_REQUIRE(batch >= 1 && H % 4 == 0 && W % 16 == 0 && E >= 32 && E <= 128, "patch_embed: need W %% 16 == 0 and 32 <= E <= 128");
     const long long groups = (long long)batch * (H / 4) * (W / 16);
+    SOCCDPT_REQUIRE(groups < (1ll << 31), "patch_embed: batch too large for one call");
     long long blocks = (groups + 7) / 8;
     const long long cap = (long long)soccdpt::sm_count() * 8;
     if (blocks > cap) blocks = cap;
     const size_t smem = (size_t)(48 * E + 8 * PE_TOK * 48) * sizeof(float);
-    SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, patch_embed_kernel, dim3((unsigned)blocks), dim3(256), smem, soccdpt::as_stream(stream), x, w, b,
-                                     ln_w, ln_b, static_cast<bf16 *>(tokens), tokens_f32, batch, H, W, E));
+#define SOCC_PE(NCH)                                                                                                     \
+    SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, patch_embed_kernel<NCH>, dim3((unsigned)blocks), dim3(256), smem, \
+                                     soccdpt::as_stream(stream), x, w, b, ln_w, ln_b, static_cast<bf16 *>(tokens), tokens_f32, \
+                                     batch, H, W, E))
+    if (E <= 32) SOCC_PE(1);
+    else if (E <= 64) SOCC_PE(2);
+    else if (E <= 96) SOCC_PE(3);
+    else SOCC_PE(4);
+#undef SOCC_PE
     return soccdpt::check_launch("patch_embed_kernel");
 }
 

@@ -142,3 +142,36 @@ def test_full_size_batch_properties(tmp_path):
     assert torch.equal(gper.max(dim=0).values, grid[0])
     assert grid[:, 0].sum() == 0 and grid[:, :, 0].sum() == 0 and grid[:, :, :, 0].sum() == 0
     assert set(torch.unique(grid).tolist()) <= {0.0, 1.0}
+
+
+@pytest.mark.parametrize("hw", [(320, 1024), (192, 640), (384, 640)])
+def test_external_depth_model_wrapper_like_eval_others(tmp_path, hw):
+    """the reference's OtherModelWrapper (scripts/eval_others.py:54-247) subclasses SOccDPT around a
+    third-party depth network, passes an all-zero segmentation at that network's resolution (monodepth2 / manydepth 320x1024
+    and 192x640, PackNet 384x640) and returns get_semantic_occupancy(inv_depth, segmentation).  Same subclass here, a stub in
+    place of the third-party network: shapes / squeeze quirks, points against the oracle, an empty grid (no class is non-zero)."""
+    geom = O.Geometry()
+    yml = write_calib_yaml(str(tmp_path / "calib.yaml"), O.SYNTHETIC_CALIB)
+
+    class OtherModelWrapper(SOccDPT):
+        def __init__(self, model, num_classes, **kwargs):
+            super().__init__(**kwargs)
+            self._model, self.num_classes = model, num_classes
+
+        def forward(self, x):
+            segmentation = torch.zeros((1, self.num_classes, x.shape[2], x.shape[3]), device=x.device)
+            return self.get_semantic_occupancy(self._model(x), segmentation)
+
+    h, w = hw
+    g = torch.Generator().manual_seed(11)
+    coarse = torch.rand(1, 1, 12, 20, generator=g) * 0.2 + 0.02
+    inv = torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear")[:, 0].contiguous()
+    net = OtherModelWrapper(lambda x: inv.to(x.device), 3, camera_intrinsics_yaml=yml, compute_occ=True)
+    out = net(torch.zeros(1, 3, h, w, device="cuda"))
+    torch.cuda.synchronize()
+    ref = O.get_semantic_occupancy(inv.clone(), torch.zeros(1, 3, h, w), geom)
+    for r, o in zip(ref, out):
+        assert tuple(r.shape) == tuple(o.shape)
+    assert torch.allclose(out[0].cpu(), ref[0], rtol=2e-6, atol=2e-7)
+    assert torch.allclose(out[2].cpu(), ref[2], rtol=1e-5, atol=1e-5, equal_nan=True)
+    assert float(out[1].abs().max()) == 0.0 and float(out[3].sum()) == 0.0 and float(ref[3].sum()) == 0.0

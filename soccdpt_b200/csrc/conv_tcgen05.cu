@@ -17,6 +17,10 @@
 //   with per-element runtime branches it ran ~170 warp-instructions per 16 columns and was as long as the
 //   whole K=2304 mainloop.
 // * persistent: grid = min(tiles, SMs); 4-stage smem ring (A 16 KB + B <=32 KB per stage).
+// * RESIDENT N BLOCK for 1x1 / linear layers whose N block of weights ([K/64][BLOCK_N][64] bf16) fits behind a >= 3-slot A ring
+//   (<= 144 KB): the grid is rounded down to a multiple of the number of N blocks, so `tile += gridDim.x` keeps a CTA on ONE
+//   N block; its weights are fetched once per CTA instead of once per tile (S2 qkv: 245 -> 98 KB arriving per tile) and the
+//   whole ring (up to 24 x 16 KB) prefetches activations.
 // * HALO variant for 3x3 convs on 128-pixel row segments: the kernel is bound by bytes ARRIVING per SM
 //   (~64 B/clk), and re-loading the 16 KB activation tile for each of the 9 taps is most of them.  Instead one
 //   TMA box {64 ch, 130 px, 3 rows} per channel block is loaded once and the nine taps are issued from it with
@@ -74,6 +78,9 @@ struct Params {
     int stride, Ho, Wo;        // output grid = ceil(input / stride)
     int b_stages;              // HALO: depth of the weight ring (96 KB / bytes per tap tile, <= 24)
     int b_resident;            // HALO: the whole weight tensor (<= 96 KB) is loaded once per CTA and stays in smem
+    int nres;                  // plain 1x1 path: the grid is a multiple of n_blocks, so a CTA keeps ONE N block for all its tiles and
+                               // that block's weights ([k_blocks][block_n][64], <= 144 KB) stay resident; the ring holds A tiles only
+    int a_stages;              // nres: depth of the A-only ring (16 KB slots in front of the resident weights)
     uint32_t a_bytes, b_bytes; // TMA transaction bytes per stage
     soccdpt_conv_t c;
 };
@@ -323,10 +330,26 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     for (int tap = 0; tap < 9; ++tap)
                         tma_load_3d(b_ring + (cb * 9 + tap) * p.b_bytes, &map_b, &full[0], cb * BLOCK_K, tap, 0);
             }
+            if (!HALO && p.nres && blockIdx.x < p.total_tiles) {
+                // this CTA's N block never changes (grid % n_blocks == 0): fetch its weights once, behind the A ring
+                uint8_t *b_res = smem + p.a_stages * A_STAGE_BYTES;
+                mbar_expect_tx(&a_full[0], (uint32_t)k_blocks * p.b_bytes);
+                for (int kb = 0; kb < k_blocks; ++kb)
+                    tma_load_3d(b_res + kb * p.b_bytes, &map_b, &a_full[0], kb * BLOCK_K, 0, (blockIdx.x % p.n_blocks) * p.block_n);
+            }
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
                 const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+                if (!HALO && p.nres) {
+                    for (int kb = 0; kb < k_blocks; ++kb) {          // 1x1: k block == channel block, tap (0, 0)
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], p.a_bytes);
+                        tma_load_4d(smem + stage * A_STAGE_BYTES, &map_a, &full[stage], kb * BLOCK_K, w0 - p.pad, h0 - p.pad, n0);
+                        if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+                    }
+                    continue;
+                }
                 if (HALO) {
                     // channel-block outer, tap inner: one halo tile (A ring) feeds nine weight tiles (B ring)
                     uint8_t *b_ring = smem + HALO_A_STAGES * HALO_STAGE_BYTES;
@@ -369,10 +392,38 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 mbar_wait(&full[0], 0);                      // resident weights have landed
                 tc_fence_after();
             }
+            if (!HALO && p.nres && blockIdx.x < p.total_tiles) {
+                mbar_wait(&a_full[0], 0);                    // resident weights of this CTA's N block have landed
+                tc_fence_after();
+            }
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+                if (!HALO && p.nres) {
+                    const uint32_t desc_hi = (uint32_t)(umma_desc(0) >> 32);
+                    uint32_t b_lo = (uint32_t)umma_desc(smem_u32(smem + p.a_stages * A_STAGE_BYTES));
+                    const uint32_t b_step = p.b_bytes >> 4;
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        const int rem = c.Cin - kb * BLOCK_K;
+                        const int ksteps = rem >= BLOCK_K ? BLOCK_K / UMMA_K : (rem + UMMA_K - 1) / UMMA_K;
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_lo = (uint32_t)umma_desc(smem_u32(smem + stage * A_STAGE_BYTES));
+                        if (ksteps == 4) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_f16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        } else {
+                            for (int k = 0; k < ksteps; ++k) umma_f16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&empty[stage]);
+                        if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+                        b_lo += b_step;
+                    }
+                    umma_commit(&acc_full[acc]);
+                    if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+                    continue;
+                }
                 if (HALO) {
                     const uint32_t b_ring = smem_u32(smem + HALO_A_STAGES * HALO_STAGE_BYTES);
                     const uint32_t desc_hi = (uint32_t)(umma_desc(0) >> 32);
@@ -717,6 +768,19 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     p.b_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
     p.b_stages = HALO_B_BYTES / (int)p.b_bytes;
     if (p.b_stages > MAX_B_STAGES) p.b_stages = MAX_B_STAGES;
+    // resident N block (see Params::nres): 1x1, stride 1, the block's weights fit behind an A ring of >= 3 slots, and enough
+    // M tiles per CTA for the one-off weight fetch to pay
+    // (per-layer A/B in profiles/r1_progress.md step 18: qkv -7..-10 %, S0 fc2 -13 %, out_conv / tap GEMM -4..-5 %, nothing slower)
+    static const bool nres_enabled = !(getenv("SOCCDPT_CONV_NRES") && getenv("SOCCDPT_CONV_NRES")[0] == '0');
+    const long long bres_bytes = (long long)p.k_blocks_per_tap * p.b_bytes;
+    p.nres = 0;
+    p.a_stages = STAGES;
+    if (nres_enabled && !halo && c->KH == 1 && c->KW == 1 && p.stride == 1 && p.n_blocks <= soccdpt::sm_count() &&
+        bres_bytes + 3 * A_STAGE_BYTES <= RING_BYTES_PLAIN && p.total_tiles >= 2 * soccdpt::sm_count()) {
+        p.nres = 1;
+        long long slots = (RING_BYTES_PLAIN - bres_bytes) / A_STAGE_BYTES;
+        p.a_stages = (int)(slots < MAX_B_STAGES ? slots : MAX_B_STAGES);
+    }
 
     CUtensorMap map_a, map_b;
     {
@@ -763,7 +827,8 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     const int mode = c->proj_n > 0 ? 2 : ((c->res1 || c->res2 || c->y_relu || !c->y) ? 1 : 0);
     if (mode == 2) SOCCDPT_REQUIRE(c->y == nullptr && c->y_relu == nullptr && !c->res1 && !c->res2,
                                    "conv: the fused projection epilogue produces proj_out only");
-    const int grid = p.total_tiles < soccdpt::sm_count() ? p.total_tiles : soccdpt::sm_count();
+    int grid = p.total_tiles < soccdpt::sm_count() ? p.total_tiles : soccdpt::sm_count();
+    if (p.nres) grid = grid / p.n_blocks * p.n_blocks;      // tile += grid keeps tile % n_blocks, i.e. the CTA's N block
     cudaStream_t st = soccdpt::as_stream(stream);
 #define SOCC_LAUNCH(A, M, HL)                                                                                           \
     do {                                                                                                                \

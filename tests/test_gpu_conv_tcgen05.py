@@ -33,6 +33,15 @@ CASES = [
     (1, 96, 96, 128, 256, 3, 0, False, 0, False, 0),
     (1, 192, 192, 256, 128, 3, 0, True, 0, False, 0),
     (1, 7, 150, 64, 48, 3, 0, True, 0, False, 0),        # W tail inside a row (150 = 128 + 22)
+    # >= 2 x 148 tiles: the RESIDENT N BLOCK path of the 1x1 / linear layers (weights of a CTA's N block fetched once,
+    # activation-only ring) -- the bench-size shapes, which the small cases above never reach
+    (1, 1, 40000, 96, 288, 1, 0, True, 0, False, 0),     # S0 qkv: 313 M tiles (M tail 64) x 2 N blocks, K tail, 8-slot A ring
+    (1, 1, 8192, 384, 1152, 1, 0, True, 0, False, 0),    # S2 qkv: 6 N blocks (grid 144), 6 k blocks through a 3-slot ring
+    (1, 1, 20000, 192, 768, 1, 2, True, 0, False, 0),    # S1 fc1 + GELU: 3 N blocks (grid 147)
+    (1, 1, 40000, 384, 96, 1, 0, True, 1, False, 0),     # S0 fc2 + residual: one N block of 96
+    (12, 64, 64, 256, 256, 1, 0, True, 0, True, 0),      # out_conv 1x1 (NHWC boxes 64 x 2) + ReLU copy
+    (3, 128, 128, 128, 288, 1, 0, False, 0, False, 0),   # depth-head tap GEMM: 2 N blocks of 144
+    (5, 128, 128, 256, 256, 1, 1, True, 0, False, 3),    # fused projection epilogue on the resident path
 ]
 
 

@@ -116,6 +116,19 @@ def test_batch_invariance(setup):
     assert torch.allclose(d3[1:2], d1, rtol=1e-3, atol=1e-4) and torch.allclose(s3[1:2], s1, rtol=1e-3, atol=1e-4)
 
 
+def test_bench_size_paths_match_small_batches(setup):
+    """B = 8 reaches the tile counts of the bench (>= 2 x 148 tiles per GEMM: the resident-N-block path of the linear layers,
+    full persistent grids) -- its per-frame results must equal the B = 2 runs of the same frames."""
+    net, sd = setup
+    net.engine("tcgen05")
+    x = synthetic_frames(8, 256, 21).cuda()
+    with torch.no_grad():
+        d8, s8 = (t.clone() for t in net.network(x))
+        for i in (0, 6):
+            d2, s2 = net.network(x[i:i + 2])
+            assert torch.allclose(d8[i:i + 2], d2, rtol=1e-3, atol=1e-4) and torch.allclose(s8[i:i + 2], s2, rtol=1e-3, atol=1e-4)
+
+
 def test_cuda_graph_replay_is_bit_identical_to_eager(setup):
     """engine.enable_graphs(): the captured launch list replays to the same bytes as the eager launches (B = 1 and 3)."""
     net, _ = setup

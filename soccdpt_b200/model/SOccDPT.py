@@ -270,6 +270,10 @@ class SOccDPT_V1(_EngineOwner, SOccDPT):
         main.wait_stream(side)
         return inv_depth, segmentation
 
+    def network_outputs(self, batch, device):
+        """the static (inverse depth, segmentation) buffers `network` fills for this batch size (soccdpt_b200.pipeline)."""
+        return (self.engine().plan_for(batch, device)["depth"], self.seg_engine().plan_for(batch, device)["seg"])
+
     def forward(self, x: torch.Tensor):
         inv_depth, segmentation = self.network(x)
         return self.get_semantic_occupancy(inv_depth, segmentation)
@@ -313,6 +317,11 @@ class SOccDPT_V3(_EngineOwner, SOccDPT):
         if self.training:
             raise _cabi.SoccdptError("soccdpt_b200 implements the inference path only: call net.eval() first")
         return self.engine().run(x)
+
+    def network_outputs(self, batch, device):
+        """the static (inverse depth, segmentation) buffers `network` fills for this batch size (soccdpt_b200.pipeline)."""
+        plan = self.engine().plan_for(batch, device)
+        return plan["depth"], plan["seg"]
 
     def forward(self, x: torch.Tensor):
         inv_depth, segmentation = self.network(x)

@@ -93,8 +93,7 @@ class FrameStream:
                 if self.transform is not None:
                     self.transform(self.u8_dev[slot], out=self.x_dev[slot])
                 out = self.net(self.x_dev[slot])
-                depth, seg = self.net.engine().plan_for(self.batch, self.device)["depth"], \
-                    self.net.engine().plan_for(self.batch, self.device)["seg"]
+                depth, seg = self.net.network_outputs(self.batch, self.device)
                 self.d_dev[slot].copy_(depth, non_blocking=True)
                 self.s_dev[slot].copy_(seg, non_blocking=True)
                 self.g_dev[slot].copy_(out[3][0], non_blocking=True)

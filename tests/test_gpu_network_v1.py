@@ -85,3 +85,19 @@ def test_v1_two_streams_equal_one_stream(setup):
         _, s1 = net.seg_engine().run(x)
     torch.cuda.synchronize()
     assert torch.equal(d1, d2) and torch.equal(s1, s2)
+
+
+def test_v1_frame_stream_equals_direct_calls(setup):
+    """the host-frame path (three streams, double buffering) on top of SOccDPT_V1's own two-stream forward."""
+    from soccdpt_b200.pipeline import FrameStream
+    net, sd = setup
+    B = 2
+    batches = [synthetic_frames(B, 256, 30 + i).pin_memory() for i in range(4)]
+    fs = FrameStream(net, B)
+    got = [(r.index, r.inv_depth.clone(), r.segmentation.clone(), r.occupancy.clone()) for r in fs.run(batches)]
+    assert [g[0] for g in got] == [0, 1, 2, 3]
+    for (_, d, s, g), xb in zip(got, batches):
+        with torch.no_grad():
+            out = net(xb.cuda())
+            d0, s0 = (t.clone().cpu() for t in net.network(xb.cuda()))
+        assert torch.equal(d, d0) and torch.equal(s, s0) and torch.equal(g, out[3][0].cpu())

@@ -38,6 +38,7 @@ CASES = [
     (1, 1, 40000, 96, 288, 1, 0, True, 0, False, 0),     # S0 qkv: 313 M tiles (M tail 64) x 2 N blocks, K tail, 8-slot A ring
     (1, 1, 8192, 384, 1152, 1, 0, True, 0, False, 0),    # S2 qkv: 6 N blocks (grid 144), 6 k blocks through a 3-slot ring
     (1, 1, 20000, 192, 768, 1, 2, True, 0, False, 0),    # S1 fc1 + GELU: 3 N blocks (grid 147)
+    (1, 1, 8192, 384, 1536, 1, 2, True, 0, False, 0),    # S2 fc1 + GELU: 6 N blocks of 256, too large to stay resident (plain ring)
     (1, 1, 40000, 384, 96, 1, 0, True, 1, False, 0),     # S0 fc2 + residual: one N block of 96
     (12, 64, 64, 256, 256, 1, 0, True, 0, True, 0),      # out_conv 1x1 (NHWC boxes 64 x 2) + ReLU copy
     (3, 128, 128, 128, 288, 1, 0, False, 0, False, 0),   # depth-head tap GEMM: 2 N blocks of 144

@@ -1,6 +1,7 @@
-"""Execution engine: packs the weights of a SOccDPT_V3 module tree once (bf16, BN folded, attention
-bias tables baked) and replays the image -> (inverse depth, segmentation) network as a fixed list of
-C-ABI kernel launches on the current CUDA stream.  PyTorch only owns the device buffers.
+"""Execution engine: packs the weights of a DPT module tree once (bf16, BN folded, attention bias tables baked) and
+replays the image -> (inverse depth, segmentation) network as a fixed list of C-ABI kernel launches on the current CUDA
+stream.  PyTorch only owns the device buffers.  One engine per network: SOccDPT_V3 has one (shared trunk, both heads),
+SOccDPT_V1 two (depth DPT; segmentation DPT with BatchNorm in its residual conv units).
 
 Kernel schedule per frame batch (reference call sites in include/soccdpt_b200.h):
   patch_embed -> for every Swin block: qkv GEMM, window attention, proj GEMM, LN+residual,
@@ -81,7 +82,6 @@ class NetworkEngine:
 
     # ------------------------------------------------------------------ weight packing
     def _pack(self, dev):
-        net = self.net
         enc = self.dpt.pretrained.model
         W = {"stages": []}
         self.hybrid = not isinstance(enc, SwinV2Params)

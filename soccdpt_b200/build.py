@@ -39,7 +39,8 @@ def _headers_mtime():
 
 def _compile(src, verbose):
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-    cmd = [NVCC, *ARCH, *COMMON, *EXTRA.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC, *ARCH, *COMMON, *EXTRA.get(src, []), *os.environ.get("SOCCDPT_NVCC_FLAGS", "").split(),
+           "-c", os.path.join(CSRC, src), "-o", obj]     # SOCCDPT_NVCC_FLAGS: experiment switches (-DSOCCDPT_...), with --force
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -186,6 +186,30 @@ int soccdpt_layernorm_master_fwd(const void *t, float *master, int accumulate, c
                                  const float *beta, void *y, long long rows, int C, float eps,
                                  soccdpt_stream_t stream);
 
+/* Fused tail of one branch of a timm SwinTransformerV2Block (res-post-norm; SURVEY.md App. A.1, driven by the reference
+ * through SOccDPT/model/backbones/swin_common.py:16-27 / utils.py:64-81):
+ *   two-GEMM mode (w1 != NULL), the MLP branch  x = x + norm2(mlp(x)):
+ *       master += LayerNorm( GELU(x @ w1^T + b1) @ w2^T + b2 ) * gamma + beta ;  y = bf16(master)
+ *   one-GEMM mode (w1 == NULL), the attention branch after the window attention  x = x + norm1(proj(attn)):
+ *       master += LayerNorm( x @ w2^T + b2 ) * gamma + beta ;  y = bf16(master)
+ * The hidden activation and the branch output never leave the SM (TMEM); fp32 accumulation, fp32 LayerNorm, fp32
+ * residual stream.  y may alias x.  C in [32, 256] (multiple of 32), HID a multiple of 128. */
+typedef struct {
+    const void *x;        /* bf16 [M, K1]   rows entering the first GEMM */
+    const void *w1;       /* bf16 [HID, K1] fc1 weight, or NULL for one-GEMM mode */
+    const float *b1;      /* f32 [HID] */
+    const void *w2;       /* bf16 [C, HID] fc2 weight (two-GEMM mode) or [C, K1] proj weight (one-GEMM mode) */
+    const float *b2;      /* f32 [C] */
+    const float *gamma;   /* f32 [C] LayerNorm weight */
+    const float *beta;    /* f32 [C] LayerNorm bias */
+    float *master;        /* f32 [M, C] residual stream, updated in place */
+    void *y;              /* bf16 [M, C] copy of the updated stream (the next GEMM's operand) */
+    long long M;
+    int K1, HID, C;
+    float eps;
+} soccdpt_block_tail_t;
+int soccdpt_swin_block_tail_fwd(const soccdpt_block_tail_t *a, soccdpt_stream_t stream);
+
 /* timm PatchMerging gather: [B,H,W,C] -> [B,H/2,W/2,4C] in (x0,x1,x2,x3) = (0,0),(1,0),(0,1),(1,1) order */
 int soccdpt_patch_merge_gather_fwd(const void *x, void *y, int batch, int H, int W, int C,
                                    soccdpt_stream_t stream);

@@ -45,6 +45,15 @@ class Conv(ctypes.Structure):
     ]
 
 
+class BlockTail(ctypes.Structure):
+    """soccdpt_block_tail_t"""
+    _fields_ = [
+        ("x", c_void_p), ("w1", c_void_p), ("b1", c_void_p), ("w2", c_void_p), ("b2", c_void_p),
+        ("gamma", c_void_p), ("beta", c_void_p), ("master", c_void_p), ("y", c_void_p),
+        ("M", ctypes.c_longlong), ("K1", ctypes.c_int), ("HID", ctypes.c_int), ("C", ctypes.c_int), ("eps", ctypes.c_float),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/soccdpt_b200.h declares
 _I, _LL, _F, _SZ = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t
 SYMBOLS = {
@@ -72,6 +81,7 @@ SYMBOLS = {
     "soccdpt_window_attention_fwd": (_I, [c_void_p] * 4 + [_I] * 7 + [c_void_p]),
     "soccdpt_layernorm_fwd": (_I, [c_void_p] * 5 + [_LL, _I, _F, c_void_p]),
     "soccdpt_layernorm_master_fwd": (_I, [c_void_p, c_void_p, _I, c_void_p, c_void_p, c_void_p, _LL, _I, _F, c_void_p]),
+    "soccdpt_swin_block_tail_fwd": (_I, [ctypes.POINTER(BlockTail), c_void_p]),
     "soccdpt_patch_merge_gather_fwd": (_I, [c_void_p, c_void_p, _I, _I, _I, _I, c_void_p]),
     "soccdpt_upsample_bilinear_fwd": (_I, [c_void_p, c_void_p] + [_I] * 6 + [c_void_p]),
     "soccdpt_seg_finish_fwd": (_I, [c_void_p, c_void_p] + [_I] * 5 + [c_void_p]),

@@ -235,6 +235,25 @@ class NetworkEngine:
         plan["keep"].append(c)
         plan["ops"].append(_Launch("conv", fn, ctypes.byref(c)))
 
+    def _fuse_tail(self, C, which):
+        """Fused Swin block tails (csrc/swin_block_tail.cu) cover C <= 256; SOCCDPT_FUSED_TAIL = comma list of {mlp, proj}
+        or 0 switches them per branch for A/B runs (default: both).  The CUDA-core cross-check engine keeps the un-fused ops."""
+        if self.conv_impl != "tcgen05" or C > 256 or C % 32:
+            return False
+        sel = os.environ.get("SOCCDPT_FUSED_TAIL", "mlp,proj")
+        return which in sel.split(",")
+
+    def _block_tail(self, plan, x, w1, b1, w2, b2, norm, master, y, M, C, HID):
+        a = _cabi.BlockTail()
+        a.x, a.w2, a.b2 = x.data_ptr(), w2.data_ptr(), b2.data_ptr()
+        a.w1 = w1.data_ptr() if w1 is not None else None
+        a.b1 = b1.data_ptr() if b1 is not None else None
+        a.gamma, a.beta, a.master, a.y = norm[0].data_ptr(), norm[1].data_ptr(), master.data_ptr(), y.data_ptr()
+        a.M, a.K1, a.HID, a.C, a.eps = M, C, HID, C, 1e-5
+        plan["keep"].append(a)
+        plan["ops"].append(_Launch("block_tail_mlp" if w1 is not None else "block_tail_proj", self.lib.soccdpt_swin_block_tail_fwd,
+                                   ctypes.byref(a)))
+
     def _plan_swin(self, plan, buf, x_in, B, img):
         Wt, lib, ops = self._weights, self.lib, plan["ops"]
         stages = Wt["stages"]
@@ -258,13 +277,20 @@ class NetworkEngine:
                 self._conv(plan, cur, b["wqkv"], 1, 1, M, C, 3 * C, 1, bias=b["bqkv"], y=qkv)
                 ops.append(_Launch("window_attention", lib.soccdpt_window_attention_fwd, qkv.data_ptr(), b["biasT"].data_ptr(),
                                    b["scale"].data_ptr(), att.data_ptr(), B, Hs, Ws, C, b["heads"], b["ws"], b["shift"]))
-                self._conv(plan, att, b["wproj"], 1, 1, M, C, C, 1, bias=b["bproj"], y=tmp)
-                ops.append(_Launch("ln_res", lib.soccdpt_layernorm_master_fwd, tmp.data_ptr(), master.data_ptr(), 1,
-                                   b["n1"][0].data_ptr(), b["n1"][1].data_ptr(), cur.data_ptr(), M, C, ctypes.c_float(1e-5)))
-                self._conv(plan, cur, b["w1"], 1, 1, M, C, 4 * C, 1, bias=b["b1"], act=_cabi.ACT_GELU, y=hid)
-                self._conv(plan, hid, b["w2"], 1, 1, M, 4 * C, C, 1, bias=b["b2"], y=tmp)
-                ops.append(_Launch("ln_res", lib.soccdpt_layernorm_master_fwd, tmp.data_ptr(), master.data_ptr(), 1,
-                                   b["n2"][0].data_ptr(), b["n2"][1].data_ptr(), cur.data_ptr(), M, C, ctypes.c_float(1e-5)))
+                if self._fuse_tail(C, "proj"):
+                    self._block_tail(plan, att, None, None, b["wproj"], b["bproj"], b["n1"], master, cur, M, C, 0)
+                else:
+                    self._conv(plan, att, b["wproj"], 1, 1, M, C, C, 1, bias=b["bproj"], y=tmp)
+                    ops.append(_Launch("ln_res", lib.soccdpt_layernorm_master_fwd, tmp.data_ptr(), master.data_ptr(), 1,
+                                       b["n1"][0].data_ptr(), b["n1"][1].data_ptr(), cur.data_ptr(), M, C, ctypes.c_float(1e-5)))
+                if self._fuse_tail(C, "mlp"):
+                    # fc1 -> GELU -> fc2 -> norm2 -> residual in one kernel; y aliases x (a tile's rows are read before they are written)
+                    self._block_tail(plan, cur, b["w1"], b["b1"], b["w2"], b["b2"], b["n2"], master, cur, M, C, 4 * C)
+                else:
+                    self._conv(plan, cur, b["w1"], 1, 1, M, C, 4 * C, 1, bias=b["b1"], act=_cabi.ACT_GELU, y=hid)
+                    self._conv(plan, hid, b["w2"], 1, 1, M, 4 * C, C, 1, bias=b["b2"], y=tmp)
+                    ops.append(_Launch("ln_res", lib.soccdpt_layernorm_master_fwd, tmp.data_ptr(), master.data_ptr(), 1,
+                                       b["n2"][0].data_ptr(), b["n2"][1].data_ptr(), cur.data_ptr(), M, C, ctypes.c_float(1e-5)))
             taps.append((cur, Hs, Ws, C))   # hooks sit on the last block of every stage (dpt.py:61-72)
             if st["down"] is not None:
                 M2 = B * L // 4

@@ -183,3 +183,20 @@ def global_attention(qkv, heads):
     out = torch.empty((B, N, C3 // 3), dtype=torch.bfloat16, device=qkv.device)
     _cabi.check(lib.soccdpt_global_attention_fwd(qkv.data_ptr(), out.data_ptr(), B, N, heads, C3 // 3 // heads, _s()), "global_attention")
     return out
+
+
+def swin_block_tail(x, w2, b2, gamma, beta, master, w1=None, b1=None, eps=1e-5, y=None):
+    """x (M,K1) bf16; w1 (HID,K1) bf16 | None; w2 (C,HID) | (C,K1) bf16; master (M,C) f32 updated in place. Returns y bf16."""
+    lib = _cabi.load()
+    M, K1 = x.shape
+    C = w2.shape[0]
+    a = _cabi.BlockTail()
+    a.x, a.w2, a.b2, a.gamma, a.beta = x.data_ptr(), w2.data_ptr(), b2.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    a.w1 = w1.data_ptr() if w1 is not None else None
+    a.b1 = b1.data_ptr() if b1 is not None else None
+    if y is None:
+        y = torch.empty((M, C), dtype=torch.bfloat16, device=x.device)
+    a.master, a.y = master.data_ptr(), y.data_ptr()
+    a.M, a.K1, a.HID, a.C, a.eps = M, K1, (w1.shape[0] if w1 is not None else 0), C, eps
+    _cabi.check(lib.soccdpt_swin_block_tail_fwd(ctypes.byref(a), _s()), "swin_block_tail")
+    return y

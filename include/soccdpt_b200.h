@@ -62,6 +62,23 @@ int soccdpt_occupancy_points_fwd(const uint32_t *mask, const int grid[3], const 
                                  double *points, long long capacity, long long *count, void *workspace,
                                  size_t workspace_bytes, soccdpt_stream_t stream);
 
+/* Counting voxeliser ("count(threshold) / argmax" modes): the reference's ground-truth generator
+ * OccupancyProcessor.transform_points_to_occupancy_grid_vect, SOccDPT/datasets/bdd_helper.py:289-362 (numpy on the CPU).
+ *   points     f64 or f32 [n,3] camera points (points_f64 selects; numpy's promotion rules decide the arithmetic:
+ *              f64 points -> all in fp64, f32 points -> fp32 division, fp64 product), NaN / inf rows are skipped
+ *   semantics  i64 or i32 [n] class ids; negative ids index from the end like numpy; ids outside [-C, C) are counted in
+ *              *bad_class (numpy raises IndexError there) and skipped
+ *   counts     i32 [G0,G1,G2,C], ACCUMULATED into (the caller zeroes it; several calls = several point sets)
+ * soccdpt_voxel_count_finish_fwd thresholds the counts: grid_gt u8 [G0,G1,G2,C] = count > threshold (the reference's
+ * "occupancy_grid", :357), mask_ge = bit-packed cells with count >= threshold (layout of SOCCDPT_OCC_PACKED; feed it to
+ * soccdpt_occupancy_points_fwd for the reference's "occupancy_points", :340-355), labels u8 [G0,G1,G2] = 0 for empty
+ * cells, else 1 + argmax_c count (first maximum).  Any of the three outputs may be NULL. */
+int soccdpt_voxel_count_fwd(const void *points, int points_f64, const void *semantics, int semantics_i64, long long n,
+                            const int grid[3], const float occ_shape[3], int num_classes, int32_t *counts,
+                            unsigned long long *bad_class, soccdpt_stream_t stream);
+int soccdpt_voxel_count_finish_fwd(const int32_t *counts, const int grid[3], int num_classes, float threshold,
+                                   uint8_t *grid_gt, uint32_t *mask_ge, uint8_t *labels, soccdpt_stream_t stream);
+
 /* ------------------------------------------------------------------ input pipeline
  * The reference's per-frame CPU transform, SOccDPT/model/loader.py:256-270 -> transforms.py:53-251:
  * cv2.resize(INTER_CUBIC) of a uint8 HWC frame to (dst_w, dst_h), NormalizeImage(0.5, 0.5), PrepareForNet.

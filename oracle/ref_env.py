@@ -73,3 +73,17 @@ def load_reference_function(rel_path, name, namespace=None):
             exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
             return ns[name]
     raise KeyError(f"{name} not found in {path}")
+
+
+def load_reference_class(rel_path, name, namespace=None):
+    """Compiles ONE top-level class of a reference source file in memory (same purpose and rules as load_reference_function)."""
+    import ast
+    path = os.path.join(REFERENCE_ROOT, rel_path)
+    with open(path) as f:
+        src = f.read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == name:
+            ns = dict(namespace or {})
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+            return ns[name]
+    raise KeyError(f"{name} not found in {path}")

@@ -69,6 +69,9 @@ SYMBOLS = {
     "soccdpt_grid_pack_fwd": (_I, [c_void_p, ctypes.POINTER(_I), _I, c_void_p, c_void_p]),
     "soccdpt_occupancy_points_fwd": (_I, [c_void_p, ctypes.POINTER(_I), ctypes.POINTER(_F), _I, c_void_p, _LL, c_void_p,
                                          c_void_p, _SZ, c_void_p]),
+    "soccdpt_voxel_count_fwd": (_I, [c_void_p, _I, c_void_p, _I, _LL, ctypes.POINTER(_I), ctypes.POINTER(_F), _I, c_void_p, c_void_p,
+                                     c_void_p]),
+    "soccdpt_voxel_count_finish_fwd": (_I, [c_void_p, ctypes.POINTER(_I), _I, _F, c_void_p, c_void_p, c_void_p, c_void_p]),
     "soccdpt_voxel_workspace_bytes": (_SZ, [ctypes.POINTER(Geometry), _I, _I]),
     "soccdpt_voxelize_fwd": (_I, [c_void_p, c_void_p, _I, ctypes.POINTER(Geometry), c_void_p, c_void_p, _I,
                                   c_void_p, _SZ, c_void_p]),

@@ -85,23 +85,26 @@ struct LnWarp {
     int tile0, tile_step, n_tiles;  // this warp group's tiles: tile0 + k * tile_step, k < n_tiles
 
     __device__ __forceinline__ long long row0_of(int k) const { return (long long)(tile0 + k * tile_step) * BM + sub * 32; }
-    // requests block q (may lie beyond the end of the stream: then only the (empty) group is committed)
-    __device__ __forceinline__ void fetch(int q) const {
-        const int k = q / nb, b = q - k * nb;
-        if (k < n_tiles) {
-            const long long r0 = row0_of(k);
+    // requests the next block of the stream (beyond its end only the (empty) group is committed); ring slot = request order
+    int fk, fb, fslot;              // fetch cursor: (tile k, block b) and the ring slot it goes to
+    __device__ __forceinline__ void fetch_next() {
+        if (fk < n_tiles) {
+            const long long r0 = row0_of(fk);
             const int rr = lane >> 3, ch = lane & 7;
-            float *dst = ring + (q % LN_RING) * 1024 + lane * 4;
+            float *dst = ring + fslot * 1024 + lane * 4;
+            const float *srcp = a->master + r0 * a->C + fb * 32 + ch * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const long long r = r0 + i * 4 + rr;
-                if (r < a->M) cp_async16(dst + i * 128, a->master + r * a->C + b * 32 + ch * 4);
+                const int rl = i * 4 + rr;
+                if (r0 + rl < a->M) cp_async16(dst + i * 128, srcp + (long long)rl * a->C);
             }
         }
         cp_async_commit();
+        if (++fb == nb) { fb = 0; ++fk; }
+        if (++fslot == LN_RING) fslot = 0;
     }
     // block q of the stream: TMEM columns [c, c + 32) of this warp's rows at taddr
-    __device__ __forceinline__ void block(int q, uint32_t taddr, int c, float rstd, float nmr, long long r0) const {
+    __device__ __forceinline__ void block(int slot, uint32_t taddr, int c, float rstd, float nmr, long long r0) const {
         uint32_t raw[32];
         tmem_ld32_nowait(taddr + (uint32_t)c, raw);
         tmem_ld_wait();
@@ -120,7 +123,7 @@ struct LnWarp {
         cp_async_wait<LN_RING - 1>();          // this thread's copies of block q have landed (it reads back only its own)
         __syncwarp();
         const int rr = lane >> 3, ch = lane & 7;
-        const float *src = ring + (q % LN_RING) * 1024 + lane * 4;
+        const float *src = ring + slot * 1024 + lane * 4;
         const int C = a->C;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -142,7 +145,8 @@ struct LnWarp {
         __syncwarp();
     }
     // one tile: statistics in one TMEM pass (sums shifted by the row's first value), then the blocks
-    __device__ __forceinline__ void tile(int k, uint32_t d2) const {
+    int cslot;                      // ring slot of the next block to consume
+    __device__ __forceinline__ void tile(int k, uint32_t d2) {
         const int C = a->C;
         float s1 = 0.f, s2 = 0.f, shift = 0.f;
         for (int c = 0; c < C; c += 32) {
@@ -170,9 +174,9 @@ struct LnWarp {
         const float nmr = -(shift + ms) * rstd;
         const long long r0 = row0_of(k);
         for (int b = 0; b < nb; ++b) {
-            const int q = k * nb + b;
-            block(q, d2, b * 32, rstd, nmr, r0);
-            fetch(q + LN_RING);                                    // refill the ring slot just consumed
+            block(cslot, d2, b * 32, rstd, nmr, r0);
+            if (++cslot == LN_RING) cslot = 0;
+            fetch_next();                                          // refill the ring slot just consumed
         }
     }
 };
@@ -246,7 +250,8 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
     if (warp == 0) {
         // ============================== TMA producer ==============================
         if (lane == 0 && my_tiles > 0) {
-            uint32_t c1 = 0, c2 = 0;            // running tile counters of the two weight rings
+            int s1 = 0, s2 = 0;                 // ring slots and their phase bits (no runtime divisions: these threads are latency bound)
+            uint32_t ph1 = 0, ph2 = 0;
             auto load_w1 = [&](int j, int kc, int slot) {
                 const bool tail = kc >= p.kc64;
                 // resident: the tiles of a hidden chunk are packed (the 8 KB tail tile does not take a 16 KB slot)
@@ -279,23 +284,36 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                 if (p.ktail) tma_load_2d(sA + p.kc64 * 16384, &mx32, &bars->a_full, p.kc64 * 64, row0);
                 if (RES) continue;
                 if (MLP) {
+                    // fc1 weight tiles only: the fc2 ring has its own producer (warp 3) -- with one thread feeding both, a full
+                    // fc2 ring (its slots free up only after GELU) kept the fc1 tiles of the NEXT chunk from being requested
                     for (int j = 0; j < p.nch; ++j) {
-                        for (int kc = 0; kc < kc1; ++kc, ++c1) {
-                            const int slot = (int)(c1 % (uint32_t)p.ns1);
-                            mbar_wait(&bars->w1_empty[slot], ((c1 / (uint32_t)p.ns1) & 1u) ^ 1u);
-                            load_w1(j, kc, slot);
-                        }
-                        for (int h = 0; h < 2; ++h, ++c2) {
-                            const int slot = (int)(c2 % (uint32_t)p.ns2);
-                            mbar_wait(&bars->w2_empty[slot], ((c2 / (uint32_t)p.ns2) & 1u) ^ 1u);
-                            load_w2(j * HC + h * 64, false, slot);
+                        for (int kc = 0; kc < kc1; ++kc) {
+                            mbar_wait(&bars->w1_empty[s1], ph1 ^ 1u);
+                            load_w1(j, kc, s1);
+                            if (++s1 == p.ns1) { s1 = 0; ph1 ^= 1u; }
                         }
                     }
                 } else {
-                    for (int kc = 0; kc < kc1; ++kc, ++c2) {
-                        const int slot = (int)(c2 % (uint32_t)p.ns2);
-                        mbar_wait(&bars->w2_empty[slot], ((c2 / (uint32_t)p.ns2) & 1u) ^ 1u);
-                        load_w2(kc * 64, kc >= p.kc64, slot);
+                    for (int kc = 0; kc < kc1; ++kc) {
+                        mbar_wait(&bars->w2_empty[s2], ph2 ^ 1u);
+                        load_w2(kc * 64, kc >= p.kc64, s2);
+                        if (++s2 == p.ns2) { s2 = 0; ph2 ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ============================== second TMA producer: the fc2 weight ring (streamed two-GEMM mode) ==============================
+        if (MLP && !RES && lane == 0 && my_tiles > 0) {
+            int s2 = 0;
+            uint32_t ph2 = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                for (int j = 0; j < p.nch; ++j) {
+                    for (int h = 0; h < 2; ++h) {
+                        mbar_wait(&bars->w2_empty[s2], ph2 ^ 1u);
+                        mbar_expect_tx(&bars->w2_full[s2], (uint32_t)C * 128u);
+                        tma_load_2d(sW2 + s2 * p.w2_slot, &mw2_64, &bars->w2_full[s2], j * HC + h * 64, 0);
+                        if (++s2 == p.ns2) { s2 = 0; ph2 ^= 1u; }
                     }
                 }
             }
@@ -309,7 +327,9 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
             const uint32_t w1_lo0 = (uint32_t)umma_desc(smem_u32(sW1), 128);
             const uint32_t w2_lo0 = (uint32_t)umma_desc(smem_u32(sW2), 128);
             const uint32_t w2_step = p.w2_slot >> 4;
-            uint32_t c1 = 0, c2 = 0;
+            int s1 = 0, s2 = 0;                 // ring slots / phase bits of the streamed weight rings
+            uint32_t ph1 = 0, ph2 = 0;
+            const bool d2_two = p.d2_bufs == 2;
             if (MLP) {
                 const int total = my_tiles * p.nch;
                 const int nch = p.nch, kc64 = p.kc64, ktail = p.ktail;
@@ -328,10 +348,10 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                         if (RES) {
                             if (it == 0) { mbar_wait(&bars->w1_full[j * (kc64 + ktail) + kc], 0u); tc_fence_after(); }
                         } else {
-                            slot = (int)(c1 % (uint32_t)p.ns1);
-                            mbar_wait(&bars->w1_full[slot], (c1 / (uint32_t)p.ns1) & 1u);
+                            slot = s1;
+                            mbar_wait(&bars->w1_full[slot], ph1);
                             tc_fence_after();
-                            ++c1;
+                            if (++s1 == p.ns1) { s1 = 0; ph1 ^= 1u; }
                             b_lo = w1_lo0 + (uint32_t)slot * (W1_SLOT >> 4);
                         }
 #pragma unroll
@@ -348,10 +368,10 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                         if (RES) {
                             if (it == 0) { mbar_wait(&bars->w1_full[j * (kc64 + 1) + kc64], 0u); tc_fence_after(); }
                         } else {
-                            slot = (int)(c1 % (uint32_t)p.ns1);
-                            mbar_wait(&bars->w1_full[slot], (c1 / (uint32_t)p.ns1) & 1u);
+                            slot = s1;
+                            mbar_wait(&bars->w1_full[slot], ph1);
                             tc_fence_after();
-                            ++c1;
+                            if (++s1 == p.ns1) { s1 = 0; ph1 ^= 1u; }
                             b_lo = w1_lo0 + (uint32_t)slot * (W1_SLOT >> 4);
                         }
                         umma_ss_lo(d1, a_lo, b_lo, hi64, idesc1, acc);
@@ -363,9 +383,9 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                 };
                 // fc2 of chunk j: D2 (+)= H (bf16 pairs in the consumed D1 columns) x W2[:, chunk]
                 auto fc2 = [&](int g, int it, int j) {
-                    const int db2 = it % p.d2_bufs;
+                    const int db2 = d2_two ? (it & 1) : 0;
                     if (j == 0) {
-                        mbar_wait(&bars->d2_empty[db2], (uint32_t)((it / p.d2_bufs) & 1) ^ 1u);
+                        mbar_wait(&bars->d2_empty[db2], (uint32_t)((d2_two ? it >> 1 : it) & 1) ^ 1u);
                         tc_fence_after();
                     }
                     mbar_wait(&bars->h_full[g & 1], (uint32_t)((g >> 1) & 1));
@@ -380,10 +400,10 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                             slot = j * 2 + hh;
                             if (it == 0) { mbar_wait(&bars->w2_full[slot], 0u); tc_fence_after(); }
                         } else {
-                            slot = (int)(c2 % (uint32_t)p.ns2);
-                            mbar_wait(&bars->w2_full[slot], (c2 / (uint32_t)p.ns2) & 1u);
+                            slot = s2;
+                            mbar_wait(&bars->w2_full[slot], ph2);
                             tc_fence_after();
-                            ++c2;
+                            if (++s2 == p.ns2) { s2 = 0; ph2 ^= 1u; }
                         }
                         const uint32_t b_lo = w2_lo0 + (uint32_t)slot * w2_step;
 #pragma unroll
@@ -424,10 +444,10 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                             slot = kc;
                             if (it == 0) { mbar_wait(&bars->w2_full[slot], 0u); tc_fence_after(); }
                         } else {
-                            slot = (int)(c2 % (uint32_t)p.ns2);
-                            mbar_wait(&bars->w2_full[slot], (c2 / (uint32_t)p.ns2) & 1u);
+                            slot = s2;
+                            mbar_wait(&bars->w2_full[slot], ph2);
                             tc_fence_after();
-                            ++c2;
+                            if (++s2 == p.ns2) { s2 = 0; ph2 ^= 1u; }
                         }
                         const uint32_t b_lo = w2_lo0 + (uint32_t)slot * w2_step;
                         if (kc < kc64) {
@@ -501,13 +521,15 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
             w.tile0 = MLP ? (int)blockIdx.x : (int)blockIdx.x + grp * (int)gridDim.x;
             w.tile_step = MLP ? (int)gridDim.x : 2 * (int)gridDim.x;
             w.n_tiles = MLP ? my_tiles : (my_tiles - grp + 1) / 2;
+            w.fk = 0; w.fb = 0; w.fslot = 0; w.cslot = 0;
 #pragma unroll
-            for (int q = 0; q < LN_RING; ++q) w.fetch(q);
+            for (int q = 0; q < LN_RING; ++q) w.fetch_next();
             for (int k = 0; k < w.n_tiles; ++k) {
                 const int it = MLP ? k : 2 * k + grp;
                 if (it + 2 >= my_tiles) soccdpt::pdl_trigger();       // the CTA's tail: let the next kernel's CTAs in
-                const int db2 = MLP ? it % p.d2_bufs : grp;
-                const uint32_t d2_par = MLP ? (uint32_t)((it / p.d2_bufs) & 1) : (uint32_t)(k & 1);
+                const bool d2_two = p.d2_bufs == 2;
+                const int db2 = MLP ? (d2_two ? (it & 1) : 0) : grp;
+                const uint32_t d2_par = MLP ? (uint32_t)((d2_two ? it >> 1 : it) & 1) : (uint32_t)(k & 1);
                 mbar_wait(&bars->d2_full[db2], d2_par);
                 tc_fence_after();
                 w.tile(k, t_lane + (MLP ? 256u + (uint32_t)(db2 * C) : (uint32_t)(db2 * 256)));
@@ -583,6 +605,7 @@ extern "C" int soccdpt_swin_block_tail_fwd(const soccdpt_block_tail_t *a, soccdp
         if (mlp) {
             SOCCDPT_REQUIRE(rest >= 2ll * W1_SLOT, "block_tail: shapes do not fit shared memory (C=%d K1=%d)", C, K1);
             if (rest >= (long long)(2 * kc1) * W1_SLOT + 2ll * p.w2_slot) { p.ns2 = 4; rest -= 2ll * p.w2_slot; }
+            else if (rest >= (long long)(kc1 + 1) * W1_SLOT + (long long)p.w2_slot) { p.ns2 = 3; rest -= p.w2_slot; }
             p.ns1 = (int)(rest / W1_SLOT);
             if (p.ns1 > MAX_SLOTS) p.ns1 = MAX_SLOTS;
         } else {

@@ -135,9 +135,20 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def current_stream():
+def current_stream(device=None):
+    """cudaStream_t of torch's current stream on ``device`` (default: the current device).  Launch sites pass the device of
+    the tensors they hand over and run inside ``torch.cuda.device(device)``: the library launches on the CURRENT device."""
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def normalize_device(device):
+    """torch.device('cuda') -> torch.device('cuda', current index): ONE spelling per device for caches keyed by device."""
+    import torch
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise SoccdptError("soccdpt_b200 runs on CUDA devices only (no CPU fallback)")
+    return torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
 
 
 def launch_count():

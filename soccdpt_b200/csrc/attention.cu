@@ -183,10 +183,9 @@ extern "C" int soccdpt_window_attention_fwd(const void *qkv, const float *bias, 
     const int threads = N > 256 ? 192 : (N + 31) / 32 * 32;   // larger windows: several query rows per thread
     const size_t smem = (size_t)N * D * 2 * sizeof(float) + (size_t)N * sizeof(int);
     SOCCDPT_REQUIRE(smem <= 227 * 1024, "window_attention: window too large for shared memory");
-    static size_t configured = 0;
-    if (smem > configured) {
+    static soccdpt::SmemAttr configured;
+    if (configured.need(smem)) {
         SOCCDPT_CUDA(cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
     }
     dim3 grid((unsigned)(batch * (Hs / ws) * (Ws / ws)), (unsigned)heads);
     SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ATTENTION, window_attention_kernel, grid, dim3(threads), smem, soccdpt::as_stream(stream),

@@ -401,11 +401,10 @@ namespace soccdpt {
 // qkv bf16 [B, Hs*Ws, 3C]; bias_tab f32 [heads][31*31] relative-position table; window must be 16x16
 int launch_window_attention_tc(const void *qkv, const float *bias_tab, const float *scale, void *out, int batch, int Hs, int Ws,
                                int C, int heads, int ws, int shift, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static SmemAttr configured;
+    if (configured.need(TC_SMEM_BYTES)) {
         SOCCDPT_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         SOCCDPT_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        configured = true;
     }
     dim3 grid((unsigned)(batch * (Hs / ws) * (Ws / ws)), (unsigned)heads);
     if (shift > 0)

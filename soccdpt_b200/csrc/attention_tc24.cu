@@ -537,11 +537,10 @@ namespace soccdpt {
 // qkv bf16 [B, Hs*Ws, 3C]; bias_tab f32 [heads][47*47] relative-position table; window must be 24x24
 int launch_window_attention_tc24(const void *qkv, const float *bias_tab, const float *scale, void *out, int batch, int Hs, int Ws,
                                  int C, int heads, int shift, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static SmemAttr configured;
+    if (configured.need(SMEM_BYTES)) {
         SOCCDPT_CUDA(cudaFuncSetAttribute(window_attention_tc24_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         SOCCDPT_CUDA(cudaFuncSetAttribute(window_attention_tc24_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
     }
     dim3 grid((unsigned)(batch * (Hs / WS) * (Ws / WS)), (unsigned)heads);
     if (shift > 0)

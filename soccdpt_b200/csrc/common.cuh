@@ -41,16 +41,36 @@ inline int check_launch(const char *what) {
         }                                                                         \
     } while (0)
 
-inline int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
+// The library serves whichever device is current on the calling thread (one process per GPU is the deployment model, but
+// nothing here assumes device 0): device properties and per-kernel attributes are cached PER DEVICE.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < kMaxDevices) ? d : 0;
 }
+inline int sm_count() {
+    static int n[kMaxDevices] = {};
+    const int d = current_device();
+    if (n[d] == 0) {
+        cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d);
+        if (n[d] <= 0) n[d] = 148;
+    }
+    return n[d];
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: remembers, per device, the largest size
+// it has been raised to.  `if (attr.need(bytes)) cudaFuncSetAttribute(...)`.
+struct SmemAttr {
+    size_t v[kMaxDevices] = {};
+    bool need(size_t bytes) {
+        const int d = current_device();
+        if (bytes > v[d]) {
+            v[d] = bytes;
+            return true;
+        }
+        return false;
+    }
+};
 
 inline cudaStream_t as_stream(soccdpt_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

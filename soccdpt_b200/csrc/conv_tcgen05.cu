@@ -832,11 +832,10 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     cudaStream_t st = soccdpt::as_stream(stream);
 #define SOCC_LAUNCH(A, M, HL)                                                                                           \
     do {                                                                                                                \
-        static bool configured = false;                                                                                 \
-        if (!configured) {                                                                                              \
+        static soccdpt::SmemAttr configured;                                                                            \
+        if (configured.need(SMEM_BYTES)) {                                                                              \
             SOCCDPT_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<A, M, HL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                               SMEM_BYTES));                                                             \
-            configured = true;                                                                                          \
         }                                                                                                               \
         SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_CONV, conv_tcgen05_kernel<A, M, HL>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, map_a, map_b, \
                                          map_y, map_yr, p));                                                            \

@@ -115,10 +115,9 @@ extern "C" int soccdpt_depth_tail_fwd(const void *T, const float *b2, const floa
     SOCCDPT_REQUIRE(N >= 1 && h >= 2 && w >= 2, "depth_tail: bad shape %dx%dx%d", N, h, w);
     const size_t smem = (size_t)w * VP * sizeof(float);
     SOCCDPT_REQUIRE(smem <= 200 * 1024, "depth_tail: row buffer of %zu bytes does not fit shared memory (w=%d)", smem, w);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static soccdpt::SmemAttr configured;
+    if (configured.need(smem)) {
         SOCCDPT_CUDA(cudaFuncSetAttribute(depth_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
     }
     SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, depth_tail_kernel, dim3((unsigned)(N * 2 * h)), dim3(256), smem, soccdpt::as_stream(stream),
                                      static_cast<const bf16 *>(T), b2, pw, pb, depth, N, h, w));

@@ -293,10 +293,9 @@ int global_attention_tc_max_tokens() { return MAX_BLOCKS * KB; }
 int launch_global_attention_tc(const void *qkv, void *out, int batch, int N, int heads, cudaStream_t st) {
     const int nb = (N + KB - 1) / KB;
     const size_t smem = (size_t)SM_K + (size_t)nb * (16384 + 2 * 8192) + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static soccdpt::SmemAttr configured;
+    if (configured.need(smem)) {
         SOCCDPT_CUDA(cudaFuncSetAttribute(global_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
     }
     dim3 grid((unsigned)(batch * heads), (unsigned)((N + 127) / 128));
     SOCCDPT_CUDA(launch_pdl(PDL_ATTENTION, global_attention_tc_kernel, grid, dim3(GT), smem, st, static_cast<const bf16 *>(qkv),

@@ -493,10 +493,9 @@ int soccdpt_global_attention_fwd(const void *qkv, void *out, int batch, int N, i
     const int Npad = (N + GCH - 1) / GCH * GCH;
     const size_t smem = (size_t)Npad * GD * 2 * sizeof(bf16);
     SOCCDPT_REQUIRE(smem <= 220 * 1024, "global_attention: %d tokens do not fit shared memory", N);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static soccdpt::SmemAttr configured;
+    if (configured.need(smem)) {
         SOCCDPT_CUDA(cudaFuncSetAttribute(global_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
     }
     dim3 grid((unsigned)(batch * heads), (unsigned)((N + 127) / 128));
     global_attention_kernel<<<grid, 128, smem, soccdpt::as_stream(stream)>>>(static_cast<const bf16 *>(qkv), static_cast<bf16 *>(out),

@@ -653,7 +653,9 @@ extern "C" int soccdpt_swin_block_tail_fwd(const soccdpt_block_tail_t *a, soccdp
     cudaStream_t st = soccdpt::as_stream(stream);
 #define SOCC_TAIL(M_, R_)                                                                                                     \
     do {                                                                                                                      \
-        SOCCDPT_CUDA(cudaFuncSetAttribute(swin_block_tail_kernel<M_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX)); \
+        static soccdpt::SmemAttr configured;                                                                                  \
+        if (configured.need(SMEM_MAX))                                                                                        \
+            SOCCDPT_CUDA(cudaFuncSetAttribute(swin_block_tail_kernel<M_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX)); \
         SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_CONV, swin_block_tail_kernel<M_, R_>, dim3(grid), dim3(NT), smem_bytes, st, mx64, \
                                          mx32, mw1_64, mw1_32, mw2_64, mw2_32, p));                                           \
     } while (0)

@@ -64,7 +64,8 @@ class NetworkEngine:
         self.seg_head = seg_head if seg_head is not None else (getattr(net, "seg_head", None) if "seg" in self.heads else None)
         self.conv_impl = conv_impl        # "tcgen05" (product) | "ref" (CUDA-core cross-check, tests only)
         self._weights = None
-        self._plans = {}
+        self._plans = {}                 # (batch, device) -> plan, least recently used first; at most `max_plans` are kept
+        self.max_plans = int(os.environ.get("SOCCDPT_MAX_PLANS", "4"))
         self.lib = _cabi.load()
         self.use_graphs = os.environ.get("SOCCDPT_CUDA_GRAPH", "0") == "1"
 
@@ -266,7 +267,7 @@ class NetworkEngine:
         hid = buf(B * maxLC * 4)
         cur = buf(B * g0 * g0, E)                               # bf16 copy of the residual stream (GEMM operand)
         master = buf(B * g0 * g0, E, dtype=torch.float32)       # fp32 residual stream
-        ops.append(_Launch("patch_embed", lib.soccdpt_patch_embed_fwd, x_in.data_ptr(), *(t.data_ptr() for t in Wt["pe"]),
+        ops.append(_Launch("patch_embed", lib.soccdpt_patch_embed_fwd, plan["x_arg"], *(t.data_ptr() for t in Wt["pe"]),
                            cur.data_ptr(), master.data_ptr(), B, img, img, E))
         taps = []
         for si, st in enumerate(stages):
@@ -317,7 +318,7 @@ class NetworkEngine:
         # ---- ResNetV2 stem: StdConv 7x7/2 (SAME) -> GroupNorm + ReLU -> MaxPool 3x3/2 (SAME)
         H1 = (img + 1) // 2
         s0 = buf(B, H1, H1, 64)
-        ops.append(_Launch("stem_conv7", lib.soccdpt_stem_conv7_fwd, x_in.data_ptr(), Hy["stem_w"].data_ptr(), s0.data_ptr(), B, img, img))
+        ops.append(_Launch("stem_conv7", lib.soccdpt_stem_conv7_fwd, plan["x_arg"], Hy["stem_w"].data_ptr(), s0.data_ptr(), B, img, img))
         gn(s0, Hy["stem_n"], H1 * H1, 64, True)
         Hc = (H1 + 1) // 2
         cur = buf(B, Hc, Hc, 64)
@@ -423,6 +424,9 @@ class NetworkEngine:
         plan["img"] = img
         x_in = buf(B, 3, img, img, dtype=torch.float32)
         plan["x_in"] = x_in
+        # the network input is read through this slot: the caller's tensor when it is contiguous fp32 (no copy), else / under
+        # CUDA-graph replay the plan's own x_in
+        plan["x_arg"] = ctypes.c_void_p(x_in.data_ptr())
         taps = self._plan_hybrid(plan, buf, x_in, B, img) if self.hybrid else self._plan_swin(plan, buf, x_in, B, img)
         plan["taps"] = taps
 
@@ -485,43 +489,62 @@ class NetworkEngine:
 
     # ------------------------------------------------------------------ run
     def plan_for(self, B, dev):
+        dev = _cabi.normalize_device(dev)
         if self._weights is None:
-            self._weights = self._pack(dev)
-        key = (B, str(dev))
-        if key not in self._plans:
-            self._plans[key] = self._build_plan(B, dev)
-        return self._plans[key]
+            with torch.cuda.device(dev):
+                self._weights = self._pack(dev)
+        key = (B, dev.index)
+        plan = self._plans.pop(key, None)
+        if plan is None:
+            with torch.cuda.device(dev):
+                plan = self._build_plan(B, dev)
+            while len(self._plans) >= max(self.max_plans, 1):       # ragged last batches must not pile up activation sets
+                self._plans.pop(next(iter(self._plans)))
+        self._plans[key] = plan                                      # most recently used last
+        return plan
+
+    def bind_input(self, plan, x=None):
+        """Points the plan's first kernel at ``x`` (contiguous fp32: read in place) or at the plan's own copy of it."""
+        if x is not None and x.dtype == torch.float32 and x.is_contiguous() and not self.use_graphs:
+            plan["x_arg"].value = x.data_ptr()
+            plan["x_ref"] = x                                        # keeps the caller's tensor alive while the launches are queued
+        else:
+            if x is not None:
+                plan["x_in"].copy_(x, non_blocking=True)
+            plan["x_arg"].value = plan["x_in"].data_ptr()
+            plan["x_ref"] = None
 
     def run(self, x):
         """x: (B,3,S,S) fp32 CUDA tensor -> (inverse depth (B,S,S) f32, segmentation (B,C,S,S) f32).
-        The returned tensors are the plan's static output buffers (overwritten by the next call)."""
+        The returned tensors are the plan's static output buffers (overwritten by the next call of this batch size)."""
         if not x.is_cuda:
             raise _cabi.SoccdptError("soccdpt_b200 runs on CUDA devices only (no CPU fallback)")
         B = x.shape[0]
         plan = self.plan_for(B, x.device)
         if tuple(x.shape[1:]) != (3, plan["img"], plan["img"]):
             raise AssertionError("Input image size doesn't match model")
-        plan["x_in"].copy_(x, non_blocking=True)
-        if self.use_graphs:
-            # CUDA-graph replay of the plan's launch list (all buffers are static, every entry point only enqueues on the
-            # current stream): the first call of a plan runs eagerly (sets the kernels' attributes), the second is captured.
-            # What it buys is the host side: ~130 ctypes launches per forward cost more than the kernels at small batches.
-            g = plan.get("graph")
-            if g is None and plan.get("warm", False):
-                g = torch.cuda.CUDAGraph()
-                torch.cuda.synchronize(x.device)
-                with torch.cuda.graph(g):
-                    stream = _cabi.current_stream()
-                    for op in plan["ops"]:
-                        op(stream)
-                plan["graph"] = g
-            if g is not None:
-                g.replay()
-                return plan["depth"], plan["seg"]
-            plan["warm"] = True
-        stream = _cabi.current_stream()
-        for op in plan["ops"]:
-            op(stream)
+        with torch.cuda.device(x.device):      # the C ABI launches on the current device / its current stream
+            self.bind_input(plan, x)
+            if self.use_graphs:
+                # CUDA-graph replay of the plan's launch list (all buffers are static, every entry point only enqueues on the
+                # current stream): the first call of a plan runs eagerly (sets the kernels' attributes), the second is captured.
+                # What it buys is the host side: ~130 ctypes launches per forward cost more than the kernels at small batches.
+                g = plan.get("graph")
+                if g is None and plan.get("warm", False):
+                    g = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize(x.device)
+                    with torch.cuda.graph(g):
+                        stream = _cabi.current_stream(x.device)
+                        for op in plan["ops"]:
+                            op(stream)
+                    plan["graph"] = g
+                if g is not None:
+                    g.replay()
+                    return plan["depth"], plan["seg"]
+                plan["warm"] = True
+            stream = _cabi.current_stream(x.device)
+            for op in plan["ops"]:
+                op(stream)
         return plan["depth"], plan["seg"]
 
     def launches_per_forward(self, B, dev):

@@ -97,7 +97,7 @@ class SOccDPT(BaseModel):
     def _workspace(self, geom, B, mode, device):
         lib = _cabi.load()
         need = int(lib.soccdpt_voxel_workspace_bytes(ctypes_byref(geom), B, mode))
-        key = (str(device), need)
+        key = (_cabi.normalize_device(device).index, need)
         if key not in self._workspaces:
             self._workspaces[key] = torch.empty(max(need, 16), dtype=torch.uint8, device=device)
         return self._workspaces[key], need
@@ -130,9 +130,10 @@ class SOccDPT(BaseModel):
         if packed:
             mode |= _cabi.OCC_PACKED
         ws, need = self._workspace(geom, B, mode, dev)      # voxel mask + resize tables
-        rc = lib.soccdpt_postprocess_fwd(
-            _cabi.ptr(inv_depth), _cabi.ptr(segmentation), B, h, w, ctypes_byref(geom), _cabi.ptr(inv_up), _cabi.ptr(seg_up),
-            _cabi.ptr(points), _cabi.ptr(grid), mode, _cabi.ptr(ws), need, _cabi.current_stream())
+        with torch.cuda.device(dev):                        # the C ABI launches on the current device
+            rc = lib.soccdpt_postprocess_fwd(
+                _cabi.ptr(inv_depth), _cabi.ptr(segmentation), B, h, w, ctypes_byref(geom), _cabi.ptr(inv_up), _cabi.ptr(seg_up),
+                _cabi.ptr(points), _cabi.ptr(grid), mode, _cabi.ptr(ws), need, _cabi.current_stream(dev))
         _cabi.check(rc, "soccdpt_postprocess_fwd")
         if packed:
             grid = self._packed_mask(ws, B)
@@ -166,8 +167,9 @@ class SOccDPT(BaseModel):
             if not packed:
                 grid = torch.empty((B, G[0], G[1], G[2], self.num_classes), dtype=torch.float32, device=dev)
             ws, need = self._workspace(geom, B, mode, dev)
-        rc = lib.soccdpt_voxelize_fwd(_cabi.ptr(inv_depth_up), _cabi.ptr(seg), B, ctypes_byref(geom), _cabi.ptr(points),
-                                      _cabi.ptr(grid), mode, _cabi.ptr(ws), need, _cabi.current_stream())
+        with torch.cuda.device(dev):
+            rc = lib.soccdpt_voxelize_fwd(_cabi.ptr(inv_depth_up), _cabi.ptr(seg), B, ctypes_byref(geom), _cabi.ptr(points),
+                                          _cabi.ptr(grid), mode, _cabi.ptr(ws), need, _cabi.current_stream(dev))
         _cabi.check(rc, "soccdpt_voxelize_fwd")
         if packed:
             grid = self._packed_mask(ws, B)

@@ -4,6 +4,7 @@
     for result in stream.run(host_batches):      # host_batches: iterable of pinned (B,3,S,S) fp32 tensors
         result.inv_depth, result.segmentation    # pinned host tensors at network resolution
         result.occupancy                          # pinned host (G0,G1,G2,C) grid of the call (union over the batch)
+    stream = FrameStream(net, batch=64, frames="u8", frame_shape=(256, 256), result="packed")   # 4x / 2.7x fewer bytes each way
 
 Three CUDA streams (upload / compute / download) and double-buffered device + pinned host buffers overlap
 the host->device copy of batch i+1 and the device->host copy of batch i-1 with the kernels of batch i.
@@ -38,34 +39,72 @@ def gather_masks(grid, group=None):
 
 
 class FrameStream:
-    """`camera_frames=(H, W)`: the batches are pinned uint8 (B, H, W, 3) camera frames instead of network-resolution fp32
-    tensors; they are uploaded as they are and resized / normalised on the device by the input-pipeline kernel
-    (soccdpt_b200.preprocess.GpuTransform, the reference's load_transforms)."""
+    """Double-buffered host <-> device pipeline around ``net``.
 
-    def __init__(self, net, batch, device=None, camera_frames=None):
+    input   ``frames="fp32"``: pinned (B,3,S,S) fp32 tensors at network resolution (what the reference's CPU transform yields);
+            ``frames="u8"`` with ``frame_shape=(H, W)``: pinned uint8 (B,H,W,3) frames (camera frames, or frames already at
+            network resolution: 4x fewer bytes than fp32), resized / normalised on the device by the input-pipeline kernel
+            (soccdpt_b200.preprocess.GpuTransform = the reference's load_transforms).
+    result  ``result="dense"``: network-resolution inverse depth + class maps (fp32) and the dense fp32 occupancy grid of the
+            call (reference_union: the B grid copies are identical, one is read back; per_frame: all B);
+            ``result="packed"``: the same maps as bf16 and the voxeliser's bit-packed occupancy mask (1 MB instead of 25 MB per
+            grid; soccdpt_b200.occupancy.packed_to_points reads it) -- 2.7x fewer device -> host bytes per step.
+    The reference's full 4-tuple (camera-resolution maps + points, 83 MB per frame) is produced on the device by ``net(x)``
+    either way; it is not copied to the host by this class.
+    """
+
+    def __init__(self, net, batch, device=None, camera_frames=None, frames=None, frame_shape=None, result="dense"):
+        from . import _cabi
         self.net = net
         self.batch = batch
-        self.device = torch.device(device) if device is not None else next(net.parameters()).device
-        if self.device.type != "cuda":
-            raise RuntimeError("FrameStream needs a CUDA device (the hot path has no CPU fallback)")
+        self.device = _cabi.normalize_device(device if device is not None else next(net.parameters()).device)
+        if camera_frames is not None:                     # round-1 spelling: uint8 camera frames of this (H, W)
+            frames, frame_shape = "u8", camera_frames
+        frames = frames or "fp32"
+        assert frames in ("fp32", "u8") and result in ("dense", "packed")
+        if not getattr(net, "compute_occ", False):
+            raise ValueError("FrameStream returns the occupancy of every call: construct the model with compute_occ=True")
+        self.result = result
+        self.per_frame = net.occupancy_mode == "per_frame"
         img = net.depth_net.pretrained.model.img_size
         C, G = net.num_classes, net.grid_size
-        self.up, self.comp, self.down = (torch.cuda.Stream(self.device) for _ in range(3))
-        self.x_dev = [torch.empty((batch, 3, img, img), dtype=torch.float32, device=self.device) for _ in range(2)]
+        dev = self.device
+        self.up, self.comp, self.down = (torch.cuda.Stream(dev) for _ in range(3))
+        self.x_dev = [torch.empty((batch, 3, img, img), dtype=torch.float32, device=dev) for _ in range(2)]
         self.transform, self.u8_dev = None, None
-        if camera_frames is not None:
+        if frames == "u8":
             from .preprocess import GpuTransform
-            fh, fw = camera_frames
+            assert frame_shape is not None, "frames='u8' needs frame_shape=(H, W)"
+            fh, fw = frame_shape
             self.transform = GpuTransform(img, img, keep_aspect_ratio=False)
-            self.u8_dev = [torch.empty((batch, fh, fw, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
-        self.d_dev = [torch.empty((batch, img, img), dtype=torch.float32, device=self.device) for _ in range(2)]
-        self.s_dev = [torch.empty((batch, C, img, img), dtype=torch.float32, device=self.device) for _ in range(2)]
-        self.g_dev = [torch.empty((G[0], G[1], G[2], C), dtype=torch.float32, device=self.device) for _ in range(2)]
-        self.d_host = [torch.empty((batch, img, img), dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.s_host = [torch.empty((batch, C, img, img), dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.g_host = [torch.empty((G[0], G[1], G[2], C), dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.h2d_bytes = self.u8_dev[0].numel() if self.u8_dev is not None else self.x_dev[0].numel() * 4
-        self.d2h_bytes = (self.d_host[0].numel() + self.s_host[0].numel() + self.g_host[0].numel()) * 4
+            self.u8_dev = [torch.empty((batch, fh, fw, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+        map_dtype = torch.float32 if result == "dense" else torch.bfloat16
+        ng = batch if self.per_frame else 1
+        if result == "dense":
+            gshape, gdtype = (ng, G[0], G[1], G[2], C), torch.float32
+        else:
+            from .occupancy import mask_words
+            gshape, gdtype = (ng, mask_words(G)), torch.int32
+        # the voxeliser's output form follows the stream's result form (the model's own setting is restored after every call)
+        self._occ_output = "dense" if result == "dense" else "packed"
+        self.d_dev = [torch.empty((batch, img, img), dtype=map_dtype, device=dev) for _ in range(2)]
+        self.s_dev = [torch.empty((batch, C, img, img), dtype=map_dtype, device=dev) for _ in range(2)]
+        self.g_dev = [torch.empty(gshape, dtype=gdtype, device=dev) for _ in range(2)]
+        self.d_host = [torch.empty((batch, img, img), dtype=map_dtype).pin_memory() for _ in range(2)]
+        self.s_host = [torch.empty((batch, C, img, img), dtype=map_dtype).pin_memory() for _ in range(2)]
+        self.g_host = [torch.empty(gshape, dtype=gdtype).pin_memory() for _ in range(2)]
+        stage = self.u8_dev[0] if self.u8_dev is not None else self.x_dev[0]
+        self.h2d_bytes = stage.numel() * stage.element_size()
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.d_host[0], self.s_host[0], self.g_host[0]))
+
+    def _to_maps(self, src, dst):
+        """fp32 network output -> the stream's map dtype (bf16 through the library's conversion kernel)."""
+        if dst.dtype == torch.float32:
+            dst.copy_(src, non_blocking=True)
+        else:
+            from . import _cabi
+            _cabi.check(_cabi.load().soccdpt_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(),
+                                                         _cabi.current_stream(self.device)), "f32_to_bf16")
 
     @torch.no_grad()
     def run(self, host_batches):
@@ -75,41 +114,52 @@ class FrameStream:
         ev_down = [torch.cuda.Event() for _ in range(2)]
         ev_free_x = [None, None]       # compute finished reading x_dev[slot]
         pending = []
-        i = -1
-        for i, xh in enumerate(host_batches):
-            slot = i & 1
-            stage_in = self.u8_dev if self.u8_dev is not None else self.x_dev
-            assert tuple(xh.shape) == tuple(stage_in[0].shape) and xh.dtype == stage_in[0].dtype, \
-                "every batch must have the FrameStream's shape and dtype"
-            with torch.cuda.stream(self.up):
-                if ev_free_x[slot] is not None:
-                    self.up.wait_event(ev_free_x[slot])
-                stage_in[slot].copy_(xh, non_blocking=True)
-                ev_up[slot].record(self.up)
-            with torch.cuda.stream(self.comp):
-                self.comp.wait_event(ev_up[slot])
-                if i >= 2:
-                    self.comp.wait_event(ev_down[slot])      # download of batch i-2 has drained this slot
-                if self.transform is not None:
-                    self.transform(self.u8_dev[slot], out=self.x_dev[slot])
-                out = self.net(self.x_dev[slot])
-                depth, seg = self.net.network_outputs(self.batch, self.device)
-                self.d_dev[slot].copy_(depth, non_blocking=True)
-                self.s_dev[slot].copy_(seg, non_blocking=True)
-                self.g_dev[slot].copy_(out[3][0], non_blocking=True)
-                ev_comp[slot].record(self.comp)
-                ev_free_x[slot] = ev_comp[slot]
-            with torch.cuda.stream(self.down):
-                self.down.wait_event(ev_comp[slot])
-                self.d_host[slot].copy_(self.d_dev[slot], non_blocking=True)
-                self.s_host[slot].copy_(self.s_dev[slot], non_blocking=True)
-                self.g_host[slot].copy_(self.g_dev[slot], non_blocking=True)
-                ev_down[slot].record(self.down)
-            pending.append((i, slot))
-            if len(pending) == 2:
-                j, sj = pending.pop(0)
+        net = self.net
+        with torch.cuda.device(self.device):
+            for i, xh in enumerate(host_batches):
+                slot = i & 1
+                stage_in = self.u8_dev if self.u8_dev is not None else self.x_dev
+                assert tuple(xh.shape) == tuple(stage_in[0].shape) and xh.dtype == stage_in[0].dtype, \
+                    "every batch must have the FrameStream's shape and dtype"
+                with torch.cuda.stream(self.up):
+                    if ev_free_x[slot] is not None:
+                        self.up.wait_event(ev_free_x[slot])
+                    stage_in[slot].copy_(xh, non_blocking=True)
+                    ev_up[slot].record(self.up)
+                with torch.cuda.stream(self.comp):
+                    self.comp.wait_event(ev_up[slot])
+                    if i >= 2:
+                        self.comp.wait_event(ev_down[slot])      # download of batch i-2 has drained this slot
+                    if self.transform is not None:
+                        self.transform(self.u8_dev[slot], out=self.x_dev[slot])
+                    saved = net.occupancy_output
+                    net.occupancy_output = self._occ_output
+                    try:
+                        depth, seg = net.network(self.x_dev[slot])      # the buffers this call filled (static engine buffers)
+                        occ = net.get_semantic_occupancy(depth, seg)[3]
+                    finally:
+                        net.occupancy_output = saved
+                    self._to_maps(depth, self.d_dev[slot])
+                    self._to_maps(seg, self.s_dev[slot])
+                    self.g_dev[slot].copy_(occ.reshape(self.g_dev[slot].shape) if self.per_frame or self.result == "packed"
+                                           else occ[:1], non_blocking=True)
+                    ev_comp[slot].record(self.comp)
+                    ev_free_x[slot] = ev_comp[slot]
+                with torch.cuda.stream(self.down):
+                    self.down.wait_event(ev_comp[slot])
+                    self.d_host[slot].copy_(self.d_dev[slot], non_blocking=True)
+                    self.s_host[slot].copy_(self.s_dev[slot], non_blocking=True)
+                    self.g_host[slot].copy_(self.g_dev[slot], non_blocking=True)
+                    ev_down[slot].record(self.down)
+                pending.append((i, slot))
+                if len(pending) == 2:
+                    j, sj = pending.pop(0)
+                    ev_down[sj].synchronize()
+                    yield self._result(sj, j)
+            for j, sj in pending:
                 ev_down[sj].synchronize()
-                yield FrameResult(self.d_host[sj], self.s_host[sj], self.g_host[sj], j)
-        for j, sj in pending:
-            ev_down[sj].synchronize()
-            yield FrameResult(self.d_host[sj], self.s_host[sj], self.g_host[sj], j)
+                yield self._result(sj, j)
+
+    def _result(self, slot, index):
+        g = self.g_host[slot]
+        return FrameResult(self.d_host[slot], self.s_host[slot], g if self.per_frame else g[0], index)

@@ -27,7 +27,7 @@ BATCHES = [1, 8, 64]
 def main():
     peak = 6539.9
     try:
-        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbps"]
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
     yml = write_calib_yaml("/tmp/bench_voxeliser_calib.yaml")

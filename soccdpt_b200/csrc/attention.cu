@@ -16,6 +16,8 @@
 namespace soccdpt {
 int launch_window_attention_tc(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
                                int C, int heads, int ws, int shift, cudaStream_t st);
+int launch_window_attention_ws(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
+                               int C, int heads, int shift, cudaStream_t st);
 int launch_window_attention_tc24(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
                                  int C, int heads, int shift, cudaStream_t st);
 }
@@ -175,6 +177,11 @@ extern "C" int soccdpt_window_attention_fwd(const void *qkv, const float *bias, 
     // (attention_tc.cu, attention_tc24.cu); the small last-stage windows (8x8, 12x12) use the CUDA-core kernel above.
     // SOCCDPT_ATTENTION_REF=1 (tests only) forces the CUDA-core kernel for an on-device cross-check.
     static const bool force_ref = getenv("SOCCDPT_ATTENTION_REF") != nullptr;
+    // 256-token windows: the warp-specialised persistent kernel (attention_ws.cu); SOCCDPT_ATTN_WS=0 keeps round 1's
+    // one-CTA-per-(window, head) kernel for A/B runs
+    static const bool use_ws = !(getenv("SOCCDPT_ATTN_WS") && getenv("SOCCDPT_ATTN_WS")[0] == '0');
+    if (N == 256 && !force_ref && use_ws)
+        return soccdpt::launch_window_attention_ws(qkv, bias, scale, out, batch, Hs, Ws, C, heads, shift, soccdpt::as_stream(stream));
     if (N == 256 && !force_ref) return soccdpt::launch_window_attention_tc(qkv, bias, scale, out, batch, Hs, Ws, C, heads, ws, shift,
                                                                            soccdpt::as_stream(stream));
     if (N == 576 && !force_ref) return soccdpt::launch_window_attention_tc24(qkv, bias, scale, out, batch, Hs, Ws, C, heads, shift,

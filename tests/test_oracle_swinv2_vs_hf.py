@@ -54,6 +54,9 @@ def _to_hf_state(sd, depths):
 
 @pytest.mark.parametrize("name,img,ws,dim,depths,heads,pws", [
     ("swinv2_tiny_window16_256", 256, 16, 96, (2, 2, 6, 2), (3, 6, 12, 24), (0, 0, 0, 0)),
+    # dpt_swin2_base_384: windows 24 / 24 / 24 / 12 with PRETRAINED windows 12 / 12 / 12 / 6 (the log-spaced coordinate table
+    # of the continuous position bias is normalised by the pretrained window: the branch the tiny model never takes)
+    ("swinv2_base_window12to24_192to384_22kft1k", 384, 24, 128, (2, 2, 18, 2), (4, 8, 16, 32), (12, 12, 12, 6)),
 ])
 def test_shim_swinv2_matches_hf(name, img, ws, dim, depths, heads, pws):
     transformers = pytest.importorskip("transformers")
@@ -79,7 +82,7 @@ def test_shim_swinv2_matches_hf(name, img, ws, dim, depths, heads, pws):
     missing, unexpected = hf.load_state_dict(_to_hf_state(m.state_dict(), depths), strict=False)
     missing = [k for k in missing if "relative_" not in k and "key.bias" not in k]
     assert not missing and not unexpected, (missing, unexpected)
-    x = torch.randn(2, 3, img, img, generator=g)
+    x = torch.randn(2 if img <= 256 else 1, 3, img, img, generator=g)
     with torch.no_grad():
         a = m.forward_features(x)
         b = hf(pixel_values=x).last_hidden_state

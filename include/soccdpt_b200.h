@@ -102,6 +102,14 @@ typedef struct {
     float pc_scale[3];           /* applied to POINTS 0,1,2 of each frame (SOccDPT.py:351-353) */
     float pc_shift[3];
     float rot[27];               /* Ra, Rb, Rc row-major; points are multiplied p @ Ra @ Rb @ Rc */
+    int scalar_div_by_reciprocal; /* device convention of "tensor / host scalar" in X = (V - cx) * depth / fx (SOccDPT.py:311-313):
+                                     0 = true division (ATen's CPU kernel; the convention of the reference fixtures),
+                                     1 = multiply by the fp32 reciprocal of the scalar (ATen's CUDA kernel): the reference's own
+                                     eager path differs between devices by 1-2 ulps in X / Y (profiles/r2_device_convention.jsonl).
+                                     With 1 the caller also passes rotation matrices built from the CUDA cos / sin. */
+    float rcp_fx, rcp_fy;        /* used when scalar_div_by_reciprocal: fp32(1.0 / fx), fp32(1.0 / fy) with the reciprocal taken in
+                                     DOUBLE on the yaml's double (what ATen's CUDA div kernel does with a Python-float scalar;
+                                     it is NOT 1.0f / fp32(fx): for fx = 1250.6 the two differ by one ulp) */
 } soccdpt_geometry_t;
 
 #define SOCCDPT_OCC_REFERENCE_UNION 0 /* reference semantics: OR over the batch, written to every b */

@@ -7,7 +7,8 @@ across the boundary -- just raw pointers, sizes and a cudaStream_t.
 import ctypes
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libsoccdpt_b200.so")
+# SOCCDPT_LIB: an alternative build of the SAME library (A/B experiments with compile-time switches, tools/ only)
+_LIB_PATH = os.environ.get("SOCCDPT_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libsoccdpt_b200.so")
 _lib = None
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -30,6 +31,7 @@ class Geometry(ctypes.Structure):
         ("height", ctypes.c_int), ("width", ctypes.c_int), ("num_classes", ctypes.c_int),
         ("grid", ctypes.c_int * 3), ("occ_shape", ctypes.c_float * 3),
         ("pc_scale", ctypes.c_float * 3), ("pc_shift", ctypes.c_float * 3), ("rot", ctypes.c_float * 27),
+        ("scalar_div_by_reciprocal", ctypes.c_int), ("rcp_fx", ctypes.c_float), ("rcp_fy", ctypes.c_float),
     ]
 
 

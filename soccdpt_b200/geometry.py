@@ -20,9 +20,10 @@ def load_calib(path):
     return cam
 
 
-def rotation_matrices(correction_angle):
-    """Ra, Rb, Rc of rotate_points (SOccDPT.py:74-111): fp32 deg2rad / cos / sin on CPU tensors."""
-    a, b, c = torch.tensor(correction_angle).to(dtype=torch.float32)
+def rotation_matrices(correction_angle, device="cpu"):
+    """Ra, Rb, Rc of rotate_points (SOccDPT.py:74-111): fp32 deg2rad / cos / sin on tensors of ``device`` -- the reference
+    builds them where the model lives, and libm's and CUDA's cos / sin may differ in the last bit."""
+    a, b, c = torch.tensor(correction_angle).to(device=device, dtype=torch.float32)
     a, b, c = torch.deg2rad(a), torch.deg2rad(b), torch.deg2rad(c)
     Ra = torch.tensor([[1, 0, 0], [0, torch.cos(a), -torch.sin(a)], [0, torch.sin(a), torch.cos(a)]])
     Rb = torch.tensor([[torch.cos(b), 0, torch.sin(b)], [0, 1, 0], [-torch.sin(b), 0, torch.cos(b)]])
@@ -31,7 +32,11 @@ def rotation_matrices(correction_angle):
 
 
 def make_geometry(fx, fy, cx, cy, height, width, num_classes, grid_size, occupancy_shape, pc_scale, pc_shift,
-                  correction_angle):
+                  correction_angle, device_convention="cpu", device=None):
+    """``device_convention``: "cpu" (default) restates the reference's eager path on CPU tensors -- the convention of its
+    fixtures; "cuda" restates what the same ATen ops do on a CUDA device (tensor / host scalar as a multiply by the fp32
+    reciprocal, rotation matrices from the CUDA cos / sin)."""
+    assert device_convention in ("cpu", "cuda")
     g = _cabi.Geometry()
     # numpy.float64 scalars meet fp32 tensors in the reference -> the scalar is cast to fp32 (SURVEY 3.3 step 6)
     g.fx, g.fy, g.cx, g.cy = (float(np.float32(v)) for v in (fx, fy, cx, cy))
@@ -41,6 +46,10 @@ def make_geometry(fx, fy, cx, cy, height, width, num_classes, grid_size, occupan
         g.occ_shape[i] = float(np.float32(occupancy_shape[i]))
         g.pc_scale[i] = float(np.float32(pc_scale[i]))
         g.pc_shift[i] = float(np.float32(pc_shift[i]))
-    for i, v in enumerate(rotation_matrices(correction_angle)):
+    cuda = device_convention == "cuda"
+    for i, v in enumerate(rotation_matrices(correction_angle, device if cuda and device is not None else "cpu")):
         g.rot[i] = v
+    g.scalar_div_by_reciprocal = 1 if cuda else 0
+    # ATen's CUDA div kernel: inv_b = 1.0 / b in DOUBLE on the Python-float scalar, cast to the op-math type (fp32)
+    g.rcp_fx, g.rcp_fy = float(np.float32(1.0 / np.float64(fx))), float(np.float32(1.0 / np.float64(fy)))
     return g

@@ -53,7 +53,8 @@ class SOccDPT(BaseModel):
                  camera_intrinsics_yaml=DEFAULT_CALIB, point_compute_method="torch",
                  grid_size=(256, 256, 32), scale=(2.0, 2.0, 0.666), shift=(0.0, 0.0, 0.0),
                  pc_scale=(10000.0, 50000.0, 800.0), pc_shift=(55.0, -20.0, 15.0), correction_angle=(7.0, 0, 0),
-                 compute_occ=False, occupancy_mode="reference_union", occupancy_output="dense", **kwargs):
+                 compute_occ=False, occupancy_mode="reference_union", occupancy_output="dense", device_convention="cpu",
+                 **kwargs):
         super(SOccDPT, self).__init__(**kwargs)
         self.compute_occ = compute_occ
         self.grid_size, self.scale, self.shift = grid_size, scale, shift
@@ -72,6 +73,13 @@ class SOccDPT(BaseModel):
         # soccdpt_b200.occupancy.packed_to_points and SOCCDPT_OCC_PACKED in include/soccdpt_b200.h
         assert occupancy_output in ("dense", "packed")
         self.occupancy_output = occupancy_output
+        # The reference's eager post-processing is device dependent in the last bits of X / Y (ATen divides a tensor by a host
+        # scalar on the CPU and multiplies by the scalar's fp32 reciprocal on CUDA; cos / sin of the rotation come from libm or
+        # from CUDA): "cpu" (default) is bit-exact against the reference run on CPU tensors -- the convention of its fixtures
+        # --, "cuda" against the reference run on a CUDA device (tests/test_gpu_device_convention.py).
+        assert device_convention in ("cpu", "cuda")
+        self.device_convention = device_convention
+        self._geom_cache = {}
 
         self.camera_intrinsics_yaml = os.path.expanduser(camera_intrinsics_yaml)
         self.cam_settings = load_calib(self.camera_intrinsics_yaml)
@@ -90,9 +98,17 @@ class SOccDPT(BaseModel):
                       "self.get_semantic_occupancy(inv_depth, segmentation)"
 
     # ------------------------------------------------------------------ A8 / A9
-    def _geometry(self):
-        return make_geometry(self.fx, self.fy, self.cx, self.cy, self.height, self.width, self.num_classes,
-                             self.grid_size, self.occupancy_shape, self.pc_scale, self.pc_shift, self.correction_angle)
+    def _geometry(self, device=None):
+        key = (self.device_convention, _cabi.normalize_device(device).index if (device is not None and self.device_convention == "cuda") else -1,
+               tuple(self.grid_size), tuple(float(v) for v in self.occupancy_shape), tuple(self.pc_scale), tuple(self.pc_shift),
+               tuple(self.correction_angle), int(self.num_classes))
+        g = self._geom_cache.get(key)
+        if g is None:       # cached: the "cuda" convention evaluates cos / sin on the device (a host sync)
+            g = make_geometry(self.fx, self.fy, self.cx, self.cy, self.height, self.width, self.num_classes,
+                              self.grid_size, self.occupancy_shape, self.pc_scale, self.pc_shift, self.correction_angle,
+                              self.device_convention, device)
+            self._geom_cache = {key: g}
+        return g
 
     def _workspace(self, geom, B, mode, device):
         lib = _cabi.load()
@@ -117,7 +133,7 @@ class SOccDPT(BaseModel):
         assert C == self.num_classes and segmentation.shape[0] == B and tuple(segmentation.shape[2:]) == (h, w)
         dev = inv_depth.device
         H, Wd = int(self.height), int(self.width)
-        geom = self._geometry()
+        geom = self._geometry(dev)
         mode = _cabi.OCC_PER_FRAME if self.occupancy_mode == "per_frame" else _cabi.OCC_REFERENCE_UNION
         inv_up = torch.empty((B, H, Wd), dtype=torch.float32, device=dev)
         seg_up = torch.empty((B, C, H, Wd), dtype=torch.float32, device=dev)
@@ -155,7 +171,7 @@ class SOccDPT(BaseModel):
         B, H, Wd = inv_depth_up.shape
         assert (H, Wd) == (int(self.height), int(self.width)) and seg.shape == (B, self.num_classes, H, Wd)
         dev = inv_depth_up.device
-        geom = self._geometry()
+        geom = self._geometry(dev)
         mode = _cabi.OCC_PER_FRAME if self.occupancy_mode == "per_frame" else _cabi.OCC_REFERENCE_UNION
         points = torch.empty((B, H, Wd, 3), dtype=torch.float32, device=dev)
         grid, ws, need = None, None, 0

@@ -66,3 +66,11 @@ def test_reference_eager_path_on_cuda_vs_cpu_vs_kernel(name, tmp_path):
     assert record["max_ulp"] <= 2, record
     # a two-ulp move of a coordinate can only move a point across a cell boundary: a handful of cells at most
     assert grid_diff <= max(8, record["grid_cells_set"] // 1000), record
+    # 3) device_convention="cuda": the product kernel restates the CUDA eager path bit for bit as well
+    vox_c = SOccDPT(camera_intrinsics_yaml=write_calib_yaml(str(tmp_path / "c2.yaml"), calib), compute_occ=True,
+                    grid_size=geom.grid_size, scale=tuple(float(s) for s in z["scale"]), device_convention="cuda")
+    inv_c = inv.cuda().clone()
+    pts_c, grid_c = vox_c.voxelize(inv_c, seg.cuda())
+    assert np.array_equal(pts_c.cpu().numpy().view(np.uint32), pts_gpu.cpu().numpy().view(np.uint32))
+    assert np.array_equal(inv_c.cpu().numpy().view(np.uint32), inv_gpu.cpu().numpy().view(np.uint32))
+    assert torch.equal(grid_c, grid_gpu)

@@ -163,6 +163,7 @@ window_attention_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ 
     }
 }
 
+
 }  // namespace
 
 extern "C" int soccdpt_window_attention_fwd(const void *qkv, const float *bias, const float *scale, void *out,
@@ -177,9 +178,11 @@ extern "C" int soccdpt_window_attention_fwd(const void *qkv, const float *bias, 
     // (attention_tc.cu, attention_tc24.cu); the small last-stage windows (8x8, 12x12) use the CUDA-core kernel above.
     // SOCCDPT_ATTENTION_REF=1 (tests only) forces the CUDA-core kernel for an on-device cross-check.
     static const bool force_ref = getenv("SOCCDPT_ATTENTION_REF") != nullptr;
-    // 256-token windows: the warp-specialised persistent kernel (attention_ws.cu); SOCCDPT_ATTN_WS=0 keeps round 1's
-    // one-CTA-per-(window, head) kernel for A/B runs
-    static const bool use_ws = !(getenv("SOCCDPT_ATTN_WS") && getenv("SOCCDPT_ATTN_WS")[0] == '0');
+    // 256-token windows: round 1's one-CTA-per-(window, head) kernel (attention_tc.cu) stays the default; SOCCDPT_ATTN_WS=1
+    // selects the warp-specialised persistent kernel of round 2 (attention_ws.cu: cp.async producers two items ahead, two
+    // independent softmax streams, one MMA-issuing thread per stream), which measures the same 140-165 us per stage-0 launch:
+    // ablations (profiles/r2_progress.md) show neither MUFU, nor the bias LDS, nor the TMEM loads bound either kernel
+    static const bool use_ws = getenv("SOCCDPT_ATTN_WS") && getenv("SOCCDPT_ATTN_WS")[0] == '1';
     if (N == 256 && !force_ref && use_ws)
         return soccdpt::launch_window_attention_ws(qkv, bias, scale, out, batch, Hs, Ws, C, heads, shift, soccdpt::as_stream(stream));
     if (N == 256 && !force_ref) return soccdpt::launch_window_attention_tc(qkv, bias, scale, out, batch, Hs, Ws, C, heads, ws, shift,

@@ -30,6 +30,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace soccdpt {
 int validate_conv(const soccdpt_conv_t *c);
@@ -574,8 +575,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
                 } else if (ACT == SOCCDPT_ACT_GELU) {
+                    // packed fp32x2 one-MUFU erf GELU (tc_ptx.cuh): 8 issue slots per element instead of ~20 -- the GELU epilogue
+                    // is issue bound (profiles/r1_progress.md step 16)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    for (int j = 0; j < 32; j += 2) tc::un2(tc::gelu_erf_f32x2(tc::mk2(v[j], v[j + 1])), v[j], v[j + 1]);
                 }
                 if (MODE == 2) {
                     for (int q = 0; q < c.proj_n; ++q) {

@@ -55,6 +55,8 @@ struct Params {
     int nch;                            // HID / 128; 0 in one-GEMM mode
     int ns1, ns2;                       // ring depths (slots)
     int resident;                       // every weight tile of an M tile has its own slot: loaded once per CTA
+    int stream_a;                       // one-GEMM mode, large K1 / C > 256: activations AND weights stream through ring 2 by K chunk
+                                        // (slot = [128 x 64] activation chunk + [C x 64] weight chunk); N = C as 256 + (C - 256)
     int d2_bufs;
     uint32_t a_bytes;                   // bytes of one activation tile (= its TMA transaction count)
     uint32_t w2_slot;                   // bytes per ring-2 slot (>= C * 128, multiple of 1024)
@@ -275,8 +277,24 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                 }
             }
             soccdpt::pdl_wait();                // x / master are the previous kernels' outputs
+            if (!MLP && !RES && p.stream_a) {
+                // K-chunk pipeline: slot = activation chunk [128 x 64] + weight chunk [C x 64] (two boxes when C > 256)
+                const uint32_t stage_bytes = 16384u + p.w2_slot;
+                const uint32_t tx = 16384u + (uint32_t)C * 128u;
+                for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                    for (int kc = 0; kc < p.kc64; ++kc) {
+                        mbar_wait(&bars->w2_empty[s2], ph2 ^ 1u);
+                        uint8_t *dst = sW2 + s2 * stage_bytes;
+                        mbar_expect_tx(&bars->w2_full[s2], tx);
+                        tma_load_2d(dst, &mx64, &bars->w2_full[s2], kc * 64, tile * BM);
+                        tma_load_2d(dst + 16384, &mw2_64, &bars->w2_full[s2], kc * 64, 0);
+                        if (C > 256) tma_load_2d(dst + 16384 + 32768, &mw2_32, &bars->w2_full[s2], kc * 64, 256);
+                        if (++s2 == p.ns2) { s2 = 0; ph2 ^= 1u; }
+                    }
+                }
+            }
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < ((!MLP && !RES && p.stream_a) ? 0 : p.tiles); tile += gridDim.x, ++it) {
                 const int row0 = tile * BM;
                 mbar_wait(&bars->a_empty, (uint32_t)(it & 1) ^ 1u);
                 mbar_expect_tx(&bars->a_full, p.a_bytes);
@@ -429,6 +447,33 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                     if (more && !fc1_first) fc1(g + 1, itn, jn);
                     it = itn; j = jn;
                 }
+            } else if (!RES && p.stream_a) {
+                // K-chunk pipeline (see the producer); N = C as one MMA (C <= 256) or two (256 + (C - 256) columns)
+                const uint32_t stage_lo = (16384u + p.w2_slot) >> 4;
+                const int n1 = C > 256 ? 256 : C;
+                const uint32_t idesc_a = umma_idesc(n1), idesc_b = umma_idesc(C > 256 ? C - 256 : 16);
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int db2 = d2_two ? (it & 1) : 0;
+                    mbar_wait(&bars->d2_empty[db2], (uint32_t)((d2_two ? it >> 1 : it) & 1) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d2 = tmem + (uint32_t)(db2 * 256);
+                    uint32_t acc = 0u;
+                    for (int kc = 0; kc < p.kc64; ++kc) {
+                        mbar_wait(&bars->w2_full[s2], ph2);
+                        tc_fence_after();
+                        const uint32_t a_lo = w2_lo0 + (uint32_t)s2 * stage_lo;
+                        const uint32_t b_lo = a_lo + (16384u >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_ss_lo(d2, a_lo + 2 * k, b_lo + 2 * k, hi128, idesc_a, acc);
+                            if (C > 256) umma_ss_lo(d2 + 256u, a_lo + 2 * k, b_lo + (32768u >> 4) + 2 * k, hi128, idesc_b, acc);
+                            acc = 1u;
+                        }
+                        umma_commit(&bars->w2_empty[s2]);
+                        if (++s2 == p.ns2) { s2 = 0; ph2 ^= 1u; }
+                    }
+                    umma_commit(&bars->d2_full[db2]);
+                }
             } else {
                 const int kc64 = p.kc64, ktail = p.ktail;
                 for (int it = 0; it < my_tiles; ++it) {
@@ -506,7 +551,7 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                     mbar_arrive(&bars->h_full[g & 1]);
                 }
             }
-        } else if (MLP ? grp == 2 : grp < 2) {
+        } else if (MLP ? grp == 2 : (grp < 2 && (p.d2_bufs == 2 || grp == 0))) {
             // ============================== LayerNorm + residual: thread = token row ==============================
             LnWarp w;
             w.a = &a;
@@ -518,18 +563,20 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
             w.sub = warp & 3;
             w.nb = C >> 5;
             // two-GEMM mode: every tile of this CTA; one-GEMM mode: group `grp` takes the CTA's tiles it = grp, grp + 2, ...
-            w.tile0 = MLP ? (int)blockIdx.x : (int)blockIdx.x + grp * (int)gridDim.x;
-            w.tile_step = MLP ? (int)gridDim.x : 2 * (int)gridDim.x;
-            w.n_tiles = MLP ? my_tiles : (my_tiles - grp + 1) / 2;
+            // (one-GEMM mode with a single D2 buffer, C > 256: group 0 alone takes every tile)
+            const bool every = MLP || p.d2_bufs == 1;
+            w.tile0 = every ? (int)blockIdx.x : (int)blockIdx.x + grp * (int)gridDim.x;
+            w.tile_step = every ? (int)gridDim.x : 2 * (int)gridDim.x;
+            w.n_tiles = every ? my_tiles : (my_tiles - grp + 1) / 2;
             w.fk = 0; w.fb = 0; w.fslot = 0; w.cslot = 0;
 #pragma unroll
             for (int q = 0; q < LN_RING; ++q) w.fetch_next();
             for (int k = 0; k < w.n_tiles; ++k) {
-                const int it = MLP ? k : 2 * k + grp;
+                const int it = every ? k : 2 * k + grp;
                 if (it + 2 >= my_tiles) soccdpt::pdl_trigger();       // the CTA's tail: let the next kernel's CTAs in
                 const bool d2_two = p.d2_bufs == 2;
-                const int db2 = MLP ? (d2_two ? (it & 1) : 0) : grp;
-                const uint32_t d2_par = MLP ? (uint32_t)((d2_two ? it >> 1 : it) & 1) : (uint32_t)(k & 1);
+                const int db2 = every ? (d2_two ? (it & 1) : 0) : grp;
+                const uint32_t d2_par = every ? (uint32_t)((d2_two ? it >> 1 : it) & 1) : (uint32_t)(k & 1);
                 mbar_wait(&bars->d2_full[db2], d2_par);
                 tc_fence_after();
                 w.tile(k, t_lane + (MLP ? 256u + (uint32_t)(db2 * C) : (uint32_t)(db2 * 256)));
@@ -555,8 +602,13 @@ extern "C" int soccdpt_swin_block_tail_fwd(const soccdpt_block_tail_t *a, soccdp
     const bool mlp = a->w1 != nullptr;
     const int C = a->C, K1 = a->K1, HID = mlp ? a->HID : 0;
     SOCCDPT_REQUIRE(a->M >= 1 && a->M < (1ll << 31) - BM, "block_tail: bad row count %lld", a->M);
-    SOCCDPT_REQUIRE(C >= 32 && C <= 256 && C % 32 == 0, "block_tail: C must be a multiple of 32 in [32, 256] (got %d)", C);
-    SOCCDPT_REQUIRE(K1 >= 32 && K1 % 32 == 0 && K1 <= 512, "block_tail: K1 must be a multiple of 32, <= 512 (got %d)", K1);
+    // one-GEMM mode with wide rows (C > 256: stage 2 of swin2_tiny / swin2_base) or a long K (fc2: K1 = 4C): activations and
+    // weights stream through shared memory by K chunk instead of the activation tile being resident
+    const bool stream_a = !mlp && (C > 256 || K1 > 512);
+    SOCCDPT_REQUIRE(C >= 32 && C % 32 == 0 && C <= (stream_a ? 512 : 256),
+                    "block_tail: C must be a multiple of 32, <= 256 (two-GEMM mode) / <= 512 (one-GEMM mode) (got %d)", C);
+    SOCCDPT_REQUIRE(K1 >= 32 && K1 % 32 == 0 && K1 <= (stream_a ? 4096 : 512) && (!stream_a || K1 % 64 == 0),
+                    "block_tail: unsupported K1 = %d", K1);
     if (mlp) {
         SOCCDPT_REQUIRE(a->b1 != nullptr, "block_tail: b1 is NULL");
         SOCCDPT_REQUIRE(HID >= 2 * HC && HID % HC == 0 && HID <= 4096, "block_tail: HID must be a multiple of 128 (got %d)", HID);
@@ -574,8 +626,9 @@ extern "C" int soccdpt_swin_block_tail_fwd(const soccdpt_block_tail_t *a, soccdp
     const int kc1 = p.kc64 + p.ktail;
     p.a_bytes = (uint32_t)(p.kc64 * 16384 + p.ktail * 8192);
     p.w2_slot = (uint32_t)((C * 128 + 1023) / 1024 * 1024);
-    // TMEM: D1 = columns 0..255 (two-GEMM mode), D2 from column 256
-    p.d2_bufs = mlp ? (2 * C <= 256 ? 2 : 1) : 2;
+    p.stream_a = stream_a ? 1 : 0;
+    // TMEM: D1 = columns 0..255 (two-GEMM mode), D2 from column 256; one-GEMM mode: D2 buffers at columns 0 / 256
+    p.d2_bufs = mlp ? (2 * C <= 256 ? 2 : 1) : (C <= 256 ? 2 : 1);
     // misc block: b1 | b2 | gamma | beta | barriers
     uint32_t m = 0;
     m += (uint32_t)((HID * 4 + 15) / 16 * 16);
@@ -585,18 +638,28 @@ extern "C" int soccdpt_swin_block_tail_fwd(const soccdpt_block_tail_t *a, soccdp
     m = (m + 15) / 16 * 16;
     p.off_bar = m; m += (uint32_t)sizeof(Bars);
     const uint32_t misc_bytes = (m + 1023) / 1024 * 1024;
-    const uint32_t ln_bytes = (uint32_t)(mlp ? 4 : 8) * LN_WARP_BYTES;   // LayerNorm warps: 4 (two-GEMM mode) or 8
-    const uint32_t a_slot = (p.a_bytes + 1023) / 1024 * 1024;
+    // LayerNorm warps: 4 (two-GEMM mode; one-GEMM mode with a single D2 buffer) or 8
+    const uint32_t ln_bytes = (uint32_t)((mlp || p.d2_bufs == 1) ? 4 : 8) * LN_WARP_BYTES;
+    const uint32_t a_slot = stream_a ? 0u : (p.a_bytes + 1023) / 1024 * 1024;
     const long long budget = SMEM_MAX - 1024 /*alignment slack*/ - (long long)misc_bytes - ln_bytes - a_slot;
     const int w1_tiles = mlp ? p.nch * kc1 : 0;
     const int w2_tiles = mlp ? p.nch * 2 : kc1;
     p.w1_chunk = (uint32_t)(p.kc64 * 16384 + p.ktail * 8192);
-    uint32_t w1_bytes = 0;
-    if ((long long)p.nch * p.w1_chunk + (long long)w2_tiles * p.w2_slot <= budget && w1_tiles <= MAX_SLOTS && w2_tiles <= MAX_SLOTS) {
+    uint32_t w1_bytes = 0, w2_bytes = 0;
+    if (stream_a) {
+        const long long stage = 16384 + (long long)p.w2_slot;
+        p.resident = 0;
+        p.ns1 = 0;
+        p.ns2 = (int)(budget / stage);
+        if (p.ns2 > MAX_SLOTS) p.ns2 = MAX_SLOTS;
+        SOCCDPT_REQUIRE(p.ns2 >= 2, "block_tail: shapes do not fit shared memory (C=%d K1=%d)", C, K1);
+        w2_bytes = (uint32_t)(p.ns2 * stage);
+    } else if ((long long)p.nch * p.w1_chunk + (long long)w2_tiles * p.w2_slot <= budget && w1_tiles <= MAX_SLOTS && w2_tiles <= MAX_SLOTS) {
         p.resident = 1;
         p.ns1 = w1_tiles;
         p.ns2 = w2_tiles;
         w1_bytes = (uint32_t)p.nch * p.w1_chunk;
+        w2_bytes = (uint32_t)p.ns2 * p.w2_slot;
     } else {
         p.resident = 0;
         // ring 2 first (one chunk = two tiles in two-GEMM mode; two chunks when they fit), the rest goes to ring 1
@@ -614,10 +677,11 @@ extern "C" int soccdpt_swin_block_tail_fwd(const soccdpt_block_tail_t *a, soccdp
             p.ns1 = 0;
         }
         w1_bytes = (uint32_t)p.ns1 * W1_SLOT;
+        w2_bytes = (uint32_t)p.ns2 * p.w2_slot;
     }
     p.off_w1 = a_slot;
     p.off_w2 = p.off_w1 + w1_bytes;
-    p.off_ln = p.off_w2 + (uint32_t)p.ns2 * p.w2_slot;
+    p.off_ln = p.off_w2 + w2_bytes;
     p.off_misc = p.off_ln + ln_bytes;
     const size_t smem_bytes = (size_t)p.off_misc + misc_bytes + 1024;
     SOCCDPT_REQUIRE(smem_bytes <= (size_t)SMEM_MAX, "block_tail: %zu bytes of shared memory needed (C=%d K1=%d HID=%d)", smem_bytes, C, K1, HID);
@@ -639,6 +703,13 @@ extern "C" int soccdpt_swin_block_tail_fwd(const soccdpt_block_tail_t *a, soccdp
         }
         r = tc::encode_2d_bf16(&mw2_64, a->w2, (uint64_t)C, (uint64_t)HID, 64, (uint32_t)C, true);
         SOCCDPT_REQUIRE(r == CUDA_SUCCESS, "block_tail: cuTensorMapEncodeTiled(w2) failed with %d", (int)r);
+    } else if (stream_a) {
+        r = tc::encode_2d_bf16(&mw2_64, a->w2, (uint64_t)C, (uint64_t)K1, 64, (uint32_t)(C > 256 ? 256 : C), true);
+        SOCCDPT_REQUIRE(r == CUDA_SUCCESS, "block_tail: cuTensorMapEncodeTiled(w2) failed with %d", (int)r);
+        if (C > 256) {      // second N part of a weight chunk: rows [256, C)
+            r = tc::encode_2d_bf16(&mw2_32, a->w2, (uint64_t)C, (uint64_t)K1, 64, (uint32_t)(C - 256), true);
+            SOCCDPT_REQUIRE(r == CUDA_SUCCESS, "block_tail: cuTensorMapEncodeTiled(w2 part 2) failed with %d", (int)r);
+        }
     } else {
         r = tc::encode_2d_bf16(&mw2_64, a->w2, (uint64_t)C, (uint64_t)K1, 64, (uint32_t)C, true);
         SOCCDPT_REQUIRE(r == CUDA_SUCCESS, "block_tail: cuTensorMapEncodeTiled(w2) failed with %d", (int)r);

@@ -210,7 +210,7 @@ __device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
 // p = degree-5 fit of log2(erfcx(u / sqrt 2) / 2), weighted by its effect on the result (max |error| of gelu 1.5e-6 over
 // [-12, 12] in fp32: three orders below the bf16 rounding of the stored value), written in nu = -|t| (sign bit OR-ed in on
 // the integer pipe) so that the last step is one FMA: nu * e + relu(t).  p -> -inf for large |t|: the tails are relu(t) exactly.
-__device__ __forceinline__ uint32_t gelu_erf_bf16x2(f32x2 t) {
+__device__ __forceinline__ f32x2 gelu_erf_f32x2(f32x2 t) {
     float t0, t1;
     un2(t, t0, t1);
     const f32x2 nu = t | 0x8000000080000000ull;
@@ -224,9 +224,11 @@ __device__ __forceinline__ uint32_t gelu_erf_bf16x2(f32x2 t) {
     un2(arg, a0, a1);
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
-    const f32x2 o = ffma2(nu, mk2(e0, e1), mk2(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f)));
+    return ffma2(nu, mk2(e0, e1), mk2(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f)));
+}
+__device__ __forceinline__ uint32_t gelu_erf_bf16x2(f32x2 t) {
     float o0, o1;
-    un2(o, o0, o1);
+    un2(gelu_erf_f32x2(t), o0, o1);
     return pack_bf16x2(o0, o1);
 }
 // scalar twin of the above (host-checkable form; used by tests through soccdpt_gelu_selftest)

@@ -237,20 +237,24 @@ class NetworkEngine:
         plan["ops"].append(_Launch("conv", fn, ctypes.byref(c)))
 
     def _fuse_tail(self, C, which):
-        """Fused Swin block tails (csrc/swin_block_tail.cu) cover C <= 256; SOCCDPT_FUSED_TAIL = comma list of {mlp, proj}
-        or 0 switches them per branch for A/B runs (default: both).  The CUDA-core cross-check engine keeps the un-fused ops."""
-        if self.conv_impl != "tcgen05" or C > 256 or C % 32:
+        """Fused Swin block tails (csrc/swin_block_tail.cu): "mlp" (fc1 -> GELU -> fc2 -> norm2 -> residual, C <= 256), "proj"
+        (proj -> norm1 -> residual, C <= 512) and "fc2" (fc2 -> norm2 -> residual behind the un-fused fc1 GEMM, for the stages
+        whose rows are too wide for the two-GEMM form: 256 < C <= 512).  SOCCDPT_FUSED_TAIL = comma list or 0 switches them
+        per kind for A/B runs (default: all).  The CUDA-core cross-check engine keeps the un-fused ops."""
+        if self.conv_impl != "tcgen05" or C % 32:
             return False
-        sel = os.environ.get("SOCCDPT_FUSED_TAIL", "mlp,proj")
+        if C > (256 if which == "mlp" else 512) or (which == "fc2" and C <= 256):
+            return False
+        sel = os.environ.get("SOCCDPT_FUSED_TAIL", "mlp,proj,fc2")
         return which in sel.split(",")
 
-    def _block_tail(self, plan, x, w1, b1, w2, b2, norm, master, y, M, C, HID):
+    def _block_tail(self, plan, x, w1, b1, w2, b2, norm, master, y, M, C, HID, K1=None):
         a = _cabi.BlockTail()
         a.x, a.w2, a.b2 = x.data_ptr(), w2.data_ptr(), b2.data_ptr()
         a.w1 = w1.data_ptr() if w1 is not None else None
         a.b1 = b1.data_ptr() if b1 is not None else None
         a.gamma, a.beta, a.master, a.y = norm[0].data_ptr(), norm[1].data_ptr(), master.data_ptr(), y.data_ptr()
-        a.M, a.K1, a.HID, a.C, a.eps = M, C, HID, C, 1e-5
+        a.M, a.K1, a.HID, a.C, a.eps = M, (K1 if K1 is not None else C), HID, C, 1e-5
         plan["keep"].append(a)
         plan["ops"].append(_Launch("block_tail_mlp" if w1 is not None else "block_tail_proj", self.lib.soccdpt_swin_block_tail_fwd,
                                    ctypes.byref(a)))
@@ -287,6 +291,10 @@ class NetworkEngine:
                 if self._fuse_tail(C, "mlp"):
                     # fc1 -> GELU -> fc2 -> norm2 -> residual in one kernel; y aliases x (a tile's rows are read before they are written)
                     self._block_tail(plan, cur, b["w1"], b["b1"], b["w2"], b["b2"], b["n2"], master, cur, M, C, 4 * C)
+                elif self._fuse_tail(C, "fc2"):
+                    # wide rows (256 < C <= 512): fc1 + GELU stays a plain GEMM, fc2 -> norm2 -> residual is one kernel
+                    self._conv(plan, cur, b["w1"], 1, 1, M, C, 4 * C, 1, bias=b["b1"], act=_cabi.ACT_GELU, y=hid)
+                    self._block_tail(plan, hid, None, None, b["w2"], b["b2"], b["n2"], master, cur, M, C, 0, K1=4 * C)
                 else:
                     self._conv(plan, cur, b["w1"], 1, 1, M, C, 4 * C, 1, bias=b["b1"], act=_cabi.ACT_GELU, y=hid)
                     self._conv(plan, hid, b["w2"], 1, 1, M, 4 * C, C, 1, bias=b["b2"], y=tmp)

@@ -11,9 +11,9 @@ import cuda_ops as K
 pytestmark = pytest.mark.gpu
 
 
-def _case(M, C, HID, seed, mlp=True):
+def _case(M, C, HID, seed, mlp=True, K1=None):
     g = torch.Generator().manual_seed(seed)
-    K1 = C
+    K1 = K1 or C
     x = (torch.randn(M, K1, generator=g)).bfloat16()
     w1 = (torch.randn(HID, K1, generator=g) / K1 ** 0.5).bfloat16() if mlp else None
     b1 = torch.randn(HID, generator=g) * 0.3 if mlp else None
@@ -60,6 +60,19 @@ def test_proj_branch_matches_torch(M, C):
     ref = _ref(*case)
     err = (m - ref).abs()
     assert err.max().item() <= 2e-3 and err.mean().item() <= 2e-4, (err.max().item(), err.mean().item())
+    assert torch.equal(y, m.bfloat16())
+
+
+@pytest.mark.parametrize("M,C,K1", [(1000, 384, 384), (128 * 128, 384, 384), (640, 512, 512), (128 * 3 + 9, 384, 1536),
+                                    (128 * 128, 384, 1536), (128 * 37, 256, 1024), (128 * 150, 512, 2048)])
+def test_wide_rows_and_long_k_stream_through_shared_memory(M, C, K1):
+    """one-GEMM mode with C > 256 (N = 256 + (C - 256) columns, single TMEM buffer) and / or K1 > 512 (fc2 -> norm2 -> residual):
+    activations and weights stream by K chunk."""
+    case = _case(M, C, 0, seed=M + C + K1, mlp=False, K1=K1)
+    m, y = _run(case)
+    ref = _ref(*case)
+    err = (m - ref).abs()
+    assert err.max().item() <= 3e-3 and err.mean().item() <= 3e-4, (err.max().item(), err.mean().item())
     assert torch.equal(y, m.bfloat16())
 
 

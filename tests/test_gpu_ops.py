@@ -79,7 +79,7 @@ def test_seg_finish(act):
 
 @pytest.mark.parametrize("res,ws,target_ws,heads,shift_block,hi_scale", [
     (32, 16, 16, 3, True, False), (16, 16, 16, 12, True, False), (8, 8, 16, 24, False, False), (24, 12, 12, 4, True, False),
-    (32, 8, 8, 2, False, False),
+    (32, 8, 8, 2, False, False), (32, 8, 8, 3, True, False), (16, 8, 8, 24, True, True),
     # 24x24 windows of swin2_base_384 (attention_tc24.cu): shifted 2x2 windows, un-shifted, one window == the whole stage
     (48, 24, 24, 4, True, False), (48, 24, 24, 2, False, False), (24, 24, 24, 3, True, False),
     # logit scales 40..100 (clamp): the exact row-max pre-pass of both tensor-core kernels

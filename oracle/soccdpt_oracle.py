@@ -273,6 +273,13 @@ class OracleV3:
         return torch.sigmoid(g) if self.sigmoid else 0.5 * torch.tanh(g) + 0.5
 
     @torch.no_grad()
+    def seg_logits(self, path_1, h="seg_head."):
+        """the head's output before Interpolate and the activation (SOccDPT.py:660-670): (B, C, h/2, w/2)."""
+        sd = self.sd
+        g = _bn(sd, h + "1", _conv(sd, h + "0", path_1, 1))
+        return _conv(sd, h + "4", F.relu(g), 0)
+
+    @torch.no_grad()
     def heads(self, path_1):
         return self.depth_head(path_1), self.seg_head(path_1)
 

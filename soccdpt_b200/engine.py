@@ -490,6 +490,7 @@ class NetworkEngine:
             logits = buf(B, PH, PW, P, dtype=torch.float32)
             self._conv(plan, path, sh["w0"], B, PH, PW, F, F, 3, bias=sh["b0"], act=_cabi.ACT_RELU,
                        proj=(sh["pw"], sh["pb"], logits, False))
+            plan["seg_logits"] = logits      # (B, PH, PW, P) fp32: the head's output before the x2 upsample and the activation
             seg = buf(B, P, 2 * PH, 2 * PW, dtype=torch.float32)
             ops.append(_Launch("seg_finish", lib.soccdpt_seg_finish_fwd, logits.data_ptr(), seg.data_ptr(), B, PH, PW, P, Wt["seg_act"]))
             plan["seg"] = seg

@@ -190,6 +190,133 @@ patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w, con
     }
 }
 
+// ------------------------------------------------------------------ patch embed on the tensor cores
+// The CUDA-core kernel above is bound by FMA issue (48 x E FMAs per token: 130 us for 64 frames against a 31 us HBM floor).
+// Here a warp owns 16 horizontally adjacent tokens: A (16 tokens x 48 taps) comes straight from the fp32 image in the
+// m16n8k16 fragment layout (k-step = input channel, k = ky*4 + kx: each lane reads float2 pieces, a warp-wide load covers two
+// full 128-byte row segments), split into bf16 hi + lo; the weights are split the same way at kernel start and kept in shared
+// memory as ready-made B fragments.  hi*hi + lo*hi + hi*lo with fp32 accumulation reproduces the fp32 convolution to ~2^-17
+// (the dropped lo*lo term), i.e. far below the bf16 rounding of the output.  LayerNorm runs on the accumulator fragments
+// (row sums across the four lanes of a quad).
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_bf16x2(float x, float y, unsigned &hi, unsigned &lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const unsigned *>(&h);
+    lo = *reinterpret_cast<const unsigned *>(&l);
+}
+
+template <int NT>      // 8-channel column tiles: E = 8 * NT (12 for swin2_tiny, 16 for swin2_base)
+__global__ void __launch_bounds__(256, 2)
+patch_embed_mma_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
+                       const float *__restrict__ g, const float *__restrict__ be, bf16 *__restrict__ out,
+                       float *__restrict__ out_f32, int B, int H, int W) {
+    constexpr int E = 8 * NT;
+    // B fragments [split][channel][column tile][lane] -> {b0, b1}; then bias / gamma / beta
+    __shared__ uint2 wfrag[2 * 3 * NT * 32];
+    __shared__ float cst[3 * E];
+    for (int i = threadIdx.x; i < 3 * NT * 32; i += 256) {
+        const int lane = i & 31, j = (i >> 5) % NT, c = i / (32 * NT);
+        const int gq = lane >> 2, t = lane & 3;
+        const float *wr = w + (size_t)(8 * j + gq) * 48 + c * 16 + 2 * t;       // B[k][n] = w[n][k]
+        uint2 hi, lo;
+        split_bf16x2(wr[0], wr[1], hi.x, lo.x);
+        split_bf16x2(wr[8], wr[9], hi.y, lo.y);
+        wfrag[i] = hi;
+        wfrag[3 * NT * 32 + i] = lo;
+    }
+    for (int i = threadIdx.x; i < E; i += 256) { cst[i] = b[i]; cst[E + i] = g[i]; cst[2 * E + i] = be[i]; }
+    soccdpt::pdl_wait();        // the weights above are constants; the frames below may come from the previous kernel
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gq = lane >> 2, t = lane & 3;
+    const int ph = H / 4, pw = W / 4, tpr = pw / 16;                     // 16-token tiles per token row
+    const unsigned tiles = (unsigned)B * (unsigned)ph * (unsigned)tpr;   // < 2^31 (checked on the host)
+    const size_t plane = (size_t)H * W;
+    // this lane's pieces of a tile: rows (tokens) gq and gq + 8, taps (ky = t>>1 [+2], kx = (t&1)*2 .. +1)
+    const size_t lane_off = (size_t)(t >> 1) * W + (size_t)gq * 4 + (size_t)(t & 1) * 2;
+    auto tile_base = [&](unsigned ti) {
+        const unsigned tx = ti % (unsigned)tpr, rowi = ti / (unsigned)tpr;
+        const unsigned ty = rowi % (unsigned)ph, n = rowi / (unsigned)ph;
+        return x + ((size_t)n * 3 * H + (size_t)ty * 4) * W + (size_t)tx * 64 + lane_off;
+    };
+    auto load_tile = [&](const float *p, float2 (&v)[3][4]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float *pc = p + c * plane;
+            v[c][0] = __ldcs(reinterpret_cast<const float2 *>(pc));                       // token gq,     ky
+            v[c][1] = __ldcs(reinterpret_cast<const float2 *>(pc + 32));                  // token gq + 8, ky
+            v[c][2] = __ldcs(reinterpret_cast<const float2 *>(pc + 2 * (size_t)W));       // token gq,     ky + 2
+            v[c][3] = __ldcs(reinterpret_cast<const float2 *>(pc + 2 * (size_t)W + 32));  // token gq + 8, ky + 2
+        }
+    };
+    unsigned ti = blockIdx.x * 8u + warp;
+    float2 nxt[3][4];
+    if (ti < tiles) load_tile(tile_base(ti), nxt);
+    for (; ti < tiles; ti += gridDim.x * 8u) {
+        unsigned ah[3][4], al[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) split_bf16x2(nxt[c][r].x, nxt[c][r].y, ah[c][r], al[c][r]);
+        const unsigned tn = ti + gridDim.x * 8u;
+        if (tn < tiles) load_tile(tile_base(tn), nxt);        // in flight under the MMAs and the LayerNorm of this tile
+        float acc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const float b0 = cst[8 * j + 2 * t], b1 = cst[8 * j + 2 * t + 1];
+            acc[j][0] = b0; acc[j][1] = b1; acc[j][2] = b0; acc[j][3] = b1;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const uint2 wh = wfrag[(c * NT + j) * 32 + lane], wl = wfrag[((3 + c) * NT + j) * 32 + lane];
+                mma_bf16_16816(acc[j], ah[c], wl.x, wl.y);      // small terms first
+                mma_bf16_16816(acc[j], al[c], wh.x, wh.y);
+                mma_bf16_16816(acc[j], ah[c], wh.x, wh.y);
+            }
+        // LayerNorm (eps 1e-5) of rows gq (acc[.][0..1]) and gq + 8 (acc[.][2..3]); a row lives in the 4 lanes of a quad
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) { s0 += acc[j][0] + acc[j][1]; s1 += acc[j][2] + acc[j][3]; }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        const float m0 = s0 / (float)E, m1 = s1 / (float)E;
+        float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            acc[j][0] -= m0; acc[j][1] -= m0; acc[j][2] -= m1; acc[j][3] -= m1;
+            q0 += acc[j][0] * acc[j][0] + acc[j][1] * acc[j][1];
+            q1 += acc[j][2] * acc[j][2] + acc[j][3] * acc[j][3];
+        }
+        q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+        q0 += __shfl_xor_sync(0xffffffffu, q0, 2); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+        const float r0 = rsqrtf(q0 / (float)E + 1e-5f), r1 = rsqrtf(q1 / (float)E + 1e-5f);
+        const size_t tok0 = (size_t)ti * 16;          // tiles are numbered in token order
+        bf16 *o16a = out + (tok0 + gq) * E + 2 * t, *o16b = o16a + 8 * E;
+        float *o32a = out_f32 ? out_f32 + (tok0 + gq) * E + 2 * t : nullptr, *o32b = out_f32 ? o32a + 8 * E : nullptr;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const float ga = cst[E + 8 * j + 2 * t], gb = cst[E + 8 * j + 2 * t + 1];
+            const float ba = cst[2 * E + 8 * j + 2 * t], bb = cst[2 * E + 8 * j + 2 * t + 1];
+            const float v0 = acc[j][0] * r0 * ga + ba, v1 = acc[j][1] * r0 * gb + bb;
+            const float v2 = acc[j][2] * r1 * ga + ba, v3 = acc[j][3] * r1 * gb + bb;
+            *reinterpret_cast<__nv_bfloat162 *>(o16a + 8 * j) = __floats2bfloat162_rn(v0, v1);
+            *reinterpret_cast<__nv_bfloat162 *>(o16b + 8 * j) = __floats2bfloat162_rn(v2, v3);
+            if (o32a) {
+                *reinterpret_cast<float2 *>(o32a + 8 * j) = make_float2(v0, v1);
+                *reinterpret_cast<float2 *>(o32b + 8 * j) = make_float2(v2, v3);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ y = res + LayerNorm(t)
 // A group of G lanes (16 or 32) owns one row; every lane keeps its ITERS x 8 elements in registers, so the
 // row is read once (16-byte bf16 loads).  C = 96 uses half-warps (12 of 16 lanes busy instead of 12 of 32).
@@ -513,6 +640,21 @@ int soccdpt_patch_embed_fwd(const float *x, const float *w, const float *b, cons
     SOCCDPT_REQUIRE(batch >= 1 && H % 4 == 0 && W % 16 == 0 && E >= 32 && E <= 128, "patch_embed: need W %% 16 == 0 and 32 <= E <= 128");
     const long long groups = (long long)batch * (H / 4) * (W / 16);
     SOCCDPT_REQUIRE(groups < (1ll << 31), "patch_embed: batch too large for one call");
+    static const bool fp32_path = getenv("SOCCDPT_PATCH_EMBED_FP32") && getenv("SOCCDPT_PATCH_EMBED_FP32")[0] == '1';
+    if ((E == 96 || E == 128) && W % 64 == 0 && !fp32_path) {
+        const long long tiles = (long long)batch * (H / 4) * (W / 64);
+        long long nb = (tiles + 7) / 8;
+        const long long capm = (long long)soccdpt::sm_count() * 2 * 4;
+        if (nb > capm) nb = capm;
+#define SOCC_PEM(NT)                                                                                                        \
+    SOCCDPT_CUDA(soccdpt::launch_pdl(soccdpt::PDL_ELEMENTWISE, patch_embed_mma_kernel<NT>, dim3((unsigned)nb), dim3(256), 0, \
+                                     soccdpt::as_stream(stream), x, w, b, ln_w, ln_b, static_cast<bf16 *>(tokens), tokens_f32, \
+                                     batch, H, W))
+        if (E == 96) SOCC_PEM(12);
+        else SOCC_PEM(16);
+#undef SOCC_PEM
+        return soccdpt::check_launch("patch_embed_mma_kernel");
+    }
     long long blocks = (groups + 7) / 8;
     const long long cap = (long long)soccdpt::sm_count() * 8;
     if (blocks > cap) blocks = cap;

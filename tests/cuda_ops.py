@@ -54,7 +54,7 @@ def layernorm(t, res, g, b, eps=1e-5):
     return y
 
 
-def patch_embed(x, w, b, g, be):
+def patch_embed(x, w, b, g, be, want_f32=False):
     lib = _cabi.load()
     B, _, H, W = x.shape
     E = w.shape[0]
@@ -63,7 +63,7 @@ def patch_embed(x, w, b, g, be):
     _cabi.check(lib.soccdpt_patch_embed_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), g.data_ptr(), be.data_ptr(),
                                             out.data_ptr(), out32.data_ptr(), B, H, W, E, _s()), "patch_embed")
     assert torch.equal(out32.bfloat16(), out)
-    return out
+    return (out, out32) if want_f32 else out
 
 
 def layernorm_master(t, master, accumulate, g, b, eps=1e-5):

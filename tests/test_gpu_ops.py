@@ -42,15 +42,20 @@ def test_layernorm_fp32_master_stream(rows, C, acc):
     assert torch.equal(y, md.bfloat16())
 
 
-@pytest.mark.parametrize("B,S,E", [(2, 64, 96), (1, 32, 128)])
+# W % 64 == 0 with E in (96, 128): the tensor-core kernel (bf16 hi/lo split of image and weights, fp32 accumulate);
+# other shapes: the fp32 CUDA-core kernel.  Both must reproduce the fp32 convolution + LayerNorm to fp32-level accuracy.
+@pytest.mark.parametrize("B,S,E", [(2, 64, 96), (1, 32, 128), (3, 128, 96), (2, 192, 128), (1, 256, 96)])
 def test_patch_embed(B, S, E):
     g = _g(2)
     x = torch.randn(B, 3, S, S, generator=g)
     w, b = torch.randn(E, 3, 4, 4, generator=g) * 0.2, torch.randn(E, generator=g) * 0.1
     lw, lb = torch.rand(E, generator=g) + 0.5, torch.rand(E, generator=g) - 0.5
-    y = K.patch_embed(x.cuda(), w.reshape(E, -1).contiguous().cuda(), b.cuda(), lw.cuda(), lb.cuda())
-    ref = F.layer_norm(F.conv2d(x, w, b, stride=4).flatten(2).transpose(1, 2), (E,), lw, lb, 1e-5)
-    assert torch.allclose(y.float().cpu(), ref, **BF)
+    y, y32 = K.patch_embed(x.cuda(), w.reshape(E, -1).contiguous().cuda(), b.cuda(), lw.cuda(), lb.cuda(), want_f32=True)
+    ref = F.layer_norm(F.conv2d(x.double(), w.double(), b.double(), stride=4).flatten(2).transpose(1, 2), (E,),
+                       lw.double(), lb.double(), 1e-5)
+    assert torch.allclose(y.float().cpu(), ref.float(), **BF)
+    err = (y32.cpu().double() - ref).abs().max().item()
+    assert err <= 2e-4, err          # fp32 master stream: the dropped lo*lo term is ~2^-17 relative per product
 
 
 def test_patch_merge_gather():

@@ -18,6 +18,10 @@ int launch_window_attention_tc(const void *qkv, const float *biasT, const float 
                                int C, int heads, int ws, int shift, cudaStream_t st);
 int launch_window_attention_ws(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
                                int C, int heads, int shift, cudaStream_t st);
+int launch_window_attention_small(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
+                                  int C, int heads, int ws, cudaStream_t st);
+int launch_window_attention_mma16(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
+                                  int C, int heads, int shift, cudaStream_t st);
 int launch_window_attention_tc24(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
                                  int C, int heads, int shift, cudaStream_t st);
 }
@@ -183,12 +187,20 @@ extern "C" int soccdpt_window_attention_fwd(const void *qkv, const float *bias, 
     // independent softmax streams, one MMA-issuing thread per stream), which measures the same 140-165 us per stage-0 launch:
     // ablations (profiles/r2_progress.md) show neither MUFU, nor the bias LDS, nor the TMEM loads bound either kernel
     static const bool use_ws = getenv("SOCCDPT_ATTN_WS") && getenv("SOCCDPT_ATTN_WS")[0] == '1';
+    // SOCCDPT_ATTN_MMA=1: the warp-level MMA kernel (attention_mma.cu) also for the 256-token windows -- 145 / 152 us per stage-0
+    // launch against 141 / 156 us (un-shifted / shifted) for the tcgen05 kernel: a tie, like every other structure tried
+    static const bool use_mma = getenv("SOCCDPT_ATTN_MMA") && getenv("SOCCDPT_ATTN_MMA")[0] == '1';
+    if (N == 256 && !force_ref && use_mma)
+        return soccdpt::launch_window_attention_mma16(qkv, bias, scale, out, batch, Hs, Ws, C, heads, shift, soccdpt::as_stream(stream));
     if (N == 256 && !force_ref && use_ws)
         return soccdpt::launch_window_attention_ws(qkv, bias, scale, out, batch, Hs, Ws, C, heads, shift, soccdpt::as_stream(stream));
     if (N == 256 && !force_ref) return soccdpt::launch_window_attention_tc(qkv, bias, scale, out, batch, Hs, Ws, C, heads, ws, shift,
                                                                            soccdpt::as_stream(stream));
     if (N == 576 && !force_ref) return soccdpt::launch_window_attention_tc24(qkv, bias, scale, out, batch, Hs, Ws, C, heads, shift,
                                                                              soccdpt::as_stream(stream));
+    // un-shifted 8x8 / 12x12 windows (the last stage): warp-level tensor-core kernel (attention_small.cu)
+    if ((ws == 8 || ws == 12) && shift == 0 && !force_ref)
+        return soccdpt::launch_window_attention_small(qkv, bias, scale, out, batch, Hs, Ws, C, heads, ws, soccdpt::as_stream(stream));
     SOCCDPT_REQUIRE(N % CH == 0 && N <= 1024, "window_attention: window tokens must be a multiple of %d and <= 1024 (got %d)", CH, N);
     const int threads = N > 256 ? 192 : (N + 31) / 32 * 32;   // larger windows: several query rows per thread
     const size_t smem = (size_t)N * D * 2 * sizeof(float) + (size_t)N * sizeof(int);

@@ -85,6 +85,8 @@ def test_seg_finish(act):
 @pytest.mark.parametrize("res,ws,target_ws,heads,shift_block,hi_scale", [
     (32, 16, 16, 3, True, False), (16, 16, 16, 12, True, False), (8, 8, 16, 24, False, False), (24, 12, 12, 4, True, False),
     (32, 8, 8, 2, False, False), (32, 8, 8, 3, True, False), (16, 8, 8, 24, True, True),
+    # un-shifted 8x8 / 12x12 windows: the warp-MMA kernel (attention_small.cu); last stage of tiny (8x8 map) and base_384 (12x12 map)
+    (12, 12, 24, 4, False, False), (24, 12, 12, 3, False, False), (8, 8, 16, 24, False, True), (12, 12, 24, 32, False, True),
     # 24x24 windows of swin2_base_384 (attention_tc24.cu): shifted 2x2 windows, un-shifted, one window == the whole stage
     (48, 24, 24, 4, True, False), (48, 24, 24, 2, False, False), (24, 24, 24, 3, True, False),
     # logit scales 40..100 (clamp): the exact row-max pre-pass of both tensor-core kernels

@@ -281,6 +281,21 @@ int soccdpt_groupnorm_fwd(const void *x, const float *gamma, const float *beta, 
 /* MaxPool2dSame(3, stride 2), NHWC bf16 [batch,H,W,C] -> [batch, ceil(H/2), ceil(W/2), C] (padding value -inf) */
 int soccdpt_maxpool3s2_fwd(const void *x, void *y, int batch, int H, int W, int C, soccdpt_stream_t stream);
 
+/* ---- fp32-storage PARITY mode of the hybrid encoder's ResNetV2 trunk (csrc/trunk_fp32.cu; NetworkEngine(trunk_fp32=True) /
+ * SOCCDPT_HYBRID_TRUNK=fp32).  Replaces, for that mode only, the bf16 tensor-core path of timm's StdConv2dSame / GroupNormAct /
+ * MaxPool2dSame as reached from SOccDPT/model/backbones/vit.py:147-258; CUDA-core fp32 FMA, fp32 activations and weights.
+ * conv: NHWC f32 x [batch,H,W,Cin], w [Cout][k][k][Cin] (already weight-standardised), TF "SAME" padding, stride 1 or 2,
+ *       y [batch, ceil(H/stride), ceil(W/stride), Cout], no bias. */
+int soccdpt_conv_f32_fwd(const float *x, const float *w, float *y, int batch, int H, int W, int Cin, int Cout, int k, int stride,
+                         soccdpt_stream_t stream);
+/* GroupNorm(32 groups, eps) [+ shortcut] [+ ReLU] on NHWC f32; y may alias x */
+int soccdpt_groupnorm_f32_fwd(const float *x, const float *gamma, const float *beta, const float *shortcut, float *y, int batch,
+                              int HW, int C, float eps, int relu, soccdpt_stream_t stream);
+/* MaxPool2dSame(3, stride 2) on NHWC f32 (padding value -inf) */
+int soccdpt_maxpool3s2_f32_fwd(const float *x, float *y, int batch, int H, int W, int C, soccdpt_stream_t stream);
+/* f32 [batch,C,HW] -> f32 [batch,HW,C] (the network input for the fp32 trunk) */
+int soccdpt_nchw_to_nhwc_f32(const float *x, float *y, int batch, int C, int HW, soccdpt_stream_t stream);
+
 /* tokens bf16 [batch, 1+L, D] (+ optional f32 copy) = cat(cls f32 [D], patches bf16 [batch, L, D]) + pos f32 [1+L, D]
  * (reference vit.py:66-80; the position embedding is used at its native 24x24 grid: 384x384 frames only) */
 int soccdpt_vit_tokens_fwd(const void *patches, const float *cls, const float *pos, void *tokens, float *tokens_f32, int batch,

@@ -82,6 +82,10 @@ SYMBOLS = {
     "soccdpt_selftest_exact_math": (_I, [ctypes.POINTER(Geometry), ctypes.POINTER(ctypes.c_ulonglong * 6), c_void_p]),
     "soccdpt_conv_fwd": (_I, [ctypes.POINTER(Conv), c_void_p]),
     "soccdpt_conv_ref_fwd": (_I, [ctypes.POINTER(Conv), c_void_p]),
+    "soccdpt_conv_f32_fwd": (_I, [c_void_p] * 3 + [_I] * 7 + [c_void_p]),
+    "soccdpt_groupnorm_f32_fwd": (_I, [c_void_p] * 5 + [_I] * 3 + [ctypes.c_float, _I, c_void_p]),
+    "soccdpt_maxpool3s2_f32_fwd": (_I, [c_void_p] * 2 + [_I] * 4 + [c_void_p]),
+    "soccdpt_nchw_to_nhwc_f32": (_I, [c_void_p] * 2 + [_I] * 3 + [c_void_p]),
     "soccdpt_patch_embed_fwd": (_I, [c_void_p] * 7 + [_I] * 4 + [c_void_p]),
     "soccdpt_window_attention_fwd": (_I, [c_void_p] * 4 + [_I] * 7 + [c_void_p]),
     "soccdpt_layernorm_fwd": (_I, [c_void_p] * 5 + [_LL, _I, _F, c_void_p]),

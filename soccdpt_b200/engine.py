@@ -68,6 +68,17 @@ class NetworkEngine:
         self.max_plans = int(os.environ.get("SOCCDPT_MAX_PLANS", "4"))
         self.lib = _cabi.load()
         self.use_graphs = os.environ.get("SOCCDPT_CUDA_GRAPH", "0") == "1"
+        # parity mode of dpt_hybrid_384: ResNetV2 trunk with fp32 storage and fp32 CUDA-core convolutions (csrc/trunk_fp32.cu)
+        self.trunk_fp32 = os.environ.get("SOCCDPT_HYBRID_TRUNK", "") == "fp32"
+
+    def set_trunk_precision(self, precision):
+        """"bf16" (product path) or "fp32" (parity mode of the hybrid encoder's ResNetV2 trunk: the 16 GroupNorm bottlenecks amplify
+        bf16 storage rounding ~50x on random-init weights; everything after the trunk stays on the product path)."""
+        assert precision in ("bf16", "fp32")
+        if self.trunk_fp32 != (precision == "fp32"):
+            self.trunk_fp32 = precision == "fp32"
+            self.invalidate()
+        return self
 
     def enable_graphs(self, on=True):
         """Replay each batch size's launch list as a CUDA graph (opt-in; SOCCDPT_CUDA_GRAPH=1 sets it at construction)."""
@@ -108,6 +119,8 @@ class NetworkEngine:
         bb = enc.patch_embed.backbone
         gn = lambda n: (_f32(n.weight, dev), _f32(n.bias, dev))
         H = dict(stem_w=_f32(self._std_weight(bb.stem.conv), dev), stem_n=gn(bb.stem.norm), stages=[])
+        f32w = (lambda c: _f32(self._std_weight(c).permute(0, 2, 3, 1).contiguous(), dev)) if self.trunk_fp32 else (lambda c: None)
+        H["stem_w32"] = f32w(bb.stem.conv)
         for stage in bb.stages:
             blocks = []
             for blk in stage.blocks:
@@ -118,6 +131,8 @@ class NetworkEngine:
                          w3=_pack_conv(self._std_weight(blk.conv3), dev), n3=gn(blk.norm3), down=None)
                 if blk.downsample is not None:
                     d["down"] = (_pack_conv(self._std_weight(blk.downsample.conv), dev), gn(blk.downsample.norm))
+                    d["down32"] = f32w(blk.downsample.conv)
+                d["w32"] = (f32w(blk.conv1), f32w(blk.conv2), f32w(blk.conv3))
                 blocks.append(d)
             H["stages"].append(blocks)
         H["proj"] = (_pack_conv(enc.patch_embed.proj.weight, dev), _f32(enc.patch_embed.proj.bias, dev))
@@ -323,6 +338,10 @@ class NetworkEngine:
                                shortcut.data_ptr() if shortcut is not None else None, (y if y is not None else x).data_ptr(),
                                B, HW, C, ctypes.c_float(1e-5), int(relu), gn_scratch.data_ptr()))
 
+        if self.trunk_fp32:
+            stage_out = self._plan_trunk_fp32(plan, buf, B, img)
+            return self._plan_vit(plan, buf, B, stage_out)
+
         # ---- ResNetV2 stem: StdConv 7x7/2 (SAME) -> GroupNorm + ReLU -> MaxPool 3x3/2 (SAME)
         H1 = (img + 1) // 2
         s0 = buf(B, H1, H1, 64)
@@ -356,6 +375,55 @@ class NetworkEngine:
                 gn(c3, b["n3"], Ho * Ho, cout, True, shortcut=shortcut)
                 cur, Hc = c3, Ho
             stage_out.append((cur, Hc, Hc, blocks[-1]["cout"]))
+        return self._plan_vit(plan, buf, B, stage_out)
+
+    def _plan_trunk_fp32(self, plan, buf, B, img):
+        """The ResNetV2 trunk of _plan_hybrid in the fp32-storage parity mode: same operator sequence, fp32 NHWC activations,
+        fp32 standardised weights, CUDA-core kernels (csrc/trunk_fp32.cu); the three stage outputs are rounded to bf16 once."""
+        Hy, lib, ops = self._weights["hy"], self.lib, plan["ops"]
+        f32 = torch.float32
+        eps = ctypes.c_float(1e-5)
+
+        def conv(x, w, H, cin, cout, k, st):
+            Ho = (H + st - 1) // st
+            y = buf(B, Ho, Ho, cout, dtype=f32)
+            ops.append(_Launch("conv_f32", lib.soccdpt_conv_f32_fwd, x.data_ptr(), w.data_ptr(), y.data_ptr(), B, H, H, cin, cout, k, st))
+            return y, Ho
+
+        def gn(x, n, HW, C, relu, shortcut=None):
+            ops.append(_Launch("groupnorm_f32", lib.soccdpt_groupnorm_f32_fwd, x.data_ptr(), n[0].data_ptr(), n[1].data_ptr(),
+                               shortcut.data_ptr() if shortcut is not None else None, x.data_ptr(), B, HW, C, eps, int(relu)))
+
+        xh = buf(B, img, img, 3, dtype=f32)
+        ops.append(_Launch("nchw_to_nhwc", lib.soccdpt_nchw_to_nhwc_f32, plan["x_arg"], xh.data_ptr(), B, 3, img * img))
+        s0, H1 = conv(xh, Hy["stem_w32"], img, 3, 64, 7, 2)
+        gn(s0, Hy["stem_n"], H1 * H1, 64, True)
+        Hc = (H1 + 1) // 2
+        cur = buf(B, Hc, Hc, 64, dtype=f32)
+        ops.append(_Launch("maxpool_f32", lib.soccdpt_maxpool3s2_f32_fwd, s0.data_ptr(), cur.data_ptr(), B, H1, H1, 64))
+        stage_out = []
+        for blocks in Hy["stages"]:
+            for b in blocks:
+                st, cin, mid, cout = b["stride"], b["cin"], b["mid"], b["cout"]
+                shortcut = cur
+                if b["down"] is not None:
+                    shortcut, Ho = conv(cur, b["down32"], Hc, cin, cout, 1, st)
+                    gn(shortcut, b["down"][1], Ho * Ho, cout, False)
+                a, _ = conv(cur, b["w32"][0], Hc, cin, mid, 1, 1)
+                gn(a, b["n1"], Hc * Hc, mid, True)
+                c2, Ho = conv(a, b["w32"][1], Hc, mid, mid, 3, st)
+                gn(c2, b["n2"], Ho * Ho, mid, True)
+                c3, _ = conv(c2, b["w32"][2], Ho, mid, cout, 1, 1)
+                gn(c3, b["n3"], Ho * Ho, cout, True, shortcut=shortcut)
+                cur, Hc = c3, Ho
+            o16 = buf(B, Hc, Hc, blocks[-1]["cout"])
+            ops.append(_Launch("f32_to_bf16", lib.soccdpt_f32_to_bf16, cur.data_ptr(), o16.data_ptr(), cur.numel()))
+            stage_out.append((o16, Hc, Hc, blocks[-1]["cout"]))
+        return stage_out
+
+    def _plan_vit(self, plan, buf, B, stage_out):
+        """Patch projection, the 12 ViT blocks and the tap post-processing of _plan_hybrid (vit.py:44-85, 179-219)."""
+        Hy, lib, ops = self._weights["hy"], self.lib, plan["ops"]
 
         # ---- patch projection (1x1 conv == linear), cls token + position embedding
         feat, g, _, Cf = stage_out[2]

@@ -65,12 +65,16 @@ def test_patch_merge_gather():
     assert torch.equal(y.cpu(), ref)
 
 
-@pytest.mark.parametrize("h,w,H,W", [(8, 8, 16, 16), (16, 16, 32, 32), (12, 12, 24, 24), (5, 7, 9, 20)])
-def test_upsample_bilinear_align_corners(h, w, H, W):
-    x = torch.randn(2, h, w, 32, generator=_g(4)).bfloat16()
+# exact x2 shapes run the row-marching kernel (segments of 8 row groups: 2, 3, 9, 17, 33 row groups cover one segment, a ragged
+# last segment and many segments); the last case is the general kernel
+@pytest.mark.parametrize("h,w,H,W,C", [(8, 8, 16, 16, 32), (16, 16, 32, 32, 32), (12, 12, 24, 24, 32), (2, 2, 4, 4, 8), (32, 20, 64, 40, 256),
+                                       (7, 9, 14, 18, 64), (5, 7, 9, 20, 32)])
+def test_upsample_bilinear_align_corners(h, w, H, W, C):
+    x = torch.randn(3, h, w, C, generator=_g(4)).bfloat16()
     y = K.upsample(x.cuda(), H, W)
     ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
     assert torch.allclose(y.float().cpu(), ref, rtol=1e-2, atol=1e-2)
+    assert (y.float().cpu() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()      # one bf16 rounding of the result
 
 
 @pytest.mark.parametrize("act", [0, 1])

@@ -175,6 +175,13 @@ typedef struct {
     int pad_trim;         /* rows/columns of zero padding REMOVED before the first row/column: the padding in front is
                              KH/2 - pad_trim (0 = symmetric torch padding).  TF-"SAME" 3x3 stride-2 convs on even
                              inputs (timm StdConv2dSame) pad 0 in front / 1 behind: pad_trim = 1. */
+    /* optional cosine-attention epilogue of a SwinV2 qkv linear (timm WindowAttention.forward: F.normalize(q) @
+     * F.normalize(k)^T * logit_scale): with qk_heads > 0 the output columns [0, 64*qk_heads) = (q | k), 32 per head, are
+     * L2-normalised per head from the fp32 accumulator (x / max(|x|, 1e-12)) and the q columns [0, 32*qk_heads) are also
+     * multiplied by qk_scale[head]; the v columns behind them are stored as they are.  Plain outputs only (no residual,
+     * projection or activation); consumer: soccdpt_window_attention_normed_fwd. */
+    const float *qk_scale; /* f32 [qk_heads] or NULL */
+    int qk_heads;
 } soccdpt_conv_t;
 
 /* tcgen05 / TMEM / TMA kernel (the product path) */
@@ -200,6 +207,16 @@ int soccdpt_patch_embed_fwd(const float *x, const float *w, const float *b, cons
 int soccdpt_window_attention_fwd(const void *qkv, const float *bias, const float *scale, void *out,
                                  int batch, int Hs, int Ws, int C, int heads, int ws, int shift,
                                  soccdpt_stream_t stream);
+
+/* The same operator for 16x16 windows on operands the qkv linear has already normalised (soccdpt_conv_t.qk_heads):
+ *   qkvn  bf16 [B, Hs*Ws, 3*C] = normalize(q) * scale * log2(e) | normalize(k) | v
+ *   bias, scale, out as above; shift in {0, 8}
+ * TMA-fed (2 x 2 boxes of 8 x 8 tokens per window: the cyclic shift is a box coordinate), persistent, pipelined across
+ * (window, head) items; one-pass softmax against the analytic logit bound, so every scale[h] must satisfy
+ * 2.01 * scale + 16 < 80 (the caller checks; soccdpt_window_attention_fwd has the exact row-max path for larger scales). */
+int soccdpt_window_attention_normed_fwd(const void *qkvn, const float *bias, const float *scale, void *out,
+                                        int batch, int Hs, int Ws, int C, int heads, int shift,
+                                        soccdpt_stream_t stream);
 
 /* y = (res ? res : 0) + LayerNorm(t) over the last dim (eps), bf16 in/out, fp32 math.
  * Swin res-post-norm: x + norm1(attn(x)), x + norm2(mlp(x)); PatchMerging norm (res = NULL). */

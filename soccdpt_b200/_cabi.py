@@ -44,6 +44,7 @@ class Conv(ctypes.Structure):
         ("Cout", ctypes.c_int), ("KH", ctypes.c_int), ("KW", ctypes.c_int), ("act", ctypes.c_int),
         ("proj_w", c_void_p), ("proj_b", c_void_p), ("proj_out", c_void_p),
         ("proj_n", ctypes.c_int), ("proj_relu", ctypes.c_int), ("stride", ctypes.c_int), ("pad_trim", ctypes.c_int),
+        ("qk_scale", c_void_p), ("qk_heads", ctypes.c_int),
     ]
 
 
@@ -88,6 +89,7 @@ SYMBOLS = {
     "soccdpt_nchw_to_nhwc_f32": (_I, [c_void_p] * 2 + [_I] * 3 + [c_void_p]),
     "soccdpt_patch_embed_fwd": (_I, [c_void_p] * 7 + [_I] * 4 + [c_void_p]),
     "soccdpt_window_attention_fwd": (_I, [c_void_p] * 4 + [_I] * 7 + [c_void_p]),
+    "soccdpt_window_attention_normed_fwd": (_I, [c_void_p] * 4 + [_I] * 6 + [c_void_p]),
     "soccdpt_layernorm_fwd": (_I, [c_void_p] * 5 + [_LL, _I, _F, c_void_p]),
     "soccdpt_layernorm_master_fwd": (_I, [c_void_p, c_void_p, _I, c_void_p, c_void_p, c_void_p, _LL, _I, _F, c_void_p]),
     "soccdpt_swin_block_tail_fwd": (_I, [ctypes.POINTER(BlockTail), c_void_p]),

@@ -571,6 +571,20 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     v[j4 * 4 + 2] = __uint_as_float(raw[j4 * 4 + 2]) + bb.z;
                     v[j4 * 4 + 3] = __uint_as_float(raw[j4 * 4 + 3]) + bb.w;
                 }
+                if (MODE == 0 && ACT == SOCCDPT_ACT_NONE && c.qk_heads > 0) {
+                    // cosine attention (timm WindowAttention): the 32 columns of this step are one head of q or k (N blocks
+                    // and column steps are head aligned): L2-normalise from the fp32 accumulator, q also takes the logit scale
+                    const int gc = cout0 + col;
+                    if (gc < 64 * c.qk_heads) {
+                        float ss = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
+                        float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+                        if (gc < 32 * c.qk_heads) inv *= c.qk_scale[gc >> 5];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= inv;
+                    }
+                }
                 if (ACT == SOCCDPT_ACT_RELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -708,8 +722,8 @@ int largest_divisor_leq(int n, int cap) {
     return 1;
 }
 
-int pick_block_n(int cout) {
-    for (int bn = 256; bn >= 16; bn -= 16)
+int pick_block_n(int cout, int step = 16) {   // step 32: N blocks made of whole 32-channel heads (cosine-attention epilogue)
+    for (int bn = 256; bn >= step; bn -= step)
         if (cout % bn == 0) return bn;
     return 0;
 }
@@ -727,7 +741,7 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
 
     Params p{};
     p.c = *c;
-    p.block_n = pick_block_n(c->Cout);
+    p.block_n = pick_block_n(c->Cout, c->qk_heads > 0 ? 32 : 16);
     SOCCDPT_REQUIRE(p.block_n >= 16, "conv: no valid N tile for Cout=%d", c->Cout);
     if (c->proj_n > 0) SOCCDPT_REQUIRE(p.block_n == c->Cout, "conv: fused projection needs the whole Cout in one tile");
     p.stride = c->stride > 1 ? c->stride : 1;

@@ -74,6 +74,11 @@ __global__ void __launch_bounds__(256) conv_ref_kernel(const soccdpt_conv_t c) {
         }
         float v = acc + (c.bias ? c.bias[co] : 0.0f);
         v = apply_act(v, c.act);
+        if (c.qk_heads > 0 && co < 64 * c.qk_heads) {   // cosine-attention epilogue: the 32 lanes hold one head of q or k
+            float inv = 1.0f / fmaxf(sqrtf(warp_sum(v * v)), 1e-12f);
+            if (co < 32 * c.qk_heads) inv *= c.qk_scale[co >> 5];
+            v *= inv;
+        }
         const long long o = pix * c.Cout + co;
         if (c.res1) v += __bfloat162float(static_cast<const bf16 *>(c.res1)[o]);
         if (c.res2) v += __bfloat162float(static_cast<const bf16 *>(c.res2)[o]);
@@ -661,6 +666,12 @@ int validate_conv(const soccdpt_conv_t *c) {
         SOCCDPT_REQUIRE(c->Cout <= 256, "conv: fused projection needs Cout <= 256");
     }
     SOCCDPT_REQUIRE(c->y || c->y_relu || c->proj_n > 0, "conv: no output requested");
+    if (c->qk_heads != 0) {
+        SOCCDPT_REQUIRE(c->qk_heads > 0 && c->qk_scale && c->Cout == 96 * c->qk_heads,
+                        "conv: the cosine-attention epilogue needs qk_scale and Cout == 3 * 32 * qk_heads (Cout=%d, qk_heads=%d)", c->Cout, c->qk_heads);
+        SOCCDPT_REQUIRE(c->y && !c->y_relu && !c->res1 && !c->res2 && c->proj_n == 0 && c->act == SOCCDPT_ACT_NONE,
+                        "conv: the cosine-attention epilogue writes y only (no activation, residual, ReLU copy or projection)");
+    }
     return SOCCDPT_OK;
 }
 }  // namespace soccdpt

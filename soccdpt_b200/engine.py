@@ -163,7 +163,11 @@ class NetworkEngine:
                 a = blk.attn
                 C = a.qkv.weight.shape[1]
                 bias = relative_position_bias_table(a, blk.window_size, layer.pretrained_window)
+                sc = torch.clamp(a.logit_scale.detach().float(), max=math.log(1.0 / 0.01)).exp().reshape(-1)
                 blocks.append(dict(
+                    # TMA-fed attention on operands the qkv GEMM already normalised (csrc/attention_tma.cu): 16x16 windows whose
+                    # logit scales admit the one-pass softmax bound (2.01 * scale + 16 < 80: every random-init head, most trained ones)
+                    qscale=_f32(sc * math.log2(math.e), dev), one_pass=bool((2.01 * sc.max() + 16.0 < 80.0).item()),
                     ws=blk.window_size, shift=blk.shift_size, heads=blk.num_heads,
                     wqkv=_bf16(a.qkv.weight, dev),
                     bqkv=_f32(torch.cat([a.q_bias.detach().float(), torch.zeros(C, device=a.q_bias.device),
@@ -232,9 +236,18 @@ class NetworkEngine:
             W["seg_act"] = 0 if isinstance(sh[6], torch.nn.Sigmoid) else 1
 
     # ------------------------------------------------------------------ plan construction
+    def _attn_tma(self, b, Hs, Ws):
+        """16x16 windows on the tcgen05 engine: the qkv GEMM normalises q / k in its epilogue and the TMA-fed pipelined kernel
+        (csrc/attention_tma.cu) consumes them.  SOCCDPT_ATTN_TMA=0 keeps the round-1 kernel (A/B runs); heads whose logit scale is too
+        large for the one-pass softmax bound keep it too (it has an exact row-max pre-pass)."""
+        return (self.conv_impl == "tcgen05" and b["ws"] == 16 and b["shift"] in (0, 8) and Hs % 16 == 0 and Ws % 16 == 0
+                and b["one_pass"] and os.environ.get("SOCCDPT_ATTN_TMA", "1") != "0")
+
     def _conv(self, plan, x, w, N, H, Wd, Cin, Cout, K, bias=None, act=_cabi.ACT_NONE, res1=None, res2=None, y=None,
-              y_relu=None, proj=None, stride=1, pad_trim=0):
+              y_relu=None, proj=None, stride=1, pad_trim=0, qk=None):
         c = _cabi.Conv()
+        if qk is not None:
+            c.qk_scale, c.qk_heads = qk[0].data_ptr(), qk[1]
         c.stride, c.pad_trim = stride, pad_trim
         c.x, c.wgt = x.data_ptr(), w.data_ptr()
         c.bias = bias.data_ptr() if bias is not None else None
@@ -294,9 +307,14 @@ class NetworkEngine:
             C, L = st["dim"], Hs * Ws
             M = B * L
             for b in st["blocks"]:
-                self._conv(plan, cur, b["wqkv"], 1, 1, M, C, 3 * C, 1, bias=b["bqkv"], y=qkv)
-                ops.append(_Launch("window_attention", lib.soccdpt_window_attention_fwd, qkv.data_ptr(), b["biasT"].data_ptr(),
-                                   b["scale"].data_ptr(), att.data_ptr(), B, Hs, Ws, C, b["heads"], b["ws"], b["shift"]))
+                if self._attn_tma(b, Hs, Ws):
+                    self._conv(plan, cur, b["wqkv"], 1, 1, M, C, 3 * C, 1, bias=b["bqkv"], y=qkv, qk=(b["qscale"], b["heads"]))
+                    ops.append(_Launch("window_attention", lib.soccdpt_window_attention_normed_fwd, qkv.data_ptr(),
+                                       b["biasT"].data_ptr(), b["scale"].data_ptr(), att.data_ptr(), B, Hs, Ws, C, b["heads"], b["shift"]))
+                else:
+                    self._conv(plan, cur, b["wqkv"], 1, 1, M, C, 3 * C, 1, bias=b["bqkv"], y=qkv)
+                    ops.append(_Launch("window_attention", lib.soccdpt_window_attention_fwd, qkv.data_ptr(), b["biasT"].data_ptr(),
+                                       b["scale"].data_ptr(), att.data_ptr(), B, Hs, Ws, C, b["heads"], b["ws"], b["shift"]))
                 if self._fuse_tail(C, "proj"):
                     self._block_tail(plan, att, None, None, b["wproj"], b["bproj"], b["n1"], master, cur, M, C, 0)
                 else:

@@ -11,7 +11,7 @@ def _s():
 
 
 def conv(x, w, bias=None, act=0, res1=None, res2=None, want_y=True, want_relu=False, proj=None, impl="tcgen05",
-         stride=1, pad_trim=0):
+         stride=1, pad_trim=0, qk=None):
     """x (N,H,W,Cin) bf16; w (Cout,KH*KW,Cin) bf16 packed. Returns (y, y_relu, proj_out)."""
     lib = _cabi.load()
     N, H, W, Cin = x.shape
@@ -34,6 +34,8 @@ def conv(x, w, bias=None, act=0, res1=None, res2=None, want_y=True, want_relu=Fa
         pw, pb, relu = proj
         po = torch.empty((N, Ho, Wo, pw.shape[0]), dtype=torch.float32, device=x.device)
         c.proj_w, c.proj_b, c.proj_out, c.proj_n, c.proj_relu = pw.data_ptr(), pb.data_ptr(), po.data_ptr(), pw.shape[0], int(relu)
+    if qk is not None:          # (qk_scale f32 [heads], heads): cosine-attention epilogue of a qkv linear
+        c.qk_scale, c.qk_heads = qk[0].data_ptr(), qk[1]
     fn = lib.soccdpt_conv_fwd if impl == "tcgen05" else lib.soccdpt_conv_ref_fwd
     _cabi.check(fn(ctypes.byref(c), _s()), "conv")
     return y, yr, po
@@ -104,6 +106,14 @@ def window_attention(qkv, biasT, scale, B, Hs, Ws, C, heads, ws, shift):
     out = torch.empty((B, Hs * Ws, C), dtype=torch.bfloat16, device=qkv.device)
     _cabi.check(lib.soccdpt_window_attention_fwd(qkv.data_ptr(), biasT.data_ptr(), scale.data_ptr(), out.data_ptr(), B, Hs,
                                                  Ws, C, heads, ws, shift, _s()), "window_attention")
+    return out
+
+
+def window_attention_normed(qkvn, biasT, scale, B, Hs, Ws, C, heads, shift):
+    lib = _cabi.load()
+    out = torch.empty((B, Hs * Ws, C), dtype=torch.bfloat16, device=qkvn.device)
+    _cabi.check(lib.soccdpt_window_attention_normed_fwd(qkvn.data_ptr(), biasT.data_ptr(), scale.data_ptr(), out.data_ptr(), B, Hs,
+                                                        Ws, C, heads, shift, _s()), "window_attention_normed")
     return out
 
 

@@ -136,6 +136,57 @@ def test_window_attention_vs_timm_restatement(res, ws, target_ws, heads, shift_b
         assert err.max().item() <= 4e-2 * mx and err.mean().item() <= 4e-3 * mx, (err.max().item(), err.mean().item(), mx)
 
 
+@pytest.mark.parametrize("res,heads,shift_block,B", [
+    (64, 3, True, 12), (64, 3, False, 2),       # stage 0 of swin2_tiny_256: 4x4 windows, every mask case (edge rows, columns, corner)
+    (32, 6, True, 3), (32, 6, False, 1),        # stage 1: 2x2 windows, each one a different mask case
+    (16, 12, True, 5),                          # stage 2: one window per frame (timm drops the shift)
+    (48, 2, True, 1), (16, 3, False, 70)])      # 3x3 windows (not a power of two); more items than CTAs x stages
+def test_window_attention_tma_vs_timm_restatement(res, heads, shift_block, B):
+    """The TMA-fed pipelined kernel on operands normalised by the qkv GEMM's epilogue (csrc/attention_tma.cu) against the oracle's
+    SwinTransformerBlock._attn, and against the round-1 kernel on the same raw qkv."""
+    ref_env.enable_shim()
+    from timm.models.swin_transformer_v2 import SwinTransformerBlock
+    from soccdpt_b200.model.encoder import relative_position_bias_table
+    C, ws = heads * 32, 16
+    torch.manual_seed(0)
+    blk = SwinTransformerBlock(C, (res, res), heads, ws, ws // 2 if shift_block else 0, 4.0, 0).eval()
+    g = _g(16)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.5 if p.dim() > 1 else 0.2))
+        blk.attn.logit_scale.copy_(torch.rand(heads, 1, 1, generator=g) * 1.4 + 1.6)   # exp -> 5 .. 20
+    a = blk.attn
+    x = torch.randn(B, res * res, C, generator=g).bfloat16()
+    with torch.no_grad():
+        wq = a.qkv.weight.bfloat16()
+        bq = torch.cat((a.q_bias, a.k_bias, a.v_bias)).float()
+        qkv32 = F.linear(x.float(), wq.float(), bq)                     # what the GEMM accumulates (fp32)
+        ref = _attn_from_qkv(blk, qkv32, B)
+        bias = relative_position_bias_table(a, ws, 0).contiguous().cuda()
+        scale = torch.clamp(a.logit_scale, max=math.log(100.0)).exp().reshape(-1).contiguous()
+    qscale = (scale * math.log2(math.e)).cuda()
+    # qkv GEMM with the cosine-attention epilogue, on both conv kernels
+    y_tc, _, _ = K.conv(x.view(1, 1, B * res * res, C).cuda(), wq.view(3 * C, 1, C).cuda().contiguous(), bias=bq.cuda(), qk=(qscale, heads))
+    y_ref, _, _ = K.conv(x.view(1, 1, B * res * res, C).cuda(), wq.view(3 * C, 1, C).cuda().contiguous(), bias=bq.cuda(), qk=(qscale, heads),
+                         impl="ref")
+    q, k, v = qkv32.view(B, res * res, 3, heads, 32).unbind(2)
+    want = torch.stack((F.normalize(q, dim=-1) * qscale.cpu().view(1, 1, heads, 1), F.normalize(k, dim=-1), v), dim=2).reshape(B * res * res, 3 * C)
+    for y in (y_tc, y_ref):
+        e = (y.float().cpu().view(-1, 3 * C) - want).abs()
+        # one bf16 rounding of the fp32 result; the absolute term covers the accumulation-order noise of a K = C sum (|terms| ~ 10)
+        assert (e <= 2.0 ** -8 * want.abs() + 1e-3).all(), (e - 2.0 ** -8 * want.abs()).max().item()
+    out = K.window_attention_normed(y_tc.view(B, res * res, 3 * C), bias, scale.cuda(), B, res, res, C, heads, blk.shift_size[0])
+    assert torch.isfinite(out.float()).all()
+    err = (out.float().cpu() - ref).abs()
+    mx = ref.abs().max().item()
+    assert err.max().item() <= 4e-2 * mx and err.mean().item() <= 4e-3 * mx, (err.max().item(), err.mean().item(), mx)
+    # the round-1 kernel on the raw bf16 qkv of the same GEMM: both are within bf16 noise of the reference, and of each other
+    raw, _, _ = K.conv(x.view(1, 1, B * res * res, C).cuda(), wq.view(3 * C, 1, C).cuda().contiguous(), bias=bq.cuda())
+    old = K.window_attention(raw.view(B, res * res, 3 * C), bias, scale.cuda(), B, res, res, C, heads, ws, blk.shift_size[0])
+    d = (out.float() - old.float()).abs().cpu()
+    assert d.max().item() <= 5e-2 * mx and d.mean().item() <= 5e-3 * mx, (d.max().item(), d.mean().item(), mx)
+
+
 def _attn_from_qkv(blk, qkv, B):
     """SwinTransformerBlock._attn with the qkv projection already applied (qkv: (B, L, 3C))."""
     from timm.models.swin_transformer_v2 import window_partition, window_reverse

@@ -92,8 +92,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// The producer and issuer warps run their loops with all 32 lanes in uniform control flow; every asynchronous instruction is
+// predicated on elect.sync inside its asm block (lane 0 of the full warp, every time).  Under `if (lane == 0)` the compiler must
+// assume a divergent warp and wraps each tcgen05.mma / cp.async.bulk.tensor in an ELECT ... BRA.U.ANY loop over the active lanes:
+// ~10 dependent SASS instructions, measured ~88 cycles per MMA on the issuing thread -- the "narrow-N floor" of round 1.  In
+// convergent code the same source is a bare UTCHMMA / UTMALDG with uniform-register operands (tools/microbench/mma_latency.cu:
+// SS N = 64 48 cycles, N = 128 63 cycles, TS N = 32 17 cycles per MMA).
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile(
+        "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
+        "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -115,12 +123,14 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
+        "@e cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n}\n"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
+        "@e cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n}\n"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
@@ -167,16 +177,19 @@ __device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint
                                             uint32_t accumulate) {
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, e;\n"
         ".reg .b64 da, db;\n"
         "setp.ne.b32 p, %5, 0;\n"
         "mov.b64 da, {%1, %3};\n"
         "mov.b64 db, {%2, %3};\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
         "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile(
+        "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -319,8 +332,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int k_blocks = taps * p.k_blocks_per_tap;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp, elect-predicated issue) =====================
+        {
             int stage = 0, a_stage = 0;
             uint32_t phase = 0, a_phase = 0;
             if (HALO && p.b_resident && blockIdx.x < p.total_tiles) {
@@ -382,8 +395,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp in uniform control flow, elect-predicated issue) =====================
+        {
             const uint32_t idesc = umma_idesc(p.block_n);
             int stage = 0, a_stage = 0;
             uint32_t phase = 0, a_phase = 0;

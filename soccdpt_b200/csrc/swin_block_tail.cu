@@ -251,19 +251,19 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
-        if (lane == 0 && my_tiles > 0) {
+        if (my_tiles > 0) {      // whole warp in uniform control flow, elect-predicated issue (tc_ptx.cuh)
             int s1 = 0, s2 = 0;                 // ring slots and their phase bits (no runtime divisions: these threads are latency bound)
             uint32_t ph1 = 0, ph2 = 0;
             auto load_w1 = [&](int j, int kc, int slot) {
                 const bool tail = kc >= p.kc64;
                 // resident: the tiles of a hidden chunk are packed (the 8 KB tail tile does not take a 16 KB slot)
                 uint8_t *dst = RES ? sW1 + (uint32_t)j * p.w1_chunk + kc * 16384 : sW1 + slot * W1_SLOT;
-                mbar_expect_tx(&bars->w1_full[slot], tail ? W1_SLOT / 2 : W1_SLOT);
-                tma_load_2d(dst, tail ? &mw1_32 : &mw1_64, &bars->w1_full[slot], kc * 64, j * HC);
+                mbar_expect_tx_elect(&bars->w1_full[slot], tail ? W1_SLOT / 2 : W1_SLOT);
+                tma_load_2d_elect(dst, tail ? &mw1_32 : &mw1_64, &bars->w1_full[slot], kc * 64, j * HC);
             };
             auto load_w2 = [&](int k0, bool tail, int slot) {
-                mbar_expect_tx(&bars->w2_full[slot], (uint32_t)C * (tail ? 64u : 128u));
-                tma_load_2d(sW2 + slot * p.w2_slot, tail ? &mw2_32 : &mw2_64, &bars->w2_full[slot], k0, 0);
+                mbar_expect_tx_elect(&bars->w2_full[slot], (uint32_t)C * (tail ? 64u : 128u));
+                tma_load_2d_elect(sW2 + slot * p.w2_slot, tail ? &mw2_32 : &mw2_64, &bars->w2_full[slot], k0, 0);
             };
             if (RES) {
                 // weights are constants: fetched before griddepcontrol.wait, under the previous kernel's tail
@@ -285,10 +285,10 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                     for (int kc = 0; kc < p.kc64; ++kc) {
                         mbar_wait(&bars->w2_empty[s2], ph2 ^ 1u);
                         uint8_t *dst = sW2 + s2 * stage_bytes;
-                        mbar_expect_tx(&bars->w2_full[s2], tx);
-                        tma_load_2d(dst, &mx64, &bars->w2_full[s2], kc * 64, tile * BM);
-                        tma_load_2d(dst + 16384, &mw2_64, &bars->w2_full[s2], kc * 64, 0);
-                        if (C > 256) tma_load_2d(dst + 16384 + 32768, &mw2_32, &bars->w2_full[s2], kc * 64, 256);
+                        mbar_expect_tx_elect(&bars->w2_full[s2], tx);
+                        tma_load_2d_elect(dst, &mx64, &bars->w2_full[s2], kc * 64, tile * BM);
+                        tma_load_2d_elect(dst + 16384, &mw2_64, &bars->w2_full[s2], kc * 64, 0);
+                        if (C > 256) tma_load_2d_elect(dst + 16384 + 32768, &mw2_32, &bars->w2_full[s2], kc * 64, 256);
                         if (++s2 == p.ns2) { s2 = 0; ph2 ^= 1u; }
                     }
                 }
@@ -297,9 +297,9 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
             for (int tile = blockIdx.x; tile < ((!MLP && !RES && p.stream_a) ? 0 : p.tiles); tile += gridDim.x, ++it) {
                 const int row0 = tile * BM;
                 mbar_wait(&bars->a_empty, (uint32_t)(it & 1) ^ 1u);
-                mbar_expect_tx(&bars->a_full, p.a_bytes);
-                for (int kc = 0; kc < p.kc64; ++kc) tma_load_2d(sA + kc * 16384, &mx64, &bars->a_full, kc * 64, row0);
-                if (p.ktail) tma_load_2d(sA + p.kc64 * 16384, &mx32, &bars->a_full, p.kc64 * 64, row0);
+                mbar_expect_tx_elect(&bars->a_full, p.a_bytes);
+                for (int kc = 0; kc < p.kc64; ++kc) tma_load_2d_elect(sA + kc * 16384, &mx64, &bars->a_full, kc * 64, row0);
+                if (p.ktail) tma_load_2d_elect(sA + p.kc64 * 16384, &mx32, &bars->a_full, p.kc64 * 64, row0);
                 if (RES) continue;
                 if (MLP) {
                     // fc1 weight tiles only: the fc2 ring has its own producer (warp 3) -- with one thread feeding both, a full
@@ -322,15 +322,15 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
         }
     } else if (warp == 3) {
         // ============================== second TMA producer: the fc2 weight ring (streamed two-GEMM mode) ==============================
-        if (MLP && !RES && lane == 0 && my_tiles > 0) {
+        if (MLP && !RES && my_tiles > 0) {
             int s2 = 0;
             uint32_t ph2 = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 for (int j = 0; j < p.nch; ++j) {
                     for (int h = 0; h < 2; ++h) {
                         mbar_wait(&bars->w2_empty[s2], ph2 ^ 1u);
-                        mbar_expect_tx(&bars->w2_full[s2], (uint32_t)C * 128u);
-                        tma_load_2d(sW2 + s2 * p.w2_slot, &mw2_64, &bars->w2_full[s2], j * HC + h * 64, 0);
+                        mbar_expect_tx_elect(&bars->w2_full[s2], (uint32_t)C * 128u);
+                        tma_load_2d_elect(sW2 + s2 * p.w2_slot, &mw2_64, &bars->w2_full[s2], j * HC + h * 64, 0);
                         if (++s2 == p.ns2) { s2 = 0; ph2 ^= 1u; }
                     }
                 }
@@ -338,7 +338,7 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
         }
     } else if (warp == 1) {
         // ============================== MMA issuer ==============================
-        if (lane == 0 && my_tiles > 0) {
+        if (my_tiles > 0) {      // whole warp in uniform control flow, elect-predicated issue (tc_ptx.cuh)
             const uint32_t idesc1 = umma_idesc(HC), idesc2 = umma_idesc(C);
             const uint32_t hi128 = (uint32_t)(umma_desc(0, 128) >> 32), hi64 = (uint32_t)(umma_desc(0, 64) >> 32);
             const uint32_t a_lo0 = (uint32_t)umma_desc(smem_u32(sA), 128);           // low words: (address & 0x3FFFF) >> 4 | LBO
@@ -374,10 +374,10 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                         }
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_ss_lo(d1, a_lo + 2 * k, b_lo + 2 * k, hi128, idesc1, acc);
+                            umma_ss_lo_elect(d1, a_lo + 2 * k, b_lo + 2 * k, hi128, idesc1, acc);
                             acc = 1u;
                         }
-                        if (!RES) umma_commit(&bars->w1_empty[slot]);
+                        if (!RES) umma_commit_elect(&bars->w1_empty[slot]);
                         a_lo += 16384 >> 4;
                         b_lo += 16384 >> 4;
                     }
@@ -392,12 +392,12 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                             if (++s1 == p.ns1) { s1 = 0; ph1 ^= 1u; }
                             b_lo = w1_lo0 + (uint32_t)slot * (W1_SLOT >> 4);
                         }
-                        umma_ss_lo(d1, a_lo, b_lo, hi64, idesc1, acc);
-                        umma_ss_lo(d1, a_lo + 2, b_lo + 2, hi64, idesc1, 1u);
-                        if (!RES) umma_commit(&bars->w1_empty[slot]);
+                        umma_ss_lo_elect(d1, a_lo, b_lo, hi64, idesc1, acc);
+                        umma_ss_lo_elect(d1, a_lo + 2, b_lo + 2, hi64, idesc1, 1u);
+                        if (!RES) umma_commit_elect(&bars->w1_empty[slot]);
                     }
-                    umma_commit(&bars->d1_full[g & 1]);
-                    if (j == nch - 1) umma_commit(&bars->a_empty);     // the activation tile is free once these MMAs retire
+                    umma_commit_elect(&bars->d1_full[g & 1]);
+                    if (j == nch - 1) umma_commit_elect(&bars->a_empty);     // the activation tile is free once these MMAs retire
                 };
                 // fc2 of chunk j: D2 (+)= H (bf16 pairs in the consumed D1 columns) x W2[:, chunk]
                 auto fc2 = [&](int g, int it, int j) {
@@ -426,12 +426,12 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                         const uint32_t b_lo = w2_lo0 + (uint32_t)slot * w2_step;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {   // hidden [hh*64 + k*16, +16) of the chunk = H columns hh*64 + k*8 .. +8
-                            umma_ts_lo(d2, h + (uint32_t)(hh * 64 + k * 8), b_lo + 2 * k, hi128, idesc2, acc);
+                            umma_ts_lo_elect(d2, h + (uint32_t)(hh * 64 + k * 8), b_lo + 2 * k, hi128, idesc2, acc);
                             acc = 1u;
                         }
-                        if (!RES) umma_commit(&bars->w2_empty[slot]);
+                        if (!RES) umma_commit_elect(&bars->w2_empty[slot]);
                     }
-                    if (j == nch - 1) umma_commit(&bars->d2_full[db2]);
+                    if (j == nch - 1) umma_commit_elect(&bars->d2_full[db2]);
                 };
                 fc1(0, 0, 0);
                 int it = 0, j = 0;                      // (tile iteration, chunk) of global chunk g
@@ -465,14 +465,14 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                         const uint32_t b_lo = a_lo + (16384u >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_ss_lo(d2, a_lo + 2 * k, b_lo + 2 * k, hi128, idesc_a, acc);
-                            if (C > 256) umma_ss_lo(d2 + 256u, a_lo + 2 * k, b_lo + (32768u >> 4) + 2 * k, hi128, idesc_b, acc);
+                            umma_ss_lo_elect(d2, a_lo + 2 * k, b_lo + 2 * k, hi128, idesc_a, acc);
+                            if (C > 256) umma_ss_lo_elect(d2 + 256u, a_lo + 2 * k, b_lo + (32768u >> 4) + 2 * k, hi128, idesc_b, acc);
                             acc = 1u;
                         }
-                        umma_commit(&bars->w2_empty[s2]);
+                        umma_commit_elect(&bars->w2_empty[s2]);
                         if (++s2 == p.ns2) { s2 = 0; ph2 ^= 1u; }
                     }
-                    umma_commit(&bars->d2_full[db2]);
+                    umma_commit_elect(&bars->d2_full[db2]);
                 }
             } else {
                 const int kc64 = p.kc64, ktail = p.ktail;
@@ -498,18 +498,18 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                         if (kc < kc64) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                umma_ss_lo(d2, a_lo + 2 * k, b_lo + 2 * k, hi128, idesc2, acc);
+                                umma_ss_lo_elect(d2, a_lo + 2 * k, b_lo + 2 * k, hi128, idesc2, acc);
                                 acc = 1u;
                             }
                         } else {
-                            umma_ss_lo(d2, a_lo, b_lo, hi64, idesc2, acc);
-                            umma_ss_lo(d2, a_lo + 2, b_lo + 2, hi64, idesc2, 1u);
+                            umma_ss_lo_elect(d2, a_lo, b_lo, hi64, idesc2, acc);
+                            umma_ss_lo_elect(d2, a_lo + 2, b_lo + 2, hi64, idesc2, 1u);
                         }
-                        if (!RES) umma_commit(&bars->w2_empty[slot]);
+                        if (!RES) umma_commit_elect(&bars->w2_empty[slot]);
                         a_lo += 16384 >> 4;
                     }
-                    umma_commit(&bars->a_empty);
-                    umma_commit(&bars->d2_full[db2]);
+                    umma_commit_elect(&bars->a_empty);
+                    umma_commit_elect(&bars->d2_full[db2]);
                 }
             }
         }

@@ -52,6 +52,24 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// warp-convergent forms (all 32 lanes execute, elect.sync picks the issuing lane; see umma_*_elect below)
+__device__ __forceinline__ void mbar_expect_tx_elect(uint64_t *bar, uint32_t bytes) {
+    asm volatile(
+        "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
+        "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
+        "@e cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n}\n"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_elect(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
+        "@e cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n}\n"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 // pulls [addr, addr + bytes) into L2 ahead of plain loads (bytes % 16 == 0, addr 16-byte aligned)
 __device__ __forceinline__ void l2_prefetch(const void *addr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
@@ -115,6 +133,43 @@ __device__ __forceinline__ void umma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uin
         "mov.b64 db, {%2, %3};\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
         "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Warp-convergent issue forms: executed by ALL 32 lanes of the issuing warp in uniform control flow, the instruction itself
+// predicated on elect.sync (lane 0 of a full warp, every time: MMAs and their commits come from the same thread).  Inside an
+// `if (lane == 0)` region the compiler has to assume a divergent warp and wraps every tcgen05.mma in an ELECT / BRA.U.ANY loop over
+// the active lanes (~10 dependent SASS instructions, measured ~88 cycles per MMA on the issuing thread: the hand-off bound of the
+// window-attention pipeline); in convergent code with the elect predicate the same source compiles to a bare UTCHMMA with its
+// descriptors in uniform registers (2-3 instructions per MMA).
+__device__ __forceinline__ void umma_ss_lo_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, e;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_ts_lo_elect(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, e;\n"
+        ".reg .b64 db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 // arrives on `bar` once every MMA issued so far by this thread has completed (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {

@@ -16,8 +16,6 @@
 namespace soccdpt {
 int launch_window_attention_tc(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
                                int C, int heads, int ws, int shift, cudaStream_t st);
-int launch_window_attention_ws(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
-                               int C, int heads, int shift, cudaStream_t st);
 int launch_window_attention_small(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
                                   int C, int heads, int ws, cudaStream_t st);
 int launch_window_attention_mma16(const void *qkv, const float *biasT, const float *scale, void *out, int batch, int Hs, int Ws,
@@ -182,18 +180,14 @@ extern "C" int soccdpt_window_attention_fwd(const void *qkv, const float *bias, 
     // (attention_tc.cu, attention_tc24.cu); the small last-stage windows (8x8, 12x12) use the CUDA-core kernel above.
     // SOCCDPT_ATTENTION_REF=1 (tests only) forces the CUDA-core kernel for an on-device cross-check.
     static const bool force_ref = getenv("SOCCDPT_ATTENTION_REF") != nullptr;
-    // 256-token windows: round 1's one-CTA-per-(window, head) kernel (attention_tc.cu) stays the default; SOCCDPT_ATTN_WS=1
-    // selects the warp-specialised persistent kernel of round 2 (attention_ws.cu: cp.async producers two items ahead, two
-    // independent softmax streams, one MMA-issuing thread per stream), which measures the same 140-165 us per stage-0 launch:
-    // ablations (profiles/r2_progress.md) show neither MUFU, nor the bias LDS, nor the TMEM loads bound either kernel
-    static const bool use_ws = getenv("SOCCDPT_ATTN_WS") && getenv("SOCCDPT_ATTN_WS")[0] == '1';
+    // 256-token windows through THIS entry point (raw qkv): round 1's one-CTA-per-(window, head) kernel (attention_tc.cu), which
+    // normalises q / k itself and has the exact row-max pre-pass for huge logit scales.  The engine's default for 16x16 windows
+    // is soccdpt_window_attention_normed_fwd (attention_tma.cu) on operands the qkv GEMM already normalised.
     // SOCCDPT_ATTN_MMA=1: the warp-level MMA kernel (attention_mma.cu) also for the 256-token windows -- 145 / 152 us per stage-0
     // launch against 141 / 156 us (un-shifted / shifted) for the tcgen05 kernel: a tie, like every other structure tried
     static const bool use_mma = getenv("SOCCDPT_ATTN_MMA") && getenv("SOCCDPT_ATTN_MMA")[0] == '1';
     if (N == 256 && !force_ref && use_mma)
         return soccdpt::launch_window_attention_mma16(qkv, bias, scale, out, batch, Hs, Ws, C, heads, shift, soccdpt::as_stream(stream));
-    if (N == 256 && !force_ref && use_ws)
-        return soccdpt::launch_window_attention_ws(qkv, bias, scale, out, batch, Hs, Ws, C, heads, shift, soccdpt::as_stream(stream));
     if (N == 256 && !force_ref) return soccdpt::launch_window_attention_tc(qkv, bias, scale, out, batch, Hs, Ws, C, heads, ws, shift,
                                                                            soccdpt::as_stream(stream));
     if (N == 576 && !force_ref) return soccdpt::launch_window_attention_tc24(qkv, bias, scale, out, batch, Hs, Ws, C, heads, shift,

@@ -1,4 +1,4 @@
-// SwinV2 window attention for 16x16 windows, TMA-fed and pipelined across (window, head) items (round 2, second half).
+// SwinV2 window attention for 16x16 windows, TMA-fed and pipelined across (window, head) items (round 2).
 // timm 0.6.12 WindowAttention + SwinTransformerBlock._attn (roll, window partition, cosine attention, cpb bias, shift mask,
 // softmax, P V, window reverse, roll back) -- reference call site SOccDPT/model/backbones/swin_common.py:16-27.
 //
@@ -16,16 +16,23 @@
 //   * the shift mask is block structured in this order: the regions of timm's attn_mask are the 8 x 8 boxes of the windows in the
 //     last window row / column, so a masked (query box, key box) pair is a warp-uniform "P = 0" (the reference adds -100 to those
 //     logits: a factor e^-100 < 2^-126 / e^-80 below every un-masked term the one-pass bound admits, i.e. exactly 0 in bf16).
-// One persistent 576-thread CTA per SM; all items of a CTA belong to ONE head (grid = a multiple of the head count), so the
-// relative-position bias table is staged once.  Work unit = (item, 128-query half h, 128-key block kb):
-//   warp 16    TMA producer, 3 stages x 48 KB, up to three items ahead
-//   warp 17    MMA issuer (one thread):  S_u = Q^_h K^_kb^T (M128 N128 K32) into TMEM buffer u % 3, two units ahead of
-//              O_h (+)= P_u V_kb (A operand = P in TMEM, M128 N32 K128), O in one of four 32-column accumulators
-//   warps 0-11 three softmax groups of 128 threads (thread = query row = TMEM lane), group g owns S buffer g:
-//              x = S + bias (log2 domain, pre-shifted by the analytic logit bound: ONE pass, no row max), ex2, row sum, bf16
-//              pairs written back over the consumed score columns (tcgen05.st)
-//   warps 12-15 epilogue: O / (l_0 + l_1) -> bf16 -> the token's un-shifted position
-// The three S buffers decouple the groups: while one waits for its P V / next S hand-off the other two keep the MUFU busy.
+// One persistent 832-thread CTA per SM; all items of a CTA belong to ONE head (grid = a multiple of the head count), so the
+// relative-position bias table is staged once.  Work unit = (item, 128-query half h, 64-key block kb = one 8 x 8 box of keys):
+//   warp 24     TMA producer, 3 stages x 48 KB, up to three items ahead; it also decodes the item (frame, window, mask case) once
+//   warp 25     MMA issuer:  S_u = Q^_h K^_kb^T (M128 N64 K32) into TMEM buffer u % 7, SIX units ahead of
+//               O_h (+)= P_u V_kb (A operand = P in TMEM, M128 N32 K64), O in one of two 32-column accumulators.  The loop is
+//               unrolled over the 8 units of an item and issues in warp-convergent, elect-predicated form (tc_ptx.cuh)
+//   warps 0-19  five softmax groups of 128 threads (thread = query row = TMEM lane); unit u goes to group u % 5:
+//               x = S + bias (log2 domain, pre-shifted by the analytic logit bound: ONE pass, no row max), ex2, row sum, bf16
+//               pairs written back over the consumed score columns (tcgen05.st).  The bias comes as two LDS.128 per key row
+//               from four shifted copies of the x-reversed table; adds and sums are packed fp32x2
+//   warps 20-23 epilogue: O / (l_0 + .. + l_3) -> bf16 -> the token's un-shifted position
+// Seven S buffers for five groups leave two units of slack for the P -> (P V, next S) -> group hand-off (~800 cycles through
+// the single issuing warp); measured structure (tools/trace_attention.py, profiles/r2b_*):
+//   * 3 groups x 128-key units on 3 buffers: the groups waited 29-47 % of the time for their next S tile;
+//   * issue inside `if (lane == 0)` cost ~88 cycles per MMA on the issuing thread (ELECT / BRA.U.ANY loop per instruction);
+//   * tensor time is irrelevant (tools/microbench/mma_latency.cu: 17 cycles per N = 32 TS MMA, 48 per N = 64 SS MMA);
+//   * inside the softmax loops the MUFU pipe is ~85 % busy; what is left is hand-off slack and the per-launch ramp.
 // Precondition (checked by the engine at pack time): every head's logit scale satisfies 2.01 * scale + 16 < 80.
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -244,7 +251,7 @@ window_attention_tma_kernel(const __grid_constant__ CUtensorMap mqkv, const floa
 #pragma unroll
         for (int j = 0; j < 6; ++j) issue_pv(prev_lo, (j + 2) & 3, j == 5 ? &empty[prev_st] : nullptr);
     } else if (warp < A_SM_WARPS) {
-        // ===================== softmax groups: group g owns the S buffers g and g + 3 and works through the units u = g (mod 3)
+        // ===================== softmax groups: group g works through the units u = g (mod A_GROUPS); unit u lives in buffer u % 7
         const int g = warp >> 2;
         const int row = (warp & 3) * 32 + lane;                 // query row of the half == TMEM lane
         const int my_bx = row >> 6;                              // box column of my query

@@ -1,10 +1,3 @@
-mkdir -p gpurun_out/r2T
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r2T/t_all.log 2>&1; echo "all rc=$?"
-tail -5 gpurun_out/r2T/t_all.log
-timeout 300 python bench.py > gpurun_out/r2T/bench.json 2> gpurun_out/r2T/bench.err; echo "bench rc=$?"
-python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/r2T/bench.json").read().strip().splitlines()[-1])
-print(d["value"], d["ms_per_step"], d["kernels_ms_per_step"], d["roofline"]["frac"], d["model_frac_of_peak"], d["e2e"]["value"])
-PY
-timeout 200 python tools/bench_block_tail.py 2>&1 | tail -8
+mkdir -p gpurun_out/r2V
+timeout 200 python tools/bench_conv.py 2>&1 | tee gpurun_out/r2V/bench_conv.log
+ONLY="S2 fc1" timeout 300 ncu --set full --import-source on --clock-control none -k regex:conv_tcgen05 -s 5 -c 1 -o gpurun_out/r2V/s2fc1 python tools/bench_conv.py > gpurun_out/r2V/ncu.log 2>&1; echo "ncu rc=$?"

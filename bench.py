@@ -430,7 +430,9 @@ def main():
     e2e_note = {"input": f"uint8 frames at network resolution ({img}x{img}x3) from pinned host memory, normalised on the device",
                 "result": "REDUCED: bf16 network-resolution inverse depth + class maps and the bit-packed occupancy mask of the "
                           "call; the reference's fp32 4-tuple at camera resolution (83 MB per frame) is produced on the device "
-                          "every step but not copied to the host"}
+                          "every step but not copied to the host",
+                "overlap": ("post-processing of batch i on its own stream under the network of batch i+1 (FrameStream overlap_post)"
+                            if fs.overlap_post else "none: network and post-processing of a batch run back to back on one stream")}
 
     with torch.no_grad():
         if args.stream_frames:

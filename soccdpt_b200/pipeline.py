@@ -8,6 +8,10 @@
 
 Three CUDA streams (upload / compute / download) and double-buffered device + pinned host buffers overlap
 the host->device copy of batch i+1 and the device->host copy of batch i-1 with the kernels of batch i.
+``overlap_post=True`` (or SOCCDPT_STREAM_OVERLAP=1) adds a fourth stream that runs the HBM-bound post-processing of batch i
+under the network of batch i+1 (the network's depth / class maps are copied out of the engine's static buffers first).  It is
+OFF by default: measured on B200 it changes nothing (9237 vs 9310 frames/s end to end, profiles/r2b_stream_overlap.log) -- the
+persistent network kernels hold all 148 SMs with ~226 KB of shared memory each, so the voxeliser's CTAs find no SM to share.
 Multi-GPU: one process per GPU, each rank feeds its own shard of the frame stream (`shard_range`); there is no
 collective on the data path.  `gather_masks` is the optional exchange step for callers that want the
 reference's union-over-batch occupancy ACROSS shards (an OR over the ranks' grids).
@@ -53,8 +57,13 @@ class FrameStream:
     either way; it is not copied to the host by this class.
     """
 
-    def __init__(self, net, batch, device=None, camera_frames=None, frames=None, frame_shape=None, result="dense"):
+    def __init__(self, net, batch, device=None, camera_frames=None, frames=None, frame_shape=None, result="dense",
+                 overlap_post=None):
+        import os
         from . import _cabi
+        if overlap_post is None:
+            overlap_post = os.environ.get("SOCCDPT_STREAM_OVERLAP", "0") == "1"
+        self.overlap_post = bool(overlap_post)
         self.net = net
         self.batch = batch
         self.device = _cabi.normalize_device(device if device is not None else next(net.parameters()).device)
@@ -70,6 +79,7 @@ class FrameStream:
         C, G = net.num_classes, net.grid_size
         dev = self.device
         self.up, self.comp, self.down = (torch.cuda.Stream(dev) for _ in range(3))
+        self.post = torch.cuda.Stream(dev) if self.overlap_post else self.comp
         self.x_dev = [torch.empty((batch, 3, img, img), dtype=torch.float32, device=dev) for _ in range(2)]
         self.transform, self.u8_dev = None, None
         if frames == "u8":
@@ -93,6 +103,9 @@ class FrameStream:
         self.d_host = [torch.empty((batch, img, img), dtype=map_dtype).pin_memory() for _ in range(2)]
         self.s_host = [torch.empty((batch, C, img, img), dtype=map_dtype).pin_memory() for _ in range(2)]
         self.g_host = [torch.empty(gshape, dtype=gdtype).pin_memory() for _ in range(2)]
+        if self.overlap_post:      # the network outputs of batch i outlive the launch plan's static buffers
+            self.nd_dev = [torch.empty((batch, img, img), dtype=torch.float32, device=dev) for _ in range(2)]
+            self.ns_dev = [torch.empty((batch, C, img, img), dtype=torch.float32, device=dev) for _ in range(2)]
         stage = self.u8_dev[0] if self.u8_dev is not None else self.x_dev[0]
         self.h2d_bytes = stage.numel() * stage.element_size()
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.d_host[0], self.s_host[0], self.g_host[0]))
@@ -111,6 +124,7 @@ class FrameStream:
         """Yields one FrameResult per input batch, in order.  A result's host buffers are reused two batches later."""
         ev_up = [torch.cuda.Event() for _ in range(2)]
         ev_comp = [torch.cuda.Event() for _ in range(2)]
+        ev_net = [torch.cuda.Event() for _ in range(2)]
         ev_down = [torch.cuda.Event() for _ in range(2)]
         ev_free_x = [None, None]       # compute finished reading x_dev[slot]
         pending = []
@@ -128,14 +142,24 @@ class FrameStream:
                     ev_up[slot].record(self.up)
                 with torch.cuda.stream(self.comp):
                     self.comp.wait_event(ev_up[slot])
-                    if i >= 2:
-                        self.comp.wait_event(ev_down[slot])      # download of batch i-2 has drained this slot
                     if self.transform is not None:
                         self.transform(self.u8_dev[slot], out=self.x_dev[slot])
+                    depth, seg = net.network(self.x_dev[slot])      # the buffers this call filled (static engine buffers)
+                    if self.overlap_post:
+                        if i >= 2:
+                            self.comp.wait_event(ev_comp[slot])     # post-processing of batch i-2 has read nd_dev / ns_dev[slot]
+                        self.nd_dev[slot].copy_(depth.reshape(self.nd_dev[slot].shape), non_blocking=True)
+                        self.ns_dev[slot].copy_(seg.reshape(self.ns_dev[slot].shape), non_blocking=True)
+                        depth, seg = self.nd_dev[slot], self.ns_dev[slot]
+                    ev_net[slot].record(self.comp)
+                    ev_free_x[slot] = ev_net[slot]
+                with torch.cuda.stream(self.post):
+                    self.post.wait_event(ev_net[slot])
+                    if i >= 2:
+                        self.post.wait_event(ev_down[slot])      # download of batch i-2 has drained this slot
                     saved = net.occupancy_output
                     net.occupancy_output = self._occ_output
                     try:
-                        depth, seg = net.network(self.x_dev[slot])      # the buffers this call filled (static engine buffers)
                         occ = net.get_semantic_occupancy(depth, seg)[3]
                     finally:
                         net.occupancy_output = saved
@@ -143,8 +167,7 @@ class FrameStream:
                     self._to_maps(seg, self.s_dev[slot])
                     self.g_dev[slot].copy_(occ.reshape(self.g_dev[slot].shape) if self.per_frame or self.result == "packed"
                                            else occ[:1], non_blocking=True)
-                    ev_comp[slot].record(self.comp)
-                    ev_free_x[slot] = ev_comp[slot]
+                    ev_comp[slot].record(self.post)
                 with torch.cuda.stream(self.down):
                     self.down.wait_event(ev_comp[slot])
                     self.d_host[slot].copy_(self.d_dev[slot], non_blocking=True)

@@ -32,12 +32,13 @@ def _direct(net, x):
         return d.clone().cpu(), s.clone().cpu(), out[3][0].clone().cpu()
 
 
-def test_stream_of_fp32_batches_equals_direct_calls(net):
+@pytest.mark.parametrize("overlap_post", [False, True])      # True: post-processing of batch i on its own stream
+def test_stream_of_fp32_batches_equals_direct_calls(net, overlap_post):
     B = 2
-    batches = [synthetic_frames(B, 256, 20 + i).pin_memory() for i in range(4)]      # > 2: the buffers are recycled
-    fs = FrameStream(net, B)
+    batches = [synthetic_frames(B, 256, 20 + i).pin_memory() for i in range(5)]      # > 2: the buffers are recycled
+    fs = FrameStream(net, B, overlap_post=overlap_post)
     got = [(r.index, r.inv_depth.clone(), r.segmentation.clone(), r.occupancy.clone()) for r in fs.run(batches)]
-    assert [g[0] for g in got] == [0, 1, 2, 3]
+    assert [g[0] for g in got] == [0, 1, 2, 3, 4]
     for (_, d, s, g), xb in zip(got, batches):
         d0, s0, g0 = _direct(net, xb.cuda())
         assert torch.equal(d, d0) and torch.equal(s, s0) and torch.equal(g, g0)

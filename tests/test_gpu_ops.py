@@ -233,6 +233,28 @@ def test_conv_ref_kernel_vs_torch(N, H, W, Cin, Cout, K3):
         assert torch.allclose(po.cpu(), F.relu(ref @ pw.t() + pb), rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("N,h,w", [(2, 16, 16), (1, 24, 40), (1, 33, 50), (1, 2, 2), (2, 70, 17), (1, 3, 129)])
+def test_depth_tail_vs_fp32_gather_of_the_same_taps(N, h, w):
+    """The tail kernel alone, on a given bf16 tap tensor, against upsample -> shift -> sum in fp32 (tolerance: fp32 rounding order).
+    Shapes cover ragged column segments (w % 16), strips of one row (h % 32 == 1), the 2x2 minimum and several strips."""
+    g = _g(21)
+    T = torch.randn(N, h, w, 288, generator=g).bfloat16()
+    b2 = torch.randn(32, generator=g) * 0.1
+    pw, pb = torch.randn(32, generator=g) * 0.2, torch.randn(1, generator=g) * 0.1
+    out = K.depth_tail(T.cuda(), b2.cuda(), pw.cuda(), pb.cuda()).cpu()
+    up = F.interpolate(T.double().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)   # (N, 288, 2h, 2w)
+    up = F.pad(up, (1, 1, 1, 1))
+    acc = b2.double().view(1, 32, 1, 1).expand(N, 32, 2 * h, 2 * w).clone()
+    for dy in range(3):
+        for dx in range(3):
+            t = dy * 3 + dx
+            acc += up[:, t * 32:(t + 1) * 32, dy:dy + 2 * h, dx:dx + 2 * w]
+    ref = F.relu((F.relu(acc) * pw.double().view(1, 32, 1, 1)).sum(1) + pb.double()).float()
+    assert out.shape == ref.shape
+    err = (out - ref).abs().max().item()
+    assert err <= 1e-4 * max(ref.abs().max().item(), 1.0), err
+
+
 @pytest.mark.parametrize("N,h,w", [(2, 16, 16), (1, 24, 40)])
 def test_depth_head_tail_equals_upsample_conv_relu_proj(N, h, w):
     """dpt.py:209-219 restructured: tap matrices at low resolution (tcgen05 GEMM) + gather == the reference order."""

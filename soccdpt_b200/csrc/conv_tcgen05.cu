@@ -59,6 +59,10 @@ constexpr int HALO_ROWS = 3 * HALO_W;                    // 390 rows of 128 B
 constexpr int HALO_BYTES = HALO_ROWS * BLOCK_K * 2;      // 49920 B moved by TMA
 constexpr int HALO_STAGE_BYTES = 50 * 1024;              // 1024-aligned slot
 constexpr int HALO_A_STAGES = 2;
+// ROW-PAIR variant of HALO for N <= 128 (Params::m2): one box {64 ch, 130 px, 4 rows} feeds TWO M tiles (image rows h0 and h0 + 1),
+// each weight tile is used by both -> half the weight bytes and 2/3 of the activation bytes per MMA; the two accumulators take
+// columns [0,128) and [128,256) of the TMEM stage and one epilogue warpgroup each.
+constexpr int HALO2_BYTES = 4 * HALO_W * BLOCK_K * 2;    // 66560 B = 65 x 1024: the slot size as well
 constexpr int HALO_B_BYTES = 3 * B_STAGE_BYTES;          // 96 KB weight ring, split into b_stages slots of one tap tile
 constexpr int MAX_B_STAGES = 24;
 constexpr int RING_BYTES_PLAIN = STAGES * STAGE_BYTES;                                           // 196608
@@ -78,6 +82,8 @@ struct Params {
     int pad;                   // zero padding before the first row / column
     int stride, Ho, Wo;        // output grid = ceil(input / stride)
     int b_stages;              // HALO: depth of the weight ring (96 KB / bytes per tap tile, <= 24)
+    int m2;                    // HALO: two M tiles (rows h0, h0 + 1) per pass, see HALO2_BYTES
+    int halo_slot, halo_bytes; // HALO: bytes between the two halo slots / moved per halo box
     int b_resident;            // HALO: the whole weight tensor (<= 96 KB) is loaded once per CTA and stays in smem
     int nres;                  // plain 1x1 path: the grid is a multiple of n_blocks, so a CTA keeps ONE N block for all its tiles and
                                // that block's weights ([k_blocks][block_n][64], <= 144 KB) stay resident; the ring holds A tiles only
@@ -338,7 +344,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             uint32_t phase = 0, a_phase = 0;
             if (HALO && p.b_resident && blockIdx.x < p.total_tiles) {
                 // narrow layers (e.g. 128->32: 72 KB of weights): fetch every (channel block, tap) tile once
-                uint8_t *b_ring = smem + HALO_A_STAGES * HALO_STAGE_BYTES;
+                uint8_t *b_ring = smem + HALO_A_STAGES * p.halo_slot;
                 mbar_expect_tx(&full[0], (uint32_t)(p.k_blocks_per_tap * 9) * p.b_bytes);
                 for (int cb = 0; cb < p.k_blocks_per_tap; ++cb)
                     for (int tap = 0; tap < 9; ++tap)
@@ -354,7 +360,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-                const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+                const int w0 = tw * p.BW, h0 = th * (HALO && p.m2 ? 2 : p.BH), n0 = tn * p.BN;
                 if (!HALO && p.nres) {
                     for (int kb = 0; kb < k_blocks; ++kb) {          // 1x1: k block == channel block, tap (0, 0)
                         mbar_wait(&empty[stage], phase ^ 1);
@@ -366,11 +372,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
                 if (HALO) {
                     // channel-block outer, tap inner: one halo tile (A ring) feeds nine weight tiles (B ring)
-                    uint8_t *b_ring = smem + HALO_A_STAGES * HALO_STAGE_BYTES;
+                    uint8_t *b_ring = smem + HALO_A_STAGES * p.halo_slot;
                     for (int cb = 0; cb < p.k_blocks_per_tap; ++cb) {
                         mbar_wait(&a_empty[a_stage], a_phase ^ 1);
-                        mbar_expect_tx(&a_full[a_stage], HALO_BYTES);
-                        tma_load_4d(smem + a_stage * HALO_STAGE_BYTES, &map_a, &a_full[a_stage], cb * BLOCK_K, w0 - 1, h0 - 1, n0);
+                        mbar_expect_tx(&a_full[a_stage], (uint32_t)p.halo_bytes);
+                        tma_load_4d(smem + a_stage * p.halo_slot, &map_a, &a_full[a_stage], cb * BLOCK_K, w0 - 1, h0 - 1, n0);
                         if (++a_stage == HALO_A_STAGES) { a_stage = 0; a_phase ^= 1; }
                         if (p.b_resident) continue;
                         for (int tap = 0; tap < 9; ++tap) {
@@ -439,7 +445,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     continue;
                 }
                 if (HALO) {
-                    const uint32_t b_ring = smem_u32(smem + HALO_A_STAGES * HALO_STAGE_BYTES);
+                    const uint32_t b_ring = smem_u32(smem + HALO_A_STAGES * p.halo_slot);
                     const uint32_t desc_hi = (uint32_t)(umma_desc(0) >> 32);
                     uint32_t first = 0u;                     // becomes 1 after the first MMA of the tile
                     for (int cb = 0; cb < p.k_blocks_per_tap; ++cb) {
@@ -449,8 +455,29 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         tc_fence_after();
                         // descriptor low word of the halo tile; a tap is a constant row offset: output pixel bw of
                         // the tile reads halo row kh, pixel bw + kw
-                        const uint32_t a_lo = (uint32_t)umma_desc(smem_u32(smem + a_stage * HALO_STAGE_BYTES));
-                        if (p.b_resident) {
+                        const uint32_t a_lo = (uint32_t)umma_desc(smem_u32(smem + a_stage * p.halo_slot));
+                        if (p.m2) {
+                            // row pair: every weight tile multiplies the halo rows of BOTH output rows (second tile: one halo row lower)
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint32_t at = a_lo + (uint32_t)(((tap / 3) * HALO_W + (tap % 3)) * 8);
+                                mbar_wait(&full[stage], phase);
+                                tc_fence_after();
+                                const uint32_t b_lo = (uint32_t)umma_desc(b_ring + stage * p.b_bytes);
+                                if (ksteps == 4) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) umma_f16_lo(d_tmem, at + 2 * k, b_lo + 2 * k, desc_hi, idesc, k == 0 ? first : 1u);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) umma_f16_lo(d_tmem + 128u, at + HALO_W * 8 + 2 * k, b_lo + 2 * k, desc_hi, idesc, k == 0 ? first : 1u);
+                                } else {
+                                    for (int k = 0; k < ksteps; ++k) umma_f16_lo(d_tmem, at + 2 * k, b_lo + 2 * k, desc_hi, idesc, k == 0 ? first : 1u);
+                                    for (int k = 0; k < ksteps; ++k) umma_f16_lo(d_tmem + 128u, at + HALO_W * 8 + 2 * k, b_lo + 2 * k, desc_hi, idesc, k == 0 ? first : 1u);
+                                }
+                                first = 1u;
+                                umma_commit(&empty[stage]);
+                                if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+                            }
+                        } else if (p.b_resident) {
                             uint32_t b_lo = (uint32_t)umma_desc(b_ring + (uint32_t)(cb * 9) * p.b_bytes);
                             const uint32_t b_step = p.b_bytes >> 4;
 #pragma unroll
@@ -541,7 +568,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // column split in whole 32-column chunks (the TMA-store granule): warpgroup 0 takes ceil(chunks/2) of them,
         // warpgroup 1 the rest plus a possible 16-column tail (N = 144, 16)
         const int c_split = (((p.block_n >> 5) + 1) >> 1) << 5;
-        const int col_begin = wg == 0 ? 0 : c_split, col_end = wg == 0 ? c_split : p.block_n;
+        const bool m2 = HALO && p.m2;              // row pair: warpgroup wg drains ALL columns of M tile wg (TMEM columns wg * 128 ...)
+        const int col_begin = m2 || wg == 0 ? 0 : c_split, col_end = m2 ? p.block_n : (wg == 0 ? c_split : p.block_n);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
@@ -560,14 +588,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             // row -> pixel
             const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
-            const int wx = tw * p.BW + bw, hy = th * p.BH + bh, ni = tn * p.BN + bn;
+            const int h_tile = m2 ? th * 2 + wg : th * p.BH;
+            const int wx = tw * p.BW + bw, hy = h_tile + bh, ni = tn * p.BN + bn;
             const bool valid = (row < m_valid) && (wx < p.Wo) && (hy < p.Ho) && (ni < c.N);
             const long long pix = ((long long)ni * p.Ho + hy) * p.Wo + wx;
             const long long obase = pix * c.Cout + cout0;
 
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + (m2 ? wg * 128 : 0));
             float proj[4] = {0.f, 0.f, 0.f, 0.f};
             int col = col_begin;
             // ---- 32-column steps
@@ -630,7 +659,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                         if (row == 0) {
-                            tma_store_4d(&map_y, stage, cout0 + col, tw * p.BW, th * p.BH, tn * p.BN);
+                            tma_store_4d(&map_y, stage, cout0 + col, tw * p.BW, h_tile, tn * p.BN);
                             tma_store_commit();
                         }
                     }
@@ -641,7 +670,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                         if (row == 0) {
-                            tma_store_4d(&map_yr, stage, cout0 + col, tw * p.BW, th * p.BH, tn * p.BN);
+                            tma_store_4d(&map_yr, stage, cout0 + col, tw * p.BW, h_tile, tn * p.BN);
                             tma_store_commit();
                         }
                     }
@@ -786,8 +815,13 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
                       p.BH == 1 && p.BN == 1;
     p.b_resident = (halo && p.block_n == c->Cout &&
                     (long long)((c->Cin + BLOCK_K - 1) / BLOCK_K) * 9 * p.block_n * BLOCK_K * 2 <= HALO_B_BYTES) ? 1 : 0;
+    const int mode = c->proj_n > 0 ? 2 : ((c->res1 || c->res2 || c->y_relu || !c->y) ? 1 : 0);
+    static const bool m2_enabled = !(getenv("SOCCDPT_CONV_M2") && getenv("SOCCDPT_CONV_M2")[0] == '0');
+    p.m2 = (m2_enabled && halo && !p.b_resident && mode != 2 && p.block_n <= 128 && p.Ho % 2 == 0 && c->qk_heads == 0) ? 1 : 0;
+    p.halo_slot = p.m2 ? HALO2_BYTES : HALO_STAGE_BYTES;
+    p.halo_bytes = p.m2 ? HALO2_BYTES : HALO_BYTES;
     p.tiles_w = (p.Wo + p.BW - 1) / p.BW;
-    p.tiles_h = (p.Ho + p.BH - 1) / p.BH;
+    p.tiles_h = p.m2 ? p.Ho / 2 : (p.Ho + p.BH - 1) / p.BH;
     p.tiles_n = (c->N + p.BN - 1) / p.BN;
     p.n_blocks = c->Cout / p.block_n;
     const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
@@ -796,7 +830,7 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     p.k_blocks_per_tap = (c->Cin + BLOCK_K - 1) / BLOCK_K;
     p.a_bytes = (uint32_t)(p.BW * p.BH * p.BN) * BLOCK_K * 2;
     p.b_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
-    p.b_stages = HALO_B_BYTES / (int)p.b_bytes;
+    p.b_stages = (p.m2 ? RING_BYTES - HALO_A_STAGES * HALO2_BYTES : HALO_B_BYTES) / (int)p.b_bytes;
     if (p.b_stages > MAX_B_STAGES) p.b_stages = MAX_B_STAGES;
     // resident N block (see Params::nres): 1x1, stride 1, the block's weights fit behind an A ring of >= 3 slots, and enough
     // M tiles per CTA for the one-off weight fetch to pay
@@ -818,7 +852,7 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
         cuuint64_t strides[3] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)c->W * c->Cin * 2, (cuuint64_t)c->H * c->W * c->Cin * 2};
         // stride 2: the box spans stride*BW input pixels and the traversal stride keeps every second one
         cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(p.BW * p.stride), (cuuint32_t)(p.BH * p.stride), (cuuint32_t)p.BN};
-        if (halo) { box[1] = HALO_W; box[2] = 3; }
+        if (halo) { box[1] = HALO_W; box[2] = p.m2 ? 4 : 3; }
         cuuint32_t estr[4] = {1, (cuuint32_t)p.stride, (cuuint32_t)p.stride, 1};
         SOCCDPT_REQUIRE(box[1] <= 256 && box[2] <= 256, "conv: tile too wide for a strided TMA box");
         CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(c->x), dims, strides, box, estr,
@@ -854,7 +888,6 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SOCCDPT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out) failed with %d", (int)r);
     }
-    const int mode = c->proj_n > 0 ? 2 : ((c->res1 || c->res2 || c->y_relu || !c->y) ? 1 : 0);
     if (mode == 2) SOCCDPT_REQUIRE(c->y == nullptr && c->y_relu == nullptr && !c->res1 && !c->res2,
                                    "conv: the fused projection epilogue produces proj_out only");
     int grid = p.total_tiles < soccdpt::sm_count() ? p.total_tiles : soccdpt::sm_count();

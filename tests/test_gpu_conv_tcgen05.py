@@ -43,6 +43,11 @@ CASES = [
     (12, 64, 64, 256, 256, 1, 0, True, 0, True, 0),      # out_conv 1x1 (NHWC boxes 64 x 2) + ReLU copy
     (3, 128, 128, 128, 288, 1, 0, False, 0, False, 0),   # depth-head tap GEMM: 2 N blocks of 144
     (5, 128, 128, 256, 256, 1, 1, True, 0, False, 3),    # fused projection epilogue on the resident path
+    # ROW-PAIR halo path (3x3, W % 128 == 0, N <= 128, even H): two M tiles per weight tile
+    (2, 4, 128, 64, 128, 3, 0, True, 0, False, 0),       # one channel block, pad rows at both image edges inside one box
+    (1, 6, 256, 96, 64, 3, 1, True, 2, True, 0),         # K tail (96), N = 64 (second accumulator at TMEM column 128), residuals + ReLU copy
+    (3, 128, 128, 256, 128, 3, 0, True, 0, False, 0),    # depth head conv 0 at > 148 pair tiles (persistent loop, accumulator ring)
+    (1, 5, 128, 128, 128, 3, 0, True, 0, False, 0),      # odd H: falls back to single-row halo tiles
 ]
 
 

@@ -23,10 +23,11 @@ def test_base_384_matches_oracle(tmp_path):
     sd = seeded_state_dict(net.state_dict(), 0)
     net.load_state_dict(sd, strict=True)
     net.to("cuda").eval()
-    x = synthetic_frames(1, 384, 0)
+    x = synthetic_frames(2, 384, 0)          # two different frames: batch > 1 takes the multi-frame tile paths of every level
     with torch.no_grad():
         depth, seg = (t.clone() for t in net.network(x.cuda()))
-        out = net(x.cuda())
+        depth1 = net.network(x[:1].cuda())[0].clone()
+        out = net(x[:1].cuda())
     torch.cuda.synchronize()
     orc = O.OracleV3(sd, mt)
     d_ref, s_ref, _, _ = orc.network(x)
@@ -36,4 +37,5 @@ def test_base_384_matches_oracle(tmp_path):
           f"seg max {serr.max().item():.3e} mean {serr.mean().item():.3e}")
     assert bool((derr <= 4e-2 * d_ref.abs().max() + 2e-2 * d_ref.abs()).all())
     assert serr.max().item() <= 8e-2 and serr.mean().item() <= 8e-3
+    assert torch.allclose(depth1[0], depth[0], rtol=1e-3, atol=1e-4), "frame 0 of a batch of two differs from the same frame alone"
     assert out[0].shape == (1, 1080, 1920) and out[3].shape == (1, 256, 256, 32, 3)

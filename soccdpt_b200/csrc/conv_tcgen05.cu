@@ -82,6 +82,7 @@ struct Params {
     int pad;                   // zero padding before the first row / column
     int stride, Ho, Wo;        // output grid = ceil(input / stride)
     int b_stages;              // HALO: depth of the weight ring (96 KB / bytes per tap tile, <= 24)
+    int alt_split;             // epilogue: alternate the column split of odd chunk counts (SOCCDPT_CONV_ALT=0 switches it off)
     int m2;                    // HALO: two M tiles (rows h0, h0 + 1) per pass, see HALO2_BYTES
     int halo_slot, halo_bytes; // HALO: bytes between the two halo slots / moved per halo box
     int b_resident;            // HALO: the whole weight tensor (<= 96 KB) is loaded once per CTA and stays in smem
@@ -569,11 +570,17 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // warpgroup 1 the rest plus a possible 16-column tail (N = 144, 16)
         const int c_split = (((p.block_n >> 5) + 1) >> 1) << 5;
         const bool m2 = HALO && p.m2;              // row pair: warpgroup wg drains ALL columns of M tile wg (TMEM columns wg * 128 ...)
-        const int col_begin = m2 || wg == 0 ? 0 : c_split, col_end = m2 ? p.block_n : (wg == 0 ? c_split : p.block_n);
+        // an ODD number of chunks (N = 96: the S0 qkv / S1 fc layers) would give warpgroup 0 two chunks and warpgroup 1 one on
+        // every tile; the split alternates with the tile instead (floor / ceil), so both drain 3 chunks per 2 tiles -- these
+        // narrow-K layers are epilogue-bound
+        const bool alt_split = p.alt_split && !m2 && MODE != 2 && ((p.block_n >> 5) & 1) && (p.block_n & 31) == 0 && p.block_n > 32;
+        int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
             const int cout0 = nb * p.block_n;
+            const int split = (alt_split && (it++ & 1)) ? c_split - 32 : c_split;
+            const int col_begin = m2 || wg == 0 ? 0 : split, col_end = m2 ? p.block_n : (wg == 0 ? split : p.block_n);
             if (tile + (int)gridDim.x >= p.total_tiles) soccdpt::pdl_trigger();   // this CTA's last tile: let the next kernel in
             if (nb != cached_nb) {
                 // per-channel constants of this N block -> smem (visible to the 256 epilogue threads only)
@@ -816,6 +823,8 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     p.b_resident = (halo && p.block_n == c->Cout &&
                     (long long)((c->Cin + BLOCK_K - 1) / BLOCK_K) * 9 * p.block_n * BLOCK_K * 2 <= HALO_B_BYTES) ? 1 : 0;
     const int mode = c->proj_n > 0 ? 2 : ((c->res1 || c->res2 || c->y_relu || !c->y) ? 1 : 0);
+    static const bool alt_enabled = !(getenv("SOCCDPT_CONV_ALT") && getenv("SOCCDPT_CONV_ALT")[0] == '0');
+    p.alt_split = alt_enabled ? 1 : 0;
     static const bool m2_enabled = !(getenv("SOCCDPT_CONV_M2") && getenv("SOCCDPT_CONV_M2")[0] == '0');
     p.m2 = (m2_enabled && halo && !p.b_resident && mode != 2 && p.block_n <= 128 && p.Ho % 2 == 0 && c->qk_heads == 0) ? 1 : 0;
     p.halo_slot = p.m2 ? HALO2_BYTES : HALO_STAGE_BYTES;

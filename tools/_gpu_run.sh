@@ -1,16 +1,16 @@
-mkdir -p gpurun_out/fin
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/fin/pytest.log; tail -3 gpurun_out/fin/pytest.log
-timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -2 > gpurun_out/fin/smoke.log; cat gpurun_out/fin/smoke.log
-timeout 400 python bench.py > gpurun_out/fin/bench_tiny.json 2> gpurun_out/fin/bench_tiny.err; echo "tiny rc=$?"
-timeout 400 python bench.py --model base_384 --no-cpu-baseline > gpurun_out/fin/bench_base_384.json 2> gpurun_out/fin/bench_base_384.err; echo "base rc=$?"
-timeout 400 python bench.py --model hybrid_384 --no-cpu-baseline > gpurun_out/fin/bench_hybrid_384.json 2> gpurun_out/fin/bench_hybrid_384.err; echo "hybrid rc=$?"
-K='conv_tcgen05|window_attention|swin_block_tail|layernorm|patch_embed|upsample|depth_tail|seg_finish|unproject|grid_expand|resize_tables|ln_res'
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"$K" -s 100 -c 110 --csv --log-file gpurun_out/fin/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/fin/ncu1.log 2>&1
-PYTHONPATH=. timeout 200 python tools/bench_models.py --version 1 --model dpt_swin2_tiny_256 --batch 64 > gpurun_out/fin/v1.log 2>&1; tail -3 gpurun_out/fin/v1.log
-PYTHONPATH=. timeout 200 python tools/bench_latency.py > gpurun_out/fin/latency.log 2>&1; tail -3 gpurun_out/fin/latency.log
+mkdir -p gpurun_out/alt
+timeout 600 python -m pytest tests/test_gpu_conv_tcgen05.py tests/test_gpu_network.py tests/test_gpu_ops.py -x -q -m gpu 2>&1 | tail -4 > gpurun_out/alt/pytest.log; tail -3 gpurun_out/alt/pytest.log
+for i in 1 2; do
+SOCCDPT_CONV_ALT=1 timeout 300 python bench.py --steps 40 --warmup 8 --no-cpu-baseline > gpurun_out/alt/on_$i.json 2> gpurun_out/alt/on_$i.err
+SOCCDPT_CONV_ALT=0 timeout 300 python bench.py --steps 40 --warmup 8 --no-cpu-baseline > gpurun_out/alt/off_$i.json 2> gpurun_out/alt/off_$i.err
+done
 python - <<'PY'
 import json
-for n in ("tiny","base_384","hybrid_384"):
-    d=json.loads(open(f"gpurun_out/fin/bench_{n}.json").read().strip().splitlines()[-1])
-    print(n, round(d["value"]), round(d["ms_per_step"],3), 'e2e', round(d["e2e"]["value"]), d.get("model_frac_of_peak"), d["roofline"]["frac"], d["clocks"], d["kernels_ms_per_step"])
+for i in (1,2):
+  for n in ("on","off"):
+    d=json.loads(open(f"gpurun_out/alt/{n}_{i}.json").read().strip().splitlines()[-1])
+    print(n, i, round(d["value"]), round(d["ms_per_step"],3), d["kernels_ms_per_step"]["conv_tcgen05_kernel"], d["clocks"]["sm_mhz"])
 PY
+PYTHONPATH=. timeout 200 python tools/bench_conv.py 2>&1 | tail -40 > gpurun_out/alt/conv_on.log
+SOCCDPT_CONV_ALT=0 PYTHONPATH=. timeout 200 python tools/bench_conv.py 2>&1 | tail -40 > gpurun_out/alt/conv_off.log
+paste -d'|' gpurun_out/alt/conv_on.log gpurun_out/alt/conv_off.log | cut -c1-230 | head -45

@@ -182,6 +182,14 @@ typedef struct {
      * projection or activation); consumer: soccdpt_window_attention_normed_fwd. */
     const float *qk_scale; /* f32 [qk_heads] or NULL */
     int qk_heads;
+    /* optional third residual, UP-SAMPLED on the fly (FeatureFusionBlock_custom.forward, SOccDPT/model/blocks.py:476-487:
+     * output = xs[0] + resConfUnit1(xs[1]) where xs[0] is the previous block's
+     * interpolate(scale_factor=2, mode="bilinear", align_corners=True) output): up_src is the LOW-resolution map
+     * bf16 [N, up_h, up_w, Cout] with H == 2*up_h and W == 2*up_w; the epilogue adds its bilinear x2 (align_corners=True)
+     * interpolation at the output pixel, evaluated in fp32 -- the up-sampled tensor is never written.  Needs stride 1,
+     * Cout % 32 == 0, no fused projection. */
+    const void *up_src;
+    int up_h, up_w;
 } soccdpt_conv_t;
 
 /* tcgen05 / TMEM / TMA kernel (the product path) */

@@ -45,6 +45,7 @@ class Conv(ctypes.Structure):
         ("proj_w", c_void_p), ("proj_b", c_void_p), ("proj_out", c_void_p),
         ("proj_n", ctypes.c_int), ("proj_relu", ctypes.c_int), ("stride", ctypes.c_int), ("pad_trim", ctypes.c_int),
         ("qk_scale", c_void_p), ("qk_heads", ctypes.c_int),
+        ("up_src", c_void_p), ("up_h", ctypes.c_int), ("up_w", ctypes.c_int),
     ]
 
 

@@ -251,6 +251,21 @@ __device__ __forceinline__ void add_bf16_impl(float (&v)[LEN], const uint4 *p) {
 }
 template <int N, int LEN>
 __device__ __forceinline__ void add_bf16(float (&v)[LEN], const uint4 *p) { add_bf16_impl<N, LEN>(v, p); }
+// v[8*N] += w * bf16 values at p
+template <int N, int LEN>
+__device__ __forceinline__ void fma_bf16(float (&v)[LEN], const uint4 *p, float w) {
+#pragma unroll
+    for (int h = 0; h < N; ++h) {
+        const uint4 u = __ldg(p + h);
+        const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(b2[k]);
+            v[h * 8 + 2 * k] = fmaf(w, f.x, v[h * 8 + 2 * k]);
+            v[h * 8 + 2 * k + 1] = fmaf(w, f.y, v[h * 8 + 2 * k + 1]);
+        }
+    }
+}
 template <int N, bool RELU, int LEN>
 __device__ __forceinline__ void store_bf16(const float (&v)[LEN], uint4 *p) {
 #pragma unroll
@@ -600,6 +615,21 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const bool valid = (row < m_valid) && (wx < p.Wo) && (hy < p.Ho) && (ni < c.N);
             const long long pix = ((long long)ni * p.Ho + hy) * p.Wo + wx;
             const long long obase = pix * c.Cout + cout0;
+            // up-sampled residual (soccdpt_conv_t.up_src): the four low-resolution corners of this pixel and their weights
+            const bf16 *up00 = nullptr, *up01 = nullptr, *up10 = nullptr, *up11 = nullptr;
+            float uw00 = 0.f, uw01 = 0.f, uw10 = 0.f, uw11 = 0.f;
+            if (MODE == 1 && c.up_src && valid) {
+                const float fy = (float)(c.up_h - 1) / (float)(2 * c.up_h - 1) * (float)hy;
+                const float fx = (float)(c.up_w - 1) / (float)(2 * c.up_w - 1) * (float)wx;
+                const int y0 = (int)fy, x0 = (int)fx, y1 = y0 + (y0 < c.up_h - 1 ? 1 : 0), x1 = x0 + (x0 < c.up_w - 1 ? 1 : 0);
+                const float ly = fy - (float)y0, lx = fx - (float)x0;
+                const bf16 *ub = static_cast<const bf16 *>(c.up_src) + (long long)ni * c.up_h * c.up_w * c.Cout + cout0;
+                up00 = ub + ((long long)y0 * c.up_w + x0) * c.Cout;
+                up01 = ub + ((long long)y0 * c.up_w + x1) * c.Cout;
+                up10 = ub + ((long long)y1 * c.up_w + x0) * c.Cout;
+                up11 = ub + ((long long)y1 * c.up_w + x1) * c.Cout;
+                uw00 = (1.0f - ly) * (1.0f - lx); uw01 = (1.0f - ly) * lx; uw10 = ly * (1.0f - lx); uw11 = ly * lx;
+            }
 
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
@@ -656,6 +686,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const long long o = obase + col;
                         if (res1) add_bf16<4>(v, reinterpret_cast<const uint4 *>(res1 + o));
                         if (res2) add_bf16<4>(v, reinterpret_cast<const uint4 *>(res2 + o));
+                        if (up00) {
+                            fma_bf16<4>(v, reinterpret_cast<const uint4 *>(up00 + col), uw00);
+                            fma_bf16<4>(v, reinterpret_cast<const uint4 *>(up01 + col), uw01);
+                            fma_bf16<4>(v, reinterpret_cast<const uint4 *>(up10 + col), uw10);
+                            fma_bf16<4>(v, reinterpret_cast<const uint4 *>(up11 + col), uw11);
+                        }
                     }
                     uint8_t *stage = s_stage + wg * STAGING_BYTES;
                     const int bar_id = 3 + wg;                      // named barrier of this warpgroup (128 threads)
@@ -822,7 +858,8 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
                       p.BH == 1 && p.BN == 1;
     p.b_resident = (halo && p.block_n == c->Cout &&
                     (long long)((c->Cin + BLOCK_K - 1) / BLOCK_K) * 9 * p.block_n * BLOCK_K * 2 <= HALO_B_BYTES) ? 1 : 0;
-    const int mode = c->proj_n > 0 ? 2 : ((c->res1 || c->res2 || c->y_relu || !c->y) ? 1 : 0);
+    const int mode = c->proj_n > 0 ? 2 : ((c->res1 || c->res2 || c->up_src || c->y_relu || !c->y) ? 1 : 0);
+    if (c->up_src) SOCCDPT_REQUIRE((p.block_n & 31) == 0, "conv: the up-sampled residual needs N blocks of whole 32-column chunks (Cout=%d)", c->Cout);
     static const bool alt_enabled = !(getenv("SOCCDPT_CONV_ALT") && getenv("SOCCDPT_CONV_ALT")[0] == '0');
     p.alt_split = alt_enabled ? 1 : 0;
     static const bool m2_enabled = !(getenv("SOCCDPT_CONV_M2") && getenv("SOCCDPT_CONV_M2")[0] == '0');

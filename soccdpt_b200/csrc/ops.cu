@@ -82,6 +82,14 @@ __global__ void __launch_bounds__(256) conv_ref_kernel(const soccdpt_conv_t c) {
         const long long o = pix * c.Cout + co;
         if (c.res1) v += __bfloat162float(static_cast<const bf16 *>(c.res1)[o]);
         if (c.res2) v += __bfloat162float(static_cast<const bf16 *>(c.res2)[o]);
+        if (c.up_src) {     // bilinear x2, align_corners=True, of the low-resolution map at this pixel
+            const bf16 *u = static_cast<const bf16 *>(c.up_src);
+            const float fy = (float)(c.up_h - 1) / (float)(2 * c.up_h - 1) * (float)h0, fx = (float)(c.up_w - 1) / (float)(2 * c.up_w - 1) * (float)w0;
+            const int y0 = (int)fy, x0 = (int)fx, y1 = y0 + (y0 < c.up_h - 1 ? 1 : 0), x1 = x0 + (x0 < c.up_w - 1 ? 1 : 0);
+            const float ly = fy - (float)y0, lx = fx - (float)x0;
+            auto at = [&](int yy, int xx) { return __bfloat162float(u[(((long long)n * c.up_h + yy) * c.up_w + xx) * c.Cout + co]); };
+            v += (1.0f - ly) * ((1.0f - lx) * at(y0, x0) + lx * at(y0, x1)) + ly * ((1.0f - lx) * at(y1, x0) + lx * at(y1, x1));
+        }
         if (c.y) static_cast<bf16 *>(c.y)[o] = __float2bfloat16_rn(v);
         if (c.y_relu) static_cast<bf16 *>(c.y_relu)[o] = __float2bfloat16_rn(fmaxf(v, 0.0f));
         for (int p = 0; p < c.proj_n; ++p) proj[p] = fmaf(c.proj_w[p * c.Cout + co], v, proj[p]);
@@ -671,6 +679,12 @@ int validate_conv(const soccdpt_conv_t *c) {
                         "conv: the cosine-attention epilogue needs qk_scale and Cout == 3 * 32 * qk_heads (Cout=%d, qk_heads=%d)", c->Cout, c->qk_heads);
         SOCCDPT_REQUIRE(c->y && !c->y_relu && !c->res1 && !c->res2 && c->proj_n == 0 && c->act == SOCCDPT_ACT_NONE,
                         "conv: the cosine-attention epilogue writes y only (no activation, residual, ReLU copy or projection)");
+    }
+    if (c->up_src) {
+        SOCCDPT_REQUIRE(c->stride <= 1 && c->proj_n == 0 && c->qk_heads == 0 && c->Cout % 32 == 0,
+                        "conv: the up-sampled residual needs stride 1, Cout %% 32 == 0 and no projection (Cout=%d)", c->Cout);
+        SOCCDPT_REQUIRE(c->up_h >= 1 && c->up_w >= 1 && c->H == 2 * c->up_h && c->W == 2 * c->up_w,
+                        "conv: the up-sampled residual is an exact x2 (%dx%d -> %dx%d)", c->up_h, c->up_w, c->H, c->W);
     }
     return SOCCDPT_OK;
 }

@@ -244,8 +244,10 @@ class NetworkEngine:
                 and b["one_pass"] and os.environ.get("SOCCDPT_ATTN_TMA", "1") != "0")
 
     def _conv(self, plan, x, w, N, H, Wd, Cin, Cout, K, bias=None, act=_cabi.ACT_NONE, res1=None, res2=None, y=None,
-              y_relu=None, proj=None, stride=1, pad_trim=0, qk=None):
+              y_relu=None, proj=None, stride=1, pad_trim=0, qk=None, up=None):
         c = _cabi.Conv()
+        if up is not None:      # (low-resolution map, h, w): residual added through a bilinear x2 in the epilogue
+            c.up_src, c.up_h, c.up_w = up[0].data_ptr(), up[1], up[2]
         if qk is not None:
             c.qk_scale, c.qk_heads = qk[0].data_ptr(), qk[1]
         c.stride, c.pad_trim = stride, pad_trim
@@ -532,27 +534,33 @@ class NetworkEngine:
             self._conv(plan, t, Wt["rn"][i], B, Hs, Ws, C, F, 3, y=y, y_relu=yr)
             lv.append((y, yr, Hs, Ws))
 
-        def rcu(w, x, xr, H, Wd, res2=None, want_relu=False):
+        def rcu(w, x, xr, H, Wd, res2=None, want_relu=False, up=None):
             c1 = buf(B, H, Wd, F)
             self._conv(plan, xr, w[0], B, H, Wd, F, F, 3, bias=w[1], act=_cabi.ACT_RELU, y=c1)
             o = buf(B, H, Wd, F)
             orl = buf(B, H, Wd, F) if want_relu else None
-            self._conv(plan, c1, w[2], B, H, Wd, F, F, 3, bias=w[3], res1=x, res2=res2, y=o, y_relu=orl)
+            self._conv(plan, c1, w[2], B, H, Wd, F, F, 3, bias=w[3], res1=x, res2=res2, up=up, y=o, y_relu=orl)
             return o, orl
 
-        path = None
+        # the x2 upsample between two fusion blocks is folded into the consumer's epilogue (soccdpt_conv_t.up_src): its only reader
+        # is the residual add `xs[0] + resConfUnit1(xs[1])`; the last one (path_1) feeds the heads' 3x3 convs and stays a kernel
+        fold_up = os.environ.get("SOCCDPT_FOLD_UPSAMPLE", "1") != "0" and F % 32 == 0
+        path = up_low = None
         for i in (4, 3, 2, 1):
             fw = Wt["fusion"][i]
             y, yr, H, Wd = lv[i - 1]
-            if path is None:
+            if path is None and up_low is None:
                 s, sr = y, yr
             else:   # output = xs[0] + resConfUnit1(xs[1])   (blocks.py:476-479)
-                s, sr = rcu(fw["rcu1"], y, yr, H, Wd, res2=path, want_relu=True)
+                s, sr = rcu(fw["rcu1"], y, yr, H, Wd, res2=path, up=up_low, want_relu=True)
             o, _ = rcu(fw["rcu2"], s, sr, H, Wd)
             low = buf(B, H, Wd, F)
             self._conv(plan, o, fw["out_w"], B, H, Wd, F, F, 1, bias=fw["out_b"], y=low)   # out_conv before the upsample
             TH, TW = (lv[i - 2][2], lv[i - 2][3]) if i > 1 else (2 * H, 2 * Wd)
-            path = buf(B, TH, TW, F)
+            if fold_up and i > 1 and TH == 2 * H and TW == 2 * Wd:
+                path, up_low = None, (low, H, Wd)
+                continue
+            path, up_low = buf(B, TH, TW, F), None
             ops.append(_Launch("upsample", lib.soccdpt_upsample_bilinear_fwd, low.data_ptr(), path.data_ptr(), B, H, Wd, TH, TW, F))
         PH, PW = 2 * lv[0][2], 2 * lv[0][3]
         plan["path_1"] = path

@@ -11,7 +11,7 @@ def _s():
 
 
 def conv(x, w, bias=None, act=0, res1=None, res2=None, want_y=True, want_relu=False, proj=None, impl="tcgen05",
-         stride=1, pad_trim=0, qk=None):
+         stride=1, pad_trim=0, qk=None, up=None):
     """x (N,H,W,Cin) bf16; w (Cout,KH*KW,Cin) bf16 packed. Returns (y, y_relu, proj_out)."""
     lib = _cabi.load()
     N, H, W, Cin = x.shape
@@ -36,6 +36,8 @@ def conv(x, w, bias=None, act=0, res1=None, res2=None, want_y=True, want_relu=Fa
         c.proj_w, c.proj_b, c.proj_out, c.proj_n, c.proj_relu = pw.data_ptr(), pb.data_ptr(), po.data_ptr(), pw.shape[0], int(relu)
     if qk is not None:          # (qk_scale f32 [heads], heads): cosine-attention epilogue of a qkv linear
         c.qk_scale, c.qk_heads = qk[0].data_ptr(), qk[1]
+    if up is not None:          # (N, H/2, W/2, Cout) bf16: residual added through a bilinear x2 (align_corners=True) in the epilogue
+        c.up_src, c.up_h, c.up_w = up.data_ptr(), up.shape[1], up.shape[2]
     fn = lib.soccdpt_conv_fwd if impl == "tcgen05" else lib.soccdpt_conv_ref_fwd
     _cabi.check(fn(ctypes.byref(c), _s()), "conv")
     return y, yr, po

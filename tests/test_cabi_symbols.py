@@ -28,12 +28,13 @@ def test_header_symbols_are_exported(lib, repo_root):
 
 
 def test_struct_layouts_match_header():
-    # soccdpt_geometry_t: 4 f32, 3 i32, 3 i32, 3+3+3+27 f32, 1 i32, 2 f32 ; soccdpt_conv_t: 7 ptr, 8 i32, 3 ptr, 4 i32, 1 ptr, 1 i32 (+ 4 bytes tail padding)
+    # soccdpt_geometry_t: 4 f32, 3 i32, 3 i32, 3+3+3+27 f32, 1 i32, 2 f32 ; soccdpt_conv_t: 7 ptr, 8 i32, 3 ptr, 4 i32, 1 ptr, 1 i32 (+ 4 bytes padding), 1 ptr, 2 i32
     assert ctypes.sizeof(_cabi.Geometry) == 4 * (4 + 3 + 3 + 3 + 3 + 3 + 27 + 1 + 2)
     # soccdpt_block_tail_t: 9 ptr, i64, 3 i32, f32
     assert ctypes.sizeof(_cabi.BlockTail) == 9 * 8 + 8 + 4 * 4
-    assert ctypes.sizeof(_cabi.Conv) == 7 * 8 + 8 * 4 + 3 * 8 + 4 * 4 + 8 + 8
+    assert ctypes.sizeof(_cabi.Conv) == 7 * 8 + 8 * 4 + 3 * 8 + 4 * 4 + 8 + 8 + 8 + 8
     assert _cabi.Conv.qk_scale.offset == 128 and _cabi.Conv.qk_heads.offset == 136
+    assert _cabi.Conv.up_src.offset == 144 and _cabi.Conv.up_h.offset == 152 and _cabi.Conv.up_w.offset == 156
 
 
 def test_version_and_error_paths(lib):

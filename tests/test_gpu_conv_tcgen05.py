@@ -84,6 +84,37 @@ def test_tcgen05_conv(N, H, W, Cin, Cout, k, act, bias, nres, relu_out, proj_n):
         assert torch.allclose(po, po2, rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("N,H,W,C,k,relu_out", [(2, 16, 16, 256, 3, True), (1, 32, 32, 256, 3, True), (3, 64, 64, 256, 3, False),
+                                                (1, 2, 2, 64, 1, False), (1, 24, 48, 128, 3, True), (1, 128, 128, 128, 3, False)])
+def test_upsampled_residual_in_the_epilogue(N, H, W, C, k, relu_out):
+    """soccdpt_conv_t.up_src: y = conv(x) + bias + res1 + bilinear_x2(up_src) (FeatureFusionBlock_custom.forward, blocks.py:476-487,
+    without writing the up-sampled tensor) == the same with F.interpolate(scale_factor=2, align_corners=True) as a plain residual;
+    the last shape takes the row-pair halo tiles."""
+    g = torch.Generator().manual_seed(H * 7 + C)
+    x = torch.randn(N, H, W, C, generator=g).bfloat16()
+    w = (torch.randn(C, C, k, k, generator=g) / math.sqrt(C * k * k)).bfloat16()
+    b = torch.randn(C, generator=g) * 0.2
+    r1 = torch.randn(N, H, W, C, generator=g).bfloat16()
+    low = torch.randn(N, H // 2, W // 2, C, generator=g).bfloat16()
+    wp = K.pack_conv_weight(w.float()).cuda()
+    args = dict(bias=b.cuda(), res1=r1.cuda(), up=low.cuda(), want_relu=relu_out)
+    y, yr, _ = K.conv(x.cuda(), wp, impl="tcgen05", **args)
+    y2, yr2, _ = K.conv(x.cuda(), wp, impl="ref", **args)
+    torch.cuda.synchronize()
+    up = F.interpolate(low.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=k // 2).permute(0, 2, 3, 1) + r1.float() + up
+    tol = dict(rtol=2e-2, atol=2e-2)
+    assert torch.allclose(y.float().cpu(), ref, **tol), (y.float().cpu() - ref).abs().max()
+    assert torch.allclose(y.float(), y2.float(), rtol=1e-2, atol=1e-2)
+    if relu_out:
+        assert torch.allclose(yr.float().cpu(), F.relu(ref), **tol)
+        assert torch.allclose(yr.float(), yr2.float(), rtol=1e-2, atol=1e-2)
+    # the interpolation itself, isolated: zero weights and bias leave res1 + up
+    z, _, _ = K.conv(x.cuda(), torch.zeros_like(wp), impl="tcgen05", res1=r1.cuda(), up=low.cuda())
+    d = (z.float().cpu() - (r1.float() + up)).abs()
+    assert d.max().item() <= 2 ** -7 * (r1.float() + up).abs().max().item() + 1e-6      # one bf16 rounding of the sum
+
+
 def test_tcgen05_conv_is_deterministic_and_reentrant():
     g = torch.Generator().manual_seed(5)
     x = torch.randn(4, 32, 32, 256, generator=g).bfloat16().cuda()

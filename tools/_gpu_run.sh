@@ -1,13 +1,14 @@
-mkdir -p gpurun_out/mg
-for n in 8 2; do
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 5 --gather > gpurun_out/mg/bench_tiny_${n}gpu.json 2> gpurun_out/mg/bench_tiny_${n}gpu.err; echo "n=$n rc=$?"
-done
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --model base_384 --stream-frames 4096 > gpurun_out/mg/stream_base384_8gpu.json 2> gpurun_out/mg/stream_base384_8gpu.err; echo "stream rc=$?"
+mkdir -p gpurun_out/fin2
+timeout 400 python bench.py > gpurun_out/fin2/bench_tiny.json 2> gpurun_out/fin2/bench_tiny.err; echo "tiny rc=$?"
+timeout 400 python bench.py --model base_384 --no-cpu-baseline > gpurun_out/fin2/bench_base_384.json 2> gpurun_out/fin2/bench_base_384.err; echo "base rc=$?"
+timeout 400 python bench.py --model hybrid_384 --no-cpu-baseline > gpurun_out/fin2/bench_hybrid_384.json 2> gpurun_out/fin2/bench_hybrid_384.err; echo "hybrid rc=$?"
+K='conv_tcgen05|window_attention|swin_block_tail|layernorm|patch_embed|upsample|depth_tail|seg_finish|unproject|grid_expand|resize_tables|ln_res'
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"$K" -s 97 -c 110 --csv --log-file gpurun_out/fin2/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/fin2/ncu1.log 2>&1
+PYTHONPATH=. timeout 200 python tools/bench_models.py --version 1 --model dpt_swin2_tiny_256 --batch 64 > gpurun_out/fin2/v1.log 2>&1; grep "frames/s" gpurun_out/fin2/v1.log
+PYTHONPATH=. timeout 200 python tools/bench_latency.py > gpurun_out/fin2/latency.log 2>&1; tail -4 gpurun_out/fin2/latency.log
 python - <<'PY'
 import json
-for f in ("bench_tiny_8gpu","bench_tiny_2gpu","stream_base384_8gpu"):
-    try:
-        d=json.loads(open(f"gpurun_out/mg/{f}.json").read().strip().splitlines()[-1])
-        print(f, round(d["value"]), round(d["ms_per_step"],3), 'e2e', round(d["e2e"]["value"]) if d.get("e2e") else None, d.get("gather"), d["clocks"])
-    except Exception as e: print(f, 'ERR', e)
+for n in ("tiny","base_384","hybrid_384"):
+    d=json.loads(open(f"gpurun_out/fin2/bench_{n}.json").read().strip().splitlines()[-1])
+    print(n, round(d["value"]), round(d["ms_per_step"],3), 'e2e', round(d["e2e"]["value"]), d.get("model_frac_of_peak"), d["roofline"]["frac"], d["clocks"], d["kernels_ms_per_step"])
 PY

@@ -36,6 +36,19 @@ namespace soccdpt {
 int validate_conv(const soccdpt_conv_t *c);
 }
 
+// -DSOCCDPT_CONV_TRACE (debug builds only, tools/trace_conv.py): CTA 0 logs SM-clock stamps of its first tiles -- the MMA warp's and the
+// first epilogue thread's hand-offs -- into a global buffer read back by soccdpt_conv_trace_read()
+#ifdef SOCCDPT_CONV_TRACE
+constexpr int CT_TILES = 24, CT_EVENTS = 32;
+__device__ unsigned long long g_conv_trace[CT_TILES * CT_EVENTS];
+#define CTRACE(tile_it, ev)                                                                                          \
+    do {                                                                                                             \
+        if (blockIdx.x == 0 && (tile_it) < CT_TILES) g_conv_trace[(tile_it) * CT_EVENTS + (ev)] = (unsigned long long)clock64(); \
+    } while (0)
+#else
+#define CTRACE(tile_it, ev) do { } while (0)
+#endif
+
 namespace {
 
 using bf16 = __nv_bfloat16;
@@ -51,6 +64,7 @@ constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 384;          // 4 control warps + 8 epilogue warps
 constexpr int EPI_THREADS = 256;          // two epilogue warpgroups, each owns half of the tile's columns
+constexpr int BAR_FREE = 5, BAR_STAGED = 7;   // named barriers (+ warpgroup): staging tile free / staged, 128 epilogue threads + the store warp
 // dynamic smem: ring + epilogue constants (bias 256 f32 + proj 4x256 f32 + proj bias) + barriers
 constexpr int EPI_CONST_BYTES = (256 + 4 * 256 + 4 + 128 * 4) * 4;   // bias, proj weights, proj bias, proj partials
 // HALO variant (3x3, W % 128 == 0): one TMA box {64 ch, 130 px, 3 rows} per channel block serves all 9 taps
@@ -93,8 +107,32 @@ struct Params {
     soccdpt_conv_t c;
 };
 
+// (N block, tile column, tile row, tile image) of tile = first + k * step, advanced WITHOUT a division per tile: the five
+// runtime divisions / modulos of the decomposition were ~1000 cycles of dependent integer code at the top of every epilogue
+// tile (tools/trace_conv.py) -- as long as a whole 32-column chunk of a narrow-K layer
+struct TileIter {
+    int nb, tw, th, tn, s_nb, s_tw, s_th, s_tn;
+    __device__ __forceinline__ void init(const Params &p, int first, int step) {
+        nb = first % p.n_blocks; int mt = first / p.n_blocks;
+        tw = mt % p.tiles_w; mt /= p.tiles_w;
+        th = mt % p.tiles_h; tn = mt / p.tiles_h;
+        s_nb = step % p.n_blocks; mt = step / p.n_blocks;
+        s_tw = mt % p.tiles_w; mt /= p.tiles_w;
+        s_th = mt % p.tiles_h; s_tn = mt / p.tiles_h;
+    }
+    __device__ __forceinline__ void next(const Params &p) {
+        nb += s_nb; int c = nb >= p.n_blocks ? 1 : 0; nb -= c ? p.n_blocks : 0;
+        tw += s_tw + c; c = tw >= p.tiles_w ? 1 : 0; tw -= c ? p.tiles_w : 0;
+        th += s_th + c; c = th >= p.tiles_h ? 1 : 0; th -= c ? p.tiles_h : 0;
+        tn += s_tn + c;
+    }
+};
+
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// producer / consumer named barriers (PTX ISA, bar.arrive + bar.sync): arriving threads do not wait
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -432,9 +470,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 mbar_wait(&a_full[0], 0);                    // resident weights of this CTA's N block have landed
                 tc_fence_after();
             }
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int mit = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++mit) {
+                if (lane == 0) CTRACE(mit, 0);
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
+                if (lane == 0) CTRACE(mit, 1);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
                 if (!HALO && p.nres) {
                     const uint32_t desc_hi = (uint32_t)(umma_desc(0) >> 32);
@@ -455,8 +496,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         umma_commit(&empty[stage]);
                         if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
                         b_lo += b_step;
+                        if (lane == 0 && kb == 0) CTRACE(mit, 2);
                     }
                     umma_commit(&acc_full[acc]);
+                    if (lane == 0) CTRACE(mit, 3);
                     if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
                     continue;
                 }
@@ -590,9 +633,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // narrow-K layers are epilogue-bound
         const bool alt_split = p.alt_split && !m2 && MODE != 2 && ((p.block_n >> 5) & 1) && (p.block_n & 31) == 0 && p.block_n > 32;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int nb = tile % p.n_blocks, mt = tile / p.n_blocks;
-            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+        int eit_count = 0;      // tiles this CTA's epilogue has started (trace builds)
+        const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);     // row -> pixel of the tile box
+        const float up_sh = c.up_src ? (float)(c.up_h - 1) / (float)(2 * c.up_h - 1) : 0.0f;
+        const float up_sw = c.up_src ? (float)(c.up_w - 1) / (float)(2 * c.up_w - 1) : 0.0f;
+        bool first_store = true;                   // the staging tile starts out free
+        TileIter ti;
+        ti.init(p, (int)blockIdx.x, (int)gridDim.x);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ti.next(p)) {
+            const int nb = ti.nb, tw = ti.tw, th = ti.th, tn = ti.tn;
             const int cout0 = nb * p.block_n;
             const int split = (alt_split && (it++ & 1)) ? c_split - 32 : c_split;
             const int col_begin = m2 || wg == 0 ? 0 : split, col_end = m2 ? p.block_n : (wg == 0 ? split : p.block_n);
@@ -608,8 +657,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 cached_nb = nb;
             }
-            // row -> pixel
-            const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
             const int h_tile = m2 ? th * 2 + wg : th * p.BH;
             const int wx = tw * p.BW + bw, hy = h_tile + bh, ni = tn * p.BN + bn;
             const bool valid = (row < m_valid) && (wx < p.Wo) && (hy < p.Ho) && (ni < c.N);
@@ -619,8 +666,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const bf16 *up00 = nullptr, *up01 = nullptr, *up10 = nullptr, *up11 = nullptr;
             float uw00 = 0.f, uw01 = 0.f, uw10 = 0.f, uw11 = 0.f;
             if (MODE == 1 && c.up_src && valid) {
-                const float fy = (float)(c.up_h - 1) / (float)(2 * c.up_h - 1) * (float)hy;
-                const float fx = (float)(c.up_w - 1) / (float)(2 * c.up_w - 1) * (float)wx;
+                const float fy = up_sh * (float)hy, fx = up_sw * (float)wx;
                 const int y0 = (int)fy, x0 = (int)fx, y1 = y0 + (y0 < c.up_h - 1 ? 1 : 0), x1 = x0 + (x0 < c.up_w - 1 ? 1 : 0);
                 const float ly = fy - (float)y0, lx = fx - (float)x0;
                 const bf16 *ub = static_cast<const bf16 *>(c.up_src) + (long long)ni * c.up_h * c.up_w * c.Cout + cout0;
@@ -631,16 +677,21 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 uw00 = (1.0f - ly) * (1.0f - lx); uw01 = (1.0f - ly) * lx; uw10 = ly * (1.0f - lx); uw11 = ly * lx;
             }
 
+            if (et == 0) CTRACE(eit_count, 8);
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
+            if (et == 0) CTRACE(eit_count, 9);
+            int cev = 10;
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + (m2 ? wg * 128 : 0));
             float proj[4] = {0.f, 0.f, 0.f, 0.f};
             int col = col_begin;
             // ---- 32-column steps
             for (; col + 32 <= col_end; col += 32) {
                 uint32_t raw[32];
+                if (et == 0 && cev < 26) CTRACE(eit_count, cev++);      // chunk start
                 tmem_ld32(t_row + (uint32_t)col, raw);
                 tmem_ld_wait();
+                if (et == 0 && cev < 26) CTRACE(eit_count, cev++);      // TMEM load done
                 float v[32];
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
@@ -655,10 +706,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     // and column steps are head aligned): L2-normalise from the fp32 accumulator, q also takes the logit scale
                     const int gc = cout0 + col;
                     if (gc < 64 * c.qk_heads) {
-                        float ss = 0.0f;
+                        // x / max(|x|, 1e-12) = x * rsqrt(max(|x|^2, 1e-24)); four partial sums instead of a 32-deep FMA chain
+                        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
-                        float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+                        for (int j = 0; j < 32; ++j) s4[j & 3] = fmaf(v[j], v[j], s4[j & 3]);
+                        float inv = rsqrtf(fmaxf((s4[0] + s4[1]) + (s4[2] + s4[3]), 1e-24f));
                         if (gc < 32 * c.qk_heads) inv *= c.qk_scale[gc >> 5];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] *= inv;
@@ -693,29 +745,27 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             fma_bf16<4>(v, reinterpret_cast<const uint4 *>(up11 + col), uw11);
                         }
                     }
+                    // staged stores: the bulk tensor store, its commit and the wait for it to have READ the staging tile cost the
+                    // issuing thread ~220 cycles each with the other 127 threads parked at the next barrier (tools/trace_conv.py);
+                    // warp 2 / 3 (store warp of warpgroup 0 / 1) does all three, this warpgroup only waits for "tile free"
+                    // (normally long passed) and announces "tile staged"
                     uint8_t *stage = s_stage + wg * STAGING_BYTES;
-                    const int bar_id = 3 + wg;                      // named barrier of this warpgroup (128 threads)
                     if (MODE == 0 || y) {
-                        if (row == 0) tma_store_wait_read();        // previous bulk store has finished reading the tile
-                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                        if (et == 0 && cev < 26) CTRACE(eit_count, cev++);      // math done
+                        if (!first_store) bar_sync(BAR_FREE + wg, 160);
+                        first_store = false;
+                        if (et == 0 && cev < 26) CTRACE(eit_count, cev++);      // staging tile free
                         stage_row32<false>(stage, row, v);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                        if (row == 0) {
-                            tma_store_4d(&map_y, stage, cout0 + col, tw * p.BW, h_tile, tn * p.BN);
-                            tma_store_commit();
-                        }
+                        bar_arrive(BAR_STAGED + wg, 160);
+                        if (et == 0 && cev < 26) CTRACE(eit_count, cev++);      // staged + proxy fence + arrive
                     }
                     if (MODE == 1 && y_relu) {
-                        if (row == 0) tma_store_wait_read();
-                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                        if (!first_store) bar_sync(BAR_FREE + wg, 160);
+                        first_store = false;
                         stage_row32<true>(stage, row, v);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                        if (row == 0) {
-                            tma_store_4d(&map_yr, stage, cout0 + col, tw * p.BW, h_tile, tn * p.BN);
-                            tma_store_commit();
-                        }
+                        bar_arrive(BAR_STAGED + wg, 160);
                     }
                 }
             }
@@ -755,6 +805,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             // accumulator fully read by this thread: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
+            if (et == 0) CTRACE(eit_count, 30);
+            ++eit_count;
             if (MODE == 2) {
                 // combine the two column halves: warpgroup 1 -> smem -> warpgroup 0 adds, finishes, stores
                 if (wg == 1) {
@@ -773,7 +825,41 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
-        if (row == 0) tma_store_wait_all();        // staged tiles must outlive the bulk stores reading them
+    } else if (MODE != 2) {
+        // ===================== store warps: warp 2 / 3 issue the bulk tensor stores of epilogue warpgroup 0 / 1 =====================
+        // (same tile / chunk sequence as the warpgroup; MODE 2 writes no staged output)
+        const int swg = warp - 2;
+        const bool m2 = HALO && p.m2;
+        const int c_split = (((p.block_n >> 5) + 1) >> 1) << 5;
+        const bool alt_split = p.alt_split && !m2 && ((p.block_n >> 5) & 1) && (p.block_n & 31) == 0 && p.block_n > 32;
+        const bool has_y = MODE == 0 || c.y != nullptr, has_yr = MODE == 1 && c.y_relu != nullptr;
+        uint8_t *stage = s_stage + swg * STAGING_BYTES;
+        int it = 0;
+        TileIter ti;
+        ti.init(p, (int)blockIdx.x, (int)gridDim.x);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ti.next(p)) {
+            const int split = (alt_split && (it++ & 1)) ? c_split - 32 : c_split;
+            const int col_begin = m2 || swg == 0 ? 0 : split, col_end = m2 ? p.block_n : (swg == 0 ? split : p.block_n);
+            const int cout0 = ti.nb * p.block_n, h_tile = m2 ? ti.th * 2 + swg : ti.th * p.BH;
+            const bool last_tile = tile + (int)gridDim.x >= p.total_tiles;
+            for (int col = col_begin; col + 32 <= col_end; col += 32) {
+                const bool last_chunk = last_tile && col + 64 > col_end;
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {
+                    if (which == 0 ? !has_y : !has_yr) continue;
+                    bar_sync(BAR_STAGED + swg, 160);                   // the warpgroup has staged (and proxy-fenced) the chunk
+                    if (lane == 0) {
+                        tma_store_4d(which == 0 ? &map_y : &map_yr, stage, cout0 + col, ti.tw * p.BW, h_tile, ti.tn * p.BN);
+                        tma_store_commit();
+                        tma_store_wait_read();                         // the tile may be overwritten
+                    }
+                    __syncwarp();
+                    const bool last = last_chunk && (which == 1 || !has_yr);
+                    if (!last) bar_arrive(BAR_FREE + swg, 160);      // nobody waits for the tile after the last store
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait_all();       // staged tiles must outlive the bulk stores reading them
     }
 
     tc_fence_before();
@@ -814,6 +900,14 @@ int pick_block_n(int cout, int step = 16) {   // step 32: N blocks made of whole
 }
 
 }  // namespace
+
+#ifdef SOCCDPT_CONV_TRACE
+extern "C" int soccdpt_conv_trace_read(unsigned long long *dst) {     // CT_TILES x CT_EVENTS stamps of the last launches (debug builds)
+    SOCCDPT_CUDA(cudaDeviceSynchronize());
+    SOCCDPT_CUDA(cudaMemcpyFromSymbol(dst, g_conv_trace, sizeof(unsigned long long) * CT_TILES * CT_EVENTS));
+    return 0;
+}
+#endif
 
 extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream) {
     int rc = soccdpt::validate_conv(c);

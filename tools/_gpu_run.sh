@@ -1,14 +1,10 @@
-mkdir -p gpurun_out/fin2
-timeout 400 python bench.py > gpurun_out/fin2/bench_tiny.json 2> gpurun_out/fin2/bench_tiny.err; echo "tiny rc=$?"
-timeout 400 python bench.py --model base_384 --no-cpu-baseline > gpurun_out/fin2/bench_base_384.json 2> gpurun_out/fin2/bench_base_384.err; echo "base rc=$?"
-timeout 400 python bench.py --model hybrid_384 --no-cpu-baseline > gpurun_out/fin2/bench_hybrid_384.json 2> gpurun_out/fin2/bench_hybrid_384.err; echo "hybrid rc=$?"
-K='conv_tcgen05|window_attention|swin_block_tail|layernorm|patch_embed|upsample|depth_tail|seg_finish|unproject|grid_expand|resize_tables|ln_res'
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"$K" -s 97 -c 110 --csv --log-file gpurun_out/fin2/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/fin2/ncu1.log 2>&1
-PYTHONPATH=. timeout 200 python tools/bench_models.py --version 1 --model dpt_swin2_tiny_256 --batch 64 > gpurun_out/fin2/v1.log 2>&1; grep "frames/s" gpurun_out/fin2/v1.log
-PYTHONPATH=. timeout 200 python tools/bench_latency.py > gpurun_out/fin2/latency.log 2>&1; tail -4 gpurun_out/fin2/latency.log
+mkdir -p gpurun_out/sw
+timeout 600 python -m pytest tests/test_gpu_conv_tcgen05.py tests/test_gpu_ops.py tests/test_gpu_network.py -x -q -m gpu 2>&1 | tail -6 > gpurun_out/sw/pytest.log; tail -4 gpurun_out/sw/pytest.log
+SOCCDPT_LIB=build/variants/trace/lib.so timeout 300 python tools/trace_conv.py > gpurun_out/sw/trace.log 2>&1
+grep -A5 "^==" gpurun_out/sw/trace.log | cut -c1-520
+timeout 300 python bench.py --steps 40 --warmup 8 --no-cpu-baseline > gpurun_out/sw/bench.json 2> gpurun_out/sw/bench.err
 python - <<'PY'
 import json
-for n in ("tiny","base_384","hybrid_384"):
-    d=json.loads(open(f"gpurun_out/fin2/bench_{n}.json").read().strip().splitlines()[-1])
-    print(n, round(d["value"]), round(d["ms_per_step"],3), 'e2e', round(d["e2e"]["value"]), d.get("model_frac_of_peak"), d["roofline"]["frac"], d["clocks"], d["kernels_ms_per_step"])
+d=json.loads(open("gpurun_out/sw/bench.json").read().strip().splitlines()[-1])
+print(round(d["value"]), round(d["ms_per_step"],3), d["kernels_ms_per_step"], d["clocks"]["sm_mhz"])
 PY

@@ -964,6 +964,14 @@ extern "C" int soccdpt_conv_fwd(const soccdpt_conv_t *c, soccdpt_stream_t stream
     p.tiles_h = p.m2 ? p.Ho / 2 : (p.Ho + p.BH - 1) / p.BH;
     p.tiles_n = (c->N + p.BN - 1) / p.BN;
     p.n_blocks = c->Cout / p.block_n;
+    // sub-wave layers (the 8x8 level of the decoder: 32 M tiles on 148 SMs, each a serial chain of K / 16 MMAs): narrower N blocks
+    // put more SMs on the same work -- the launch is latency-bound, not throughput-bound (SOCCDPT_CONV_NSPLIT=0 switches it off)
+    static const bool nsplit_enabled = !(getenv("SOCCDPT_CONV_NSPLIT") && getenv("SOCCDPT_CONV_NSPLIT")[0] == '0');
+    while (nsplit_enabled && !halo && c->proj_n == 0 && c->qk_heads == 0 && p.block_n >= 128 && p.block_n % 64 == 0 &&
+           2ll * p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks <= soccdpt::sm_count()) {
+        p.block_n /= 2;
+        p.n_blocks *= 2;
+    }
     const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
     SOCCDPT_REQUIRE(total < (1ll << 31), "conv: too many tiles");
     p.total_tiles = (int)total;

@@ -34,6 +34,19 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+// -DSOCCDPT_TAIL_TRACE (debug builds only, tools/trace_block_tail.py): CTA 0 logs SM-clock stamps of its hand-offs (one lane of the MMA
+// warp, of the first GELU warp and of the first LayerNorm warp) into a global buffer read back by soccdpt_block_tail_trace_read()
+#ifdef SOCCDPT_TAIL_TRACE
+constexpr int BT_EVENTS = 24, BT_IDS = 64;
+__device__ unsigned long long g_bt_trace[BT_EVENTS * BT_IDS];
+#define BTRACE(ev, id)                                                                                                   \
+    do {                                                                                                                 \
+        if (blockIdx.x == 0 && (id) < BT_IDS) g_bt_trace[(ev) * BT_IDS + (id)] = (unsigned long long)clock64();          \
+    } while (0)
+#else
+#define BTRACE(ev, id) do { } while (0)
+#endif
+
 namespace {
 
 using bf16 = __nv_bfloat16;
@@ -89,27 +102,41 @@ struct LnWarp {
     __device__ __forceinline__ long long row0_of(int k) const { return (long long)(tile0 + k * tile_step) * BM + sub * 32; }
     // requests the next block of the stream (beyond its end only the (empty) group is committed); ring slot = request order
     int fk, fb, fslot;              // fetch cursor: (tile k, block b) and the ring slot it goes to
-    __device__ __forceinline__ void fetch_next() {
+    // Per-lane addressing of a tile, set once per tile (the per-row 64-bit products and bound checks of the first version made a
+    // 32-column block ~700 instructions of one latency-bound warp: tools/trace_block_tail.py): lane = (row rr + 4 i, 16-byte chunk ch);
+    // element offset of (row rr, chunk ch) from the tile's first row, the step of 4 rows, and the number of valid rows - rr.
+    int lane_off, rstep;            // rr * C + ch * 4, 4 * C
+    const float *fsrc;              // fetch cursor: master + row0_of(fk) * C + lane_off
+    int frows;                      // valid rows of the fetch tile minus rr (row rr + 4 i is valid iff 4 i < frows)
+    __device__ __forceinline__ void set_fetch_tile() {
         if (fk < n_tiles) {
             const long long r0 = row0_of(fk);
-            const int rr = lane >> 3, ch = lane & 7;
+            fsrc = a->master + r0 * a->C + lane_off;
+            const long long left = a->M - r0;
+            frows = (int)(left < 32 ? left : 32) - (lane >> 3);
+        }
+    }
+    __device__ __forceinline__ void fetch_next() {
+        if (fk < n_tiles) {
             float *dst = ring + fslot * 1024 + lane * 4;
-            const float *srcp = a->master + r0 * a->C + fb * 32 + ch * 4;
+            const float *srcp = fsrc + fb * 32;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int rl = i * 4 + rr;
-                if (r0 + rl < a->M) cp_async16(dst + i * 128, srcp + (long long)rl * a->C);
+                if (4 * i < frows) cp_async16(dst + i * 128, srcp);
+                srcp += rstep;
             }
         }
         cp_async_commit();
-        if (++fb == nb) { fb = 0; ++fk; }
+        if (++fb == nb) { fb = 0; ++fk; set_fetch_tile(); }
         if (++fslot == LN_RING) fslot = 0;
     }
     // block q of the stream: TMEM columns [c, c + 32) of this warp's rows at taddr
-    __device__ __forceinline__ void block(int slot, uint32_t taddr, int c, float rstd, float nmr, long long r0) const {
+    __device__ __forceinline__ void block(int slot, uint32_t taddr, int c, float rstd, float nmr, float *mrow, bf16 *yrow, int rows, int tk = -1) const {
         uint32_t raw[32];
+        if (tk >= 0) BTRACE(14, tk);
         tmem_ld32_nowait(taddr + (uint32_t)c, raw);
         tmem_ld_wait();
+        if (tk >= 0) BTRACE(15, tk);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 bb = *reinterpret_cast<const float4 *>(b2 + c + j * 4);
@@ -122,29 +149,41 @@ struct LnWarp {
             v.w = fmaf((__uint_as_float(raw[j * 4 + 3]) + bb.w) * rstd + nmr, gg.w, ee.w);
             *reinterpret_cast<float4 *>(scr + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
         }
+        if (tk >= 0) BTRACE(16, tk);
         cp_async_wait<LN_RING - 1>();          // this thread's copies of block q have landed (it reads back only its own)
         __syncwarp();
+        if (tk >= 0) BTRACE(17, tk);
         const int rr = lane >> 3, ch = lane & 7;
         const float *src = ring + slot * 1024 + lane * 4;
-        const int C = a->C;
+        float *mp = mrow + c;               // (row rr, chunk ch) of the block; + rstep per 4 rows
+        bf16 *yp = yrow + c;
+        // loads of four rows first, then their (predicated) stores: with the row-bound test around the whole body every row was its
+        // own branch region and paid the shared-memory latency serially (~120 cycles per row: tools/trace_block_tail.py)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int rl = i * 4 + rr;
-            const float4 v = *reinterpret_cast<const float4 *>(scr + rl * 32 + ((ch ^ (rl & 7)) << 2));
-            const long long r = r0 + rl;
-            if (r < a->M) {
-                const float4 m = *reinterpret_cast<const float4 *>(src + i * 128);
-                float4 o;
-                o.x = m.x + v.x; o.y = m.y + v.y; o.z = m.z + v.z; o.w = m.w + v.w;
-                const long long off = r * C + c + ch * 4;
-                *reinterpret_cast<float4 *>(a->master + off) = o;
+        for (int h = 0; h < 2; ++h) {
+            float4 o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rl = (h * 4 + i) * 4 + rr;
+                const float4 v = *reinterpret_cast<const float4 *>(scr + rl * 32 + ((ch ^ (rl & 7)) << 2));
+                const float4 m = *reinterpret_cast<const float4 *>(src + (h * 4 + i) * 128);      // stale ring contents for rows past the end
+                o[i].x = m.x + v.x; o[i].y = m.y + v.y; o[i].z = m.z + v.z; o[i].w = m.w + v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
                 uint2 u;
-                u.x = pack_bf16x2(o.x, o.y);
-                u.y = pack_bf16x2(o.z, o.w);
-                *reinterpret_cast<uint2 *>(static_cast<bf16 *>(a->y) + off) = u;
+                u.x = pack_bf16x2(o[i].x, o[i].y);
+                u.y = pack_bf16x2(o[i].z, o[i].w);
+                if (4 * (h * 4 + i) < rows) {
+                    *reinterpret_cast<float4 *>(mp) = o[i];
+                    *reinterpret_cast<uint2 *>(yp) = u;
+                }
+                mp += rstep;
+                yp += rstep;
             }
         }
         __syncwarp();
+        if (tk >= 0) BTRACE(18, tk);
     }
     // one tile: statistics in one TMEM pass (sums shifted by the row's first value), then the blocks
     int cslot;                      // ring slot of the next block to consume
@@ -175,12 +214,20 @@ struct LnWarp {
         const float rstd = rsqrtf(var + a->eps);
         const float nmr = -(shift + ms) * rstd;
         const long long r0 = row0_of(k);
+        float *mrow = a->master + r0 * C + lane_off;
+        bf16 *yrow = static_cast<bf16 *>(a->y) + r0 * C + lane_off;
+        const long long left = a->M - r0;
+        const int rows = (int)(left < 32 ? left : 32) - (lane >> 3);
+        if (trace_lane) BTRACE(12, k);
         for (int b = 0; b < nb; ++b) {
-            block(cslot, d2, b * 32, rstd, nmr, r0);
+            block(cslot, d2, b * 32, rstd, nmr, mrow, yrow, rows, (trace_lane && b == 1) ? k : -1);
             if (++cslot == LN_RING) cslot = 0;
             fetch_next();                                          // refill the ring slot just consumed
+            if (trace_lane && b == 1) BTRACE(19, k);
         }
+        if (trace_lane) BTRACE(13, k);
     }
+    bool trace_lane = false;
 };
 
 template <bool MLP, bool RES>
@@ -355,8 +402,10 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                 // fc1 of hidden chunk j of tile iteration it -> D1[g & 1] (g = global chunk index)
                 auto fc1 = [&](int g, int it, int j) {
                     if (j == 0) {
+                        if (lane == 0) BTRACE(6, it);
                         mbar_wait(&bars->a_full, (uint32_t)(it & 1));
                         tc_fence_after();
+                        if (lane == 0) BTRACE(7, it);
                     }
                     const uint32_t d1 = tmem + (uint32_t)((g & 1) * HC);
                     uint32_t a_lo = a_lo0, acc = 0u;
@@ -403,11 +452,15 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                 auto fc2 = [&](int g, int it, int j) {
                     const int db2 = d2_two ? (it & 1) : 0;
                     if (j == 0) {
+                        if (lane == 0) BTRACE(8, it);
                         mbar_wait(&bars->d2_empty[db2], (uint32_t)((d2_two ? it >> 1 : it) & 1) ^ 1u);
                         tc_fence_after();
+                        if (lane == 0) BTRACE(9, it);
                     }
+                    if (lane == 0) BTRACE(4, g);
                     mbar_wait(&bars->h_full[g & 1], (uint32_t)((g >> 1) & 1));
                     tc_fence_after();
+                    if (lane == 0) BTRACE(5, g);
                     const uint32_t d2 = tmem + 256u + (uint32_t)(db2 * C);
                     const uint32_t h = tmem + (uint32_t)((g & 1) * HC);
                     uint32_t acc = j != 0 ? 1u : 0u;
@@ -522,14 +575,17 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
             int g = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 for (int j = 0; j < p.nch; ++j, ++g) {
+                    if (threadIdx.x == 128) BTRACE(0, g);
                     mbar_wait(&bars->d1_full[g & 1], (uint32_t)((g >> 1) & 1));
                     tc_fence_after();
+                    if (threadIdx.x == 128) BTRACE(1, g);
                     const uint32_t base = t_lane + (uint32_t)((g & 1) * HC + grp * 64);
                     const float4 *bb = reinterpret_cast<const float4 *>(s_b1 + j * HC + grp * 64);
                     uint32_t r0[32], r1[32];
                     tmem_ld32_nowait(base, r0);
                     tmem_ld32_nowait(base + 32, r1);
                     tmem_ld_wait();
+                    if (threadIdx.x == 128) BTRACE(2, g);
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {       // 4 values per step: one broadcast LDS.128 of the bias
@@ -549,6 +605,7 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(&bars->h_full[g & 1]);
+                    if (threadIdx.x == 128) BTRACE(3, g);
                 }
             }
         } else if (MLP ? grp == 2 : (grp < 2 && (p.d2_bufs == 2 || grp == 0))) {
@@ -569,6 +626,10 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
             w.tile_step = every ? (int)gridDim.x : 2 * (int)gridDim.x;
             w.n_tiles = every ? my_tiles : (my_tiles - grp + 1) / 2;
             w.fk = 0; w.fb = 0; w.fslot = 0; w.cslot = 0;
+            w.lane_off = (lane >> 3) * C + (lane & 7) * 4;
+            w.rstep = 4 * C;
+            w.set_fetch_tile();
+            w.trace_lane = lane == 0 && ln_idx == 0;
 #pragma unroll
             for (int q = 0; q < LN_RING; ++q) w.fetch_next();
             for (int k = 0; k < w.n_tiles; ++k) {
@@ -577,8 +638,10 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
                 const bool d2_two = p.d2_bufs == 2;
                 const int db2 = every ? (d2_two ? (it & 1) : 0) : grp;
                 const uint32_t d2_par = every ? (uint32_t)((d2_two ? it >> 1 : it) & 1) : (uint32_t)(k & 1);
+                if (w.trace_lane) BTRACE(10, k);
                 mbar_wait(&bars->d2_full[db2], d2_par);
                 tc_fence_after();
+                if (w.trace_lane) BTRACE(11, k);
                 w.tile(k, t_lane + (MLP ? 256u + (uint32_t)(db2 * C) : (uint32_t)(db2 * 256)));
                 tc_fence_before();
                 mbar_arrive(&bars->d2_empty[db2]);
@@ -596,6 +659,14 @@ swin_block_tail_kernel(const __grid_constant__ CUtensorMap mx64, const __grid_co
 }
 
 }  // namespace
+
+#ifdef SOCCDPT_TAIL_TRACE
+extern "C" int soccdpt_block_tail_trace_read(unsigned long long *dst) {     // BT_EVENTS x BT_IDS stamps of the last launch (debug builds)
+    SOCCDPT_CUDA(cudaDeviceSynchronize());
+    SOCCDPT_CUDA(cudaMemcpyFromSymbol(dst, g_bt_trace, sizeof(unsigned long long) * BT_EVENTS * BT_IDS));
+    return 0;
+}
+#endif
 
 extern "C" int soccdpt_swin_block_tail_fwd(const soccdpt_block_tail_t *a, soccdpt_stream_t stream) {
     SOCCDPT_REQUIRE(a && a->x && a->w2 && a->b2 && a->gamma && a->beta && a->master && a->y, "block_tail: NULL pointer");

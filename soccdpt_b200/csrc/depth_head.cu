@@ -25,12 +25,17 @@ constexpr int VP = VC + 4;      // smem pitch in floats (400 B): conflict-free f
 #define SOCCDPT_DT_KP 32
 #endif
 #ifndef SOCCDPT_DT_NRING
-#define SOCCDPT_DT_NRING 6
+#define SOCCDPT_DT_NRING 4
+#endif
+#ifndef SOCCDPT_DT_CTAS
+#define SOCCDPT_DT_CTAS 3
 #endif
 constexpr int SW = 16;          // low-resolution columns per CTA (32 output columns)
 constexpr int NC = SW + 2;      // + one halo column on each side
 constexpr int KP = SOCCDPT_DT_KP;          // low-resolution rows (= output row PAIRS) per CTA
-constexpr int NRING = SOCCDPT_DT_NRING;    // T rows resident in shared memory: three in use, the rest in flight
+constexpr int NRING = SOCCDPT_DT_NRING;    // T rows resident in shared memory: three in use, the rest in flight.  Four rows (70 KB with V) let
+                                           // THREE CTAs share an SM: 221 us against 247 us for six rows / two CTAs (one row in flight per CTA is
+                                           // enough when two other CTAs cover its wait)
 constexpr int ROWB = NC * TC * 2;                    // bytes of one staged T row segment (10368)
 constexpr int VROW = NC * VP;                        // floats of one V row
 constexpr int SMEM_BYTES = NRING * ROWB + 2 * 2 * VROW * 4 + NRING * 8;
@@ -64,13 +69,13 @@ __device__ __forceinline__ void lerp4(float (&acc)[4], const float4 &a, const fl
 // for t = 2j and (j, j+1) for t = 2j+1.  The output row pair (2k, 2k+1) therefore touches the tap rows 2k-1 .. 2k+2 and only
 // the source rows k-1, k, k+1 -- and the same holds for columns -- so the kernel works on 2x2 output blocks:
 //   * a CTA owns SW source columns (+ halo) and MARCHES down KP source rows.  Every T row segment is fetched ONCE, by one
-//     cp.async.bulk into a ring of NRING rows (three rows in use, the rest in flight), completion on one mbarrier per slot.
+//     cp.async.bulk into a ring of NRING rows (three rows in use, one in flight), completion on one mbarrier per slot.
 //     The first version (one CTA per output row, every row re-reading its six source row slices from L2: 2.4 GB of L2 reads
 //     per 64-frame step for 0.6 GB of T) was L2-bound at 0.33 ms;
 //   * pass A: a thread owns 8 (dx, c) values of one column: 7 shared-memory loads (instead of 12) feed both rows of the pair,
 //     packed fma.f32x2;   pass B: a thread owns 4 channels of one 2-pixel block of one row: 7 loads instead of 12, then a
 //     three-step shuffle reduction over the 8 channel groups.  V is double-buffered: one __syncthreads per row pair.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, SOCCDPT_DT_CTAS)
 depth_tail_kernel(const bf16 *__restrict__ T, const float *__restrict__ b2, const float *__restrict__ pw,
                   const float *__restrict__ pb, float *__restrict__ out, int N, int h, int w, int segs, int strips) {
     extern __shared__ __align__(128) uint8_t smem[];

@@ -1,4 +1,6 @@
-mkdir -p gpurun_out/cap
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:conv_tcgen05 --launch-skip 52 -c 1 -o gpurun_out/cap/s0_qkv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/cap/ncu_a.log 2>&1
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:conv_tcgen05 --launch-skip 101 -c 1 -o gpurun_out/cap/depth_conv0 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/cap/ncu_b.log 2>&1
-ls -la gpurun_out/cap
+for v in default dt_r4_c3 dt_r5_c2 dt_r4_c2; do
+  if [ $v = default ]; then unset SOCCDPT_LIB; else export SOCCDPT_LIB=build/variants/$v/lib.so; fi
+  echo "== $v"; timeout 200 python tools/bench_depth_tail.py 2>&1 | tail -2
+done
+unset SOCCDPT_LIB
+SOCCDPT_LIB=build/variants/dt_r4_c3/lib.so timeout 200 python -m pytest tests/test_gpu_ops.py -k depth -x -q -m gpu 2>&1 | tail -2
